@@ -1,0 +1,319 @@
+// C ABI of libeftb200: plan management, stage entry points, the fused per-batch pipeline.
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include "common.cuh"
+
+static thread_local char g_error[512] = "";
+
+void eftb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+template <typename T>
+int upload(T** dst, const T* src, size_t n) {
+  *dst = nullptr;
+  if (n == 0 || !src) return EFTB_OK;
+  EFTB_CUDA_CHECK(cudaMalloc((void**)dst, n * sizeof(T)));
+  EFTB_CUDA_CHECK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return EFTB_OK;
+}
+
+struct Sizes {
+  size_t u, F, D, P22, Cs, T, Cr, scal, out;
+};
+
+Sizes sizes(const eftb_plan* p, int Bp) {
+  const eftb_config& c = p->cfg;
+  Sizes z;
+  z.u = (size_t)p->K * Bp;
+  z.F = (size_t)c.front_rows * Bp;
+  z.D = (size_t)EFTB_NCH * (c.Nmax + 1) * 2 * Bp;
+  z.P22 = (size_t)EFTB_N22 * c.Nk * Bp;
+  z.Cs = (size_t)c.Nl * EFTB_NCH * c.Ns * Bp;
+  z.T = (size_t)c.Nl * c.Nk * c.nterm * Bp;
+  z.Cr = (size_t)c.Nl * (14 + (c.with_nnlo ? 1 : 0)) * c.Ns * Bp;
+  z.scal = (size_t)3 * Bp;
+  z.out = c.has_project ? (size_t)c.nout * c.nterm * Bp : 0;
+  return z;
+}
+
+__global__ void probe_fp64_kernel(double* sink, int iters) {
+  // 16 independent DFMA chains per thread
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  const double m = 1.0 + 1e-12, c = 1e-13;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678) sink[0] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eftb_abi_version(void) { return EFTB_ABI_VERSION; }
+const char* eftb_last_error(void) { return g_error; }
+int eftb_padded_batch(int B) { return B < 1 ? 0 : eftb_round_up(B, 32); }
+
+int eftb_probe_fp64(int iters, double* tflops, void* stream) {
+  if (!tflops || iters < 1) { eftb_set_error("eftb_probe_fp64: bad argument"); return EFTB_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  EFTB_CUDA_CHECK(cudaGetDevice(&dev));
+  EFTB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* sink = nullptr;
+  EFTB_CUDA_CHECK(cudaMalloc(&sink, sizeof(double)));
+  cudaEvent_t e0, e1;
+  EFTB_CUDA_CHECK(cudaEventCreate(&e0));
+  EFTB_CUDA_CHECK(cudaEventCreate(&e1));
+  const int blocks = sms * 4, threads = 256;
+  probe_fp64_kernel<<<blocks, threads, 0, s>>>(sink, iters / 8 + 1);  // warm-up
+  EFTB_CUDA_CHECK(cudaEventRecord(e0, s));
+  probe_fp64_kernel<<<blocks, threads, 0, s>>>(sink, iters);
+  EFTB_CUDA_CHECK(cudaEventRecord(e1, s));
+  EFTB_CUDA_CHECK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  EFTB_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  *tflops = 2.0 * 16.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return EFTB_OK;
+}
+
+int eftb_plan_create(const eftb_config* cfg, const eftb_constants* h, eftb_plan** out) {
+  if (!cfg || !h || !out) { eftb_set_error("eftb_plan_create: NULL argument"); return EFTB_ERR_ARG; }
+  const eftb_config& c = *cfg;
+  if (c.Nl < 2 || c.Nl > 3 || c.Nk < 8 || c.Ns < 4 || c.Nmax < 8 || (c.Nmax & 1) || c.nterm < 24 || c.nin < 4) {
+    eftb_set_error("eftb_plan_create: unsupported sizes Nl=%d Nk=%d Ns=%d Nmax=%d nterm=%d", c.Nl, c.Nk, c.Ns, c.Nmax, c.nterm);
+    return EFTB_ERR_ARG;
+  }
+  if (c.nterm != 24 + (c.with_nnlo ? 3 : 0)) { eftb_set_error("eftb_plan_create: nterm inconsistent with with_nnlo"); return EFTB_ERR_ARG; }
+  eftb_plan* p = new eftb_plan();
+  p->cfg = c;
+  p->K = c.nin + c.ntail + c.ntailx;
+  int rc = 0;
+  rc |= upload(&p->k, h->k, c.Nk);
+  rc |= upload(&p->l11, h->l11, (size_t)c.Nl * 3);
+  rc |= upload(&p->lct, h->lct, (size_t)c.Nl * 6);
+  rc |= upload(&p->lctnnlo, h->lctnnlo, (size_t)c.Nl * 3);
+  rc |= upload(&p->l22, h->l22, (size_t)c.Nl * EFTB_N22);
+  rc |= upload(&p->l13, h->l13, (size_t)c.Nl * EFTB_N13);
+  rc |= upload(&p->lr, h->lr, c.ntail);
+  rc |= upload(&p->lrx, h->lrx, c.ntailx);
+  rc |= gemm_upload(h->Wf, 1, c.front_rows, p->K, &p->Wf);
+  rc |= upload(&p->pair_table, reinterpret_cast<const double2*>(h->pair_table), (size_t)c.npair * EFTB_NCH);
+  rc |= upload(&p->pair_offsets, h->pair_offsets, (size_t)c.Nmax + 2);
+  rc |= gemm_upload(h->Ak, 1, c.Nk, 2 * (c.Nmax + 1), &p->Ak);
+  rc |= gemm_upload(h->As, c.Nl, c.Ns, 2 * (c.Nmax + 1), &p->As);
+  if (c.has_resum) {
+    rc |= upload(&p->R, h->R, (size_t)c.Na * c.Nkr * c.Ns);
+    rc |= upload(&p->q, h->q, (size_t)2 * c.Nl * c.Nl * 2 * c.NIR * c.Na * c.qdeg);
+    rc |= upload(&p->kr2, h->kr2, c.Nkr);
+  }
+  if (c.has_ap) {
+    rc |= gemm_upload(h->Cinv, 1, c.Nk, c.Nk, &p->Cinv);
+    rc |= upload(&p->knot_lo, h->knot_lo, c.nint);
+    rc |= upload(&p->basis, h->basis, (size_t)c.nint * 16);
+    rc |= upload(&p->mu, h->mu, c.nmu);
+    rc |= upload(&p->wl, h->wl, (size_t)c.Nl * c.nmu);
+  }
+  int nl_out = c.Nl, nk_out = c.Nk;
+  if (c.has_project) {
+    rc |= gemm_upload(h->project, 1, c.nout, c.Nl * c.Nk, &p->project);
+    nl_out = c.nl_out;
+    nk_out = c.nl_out > 0 ? c.nout / c.nl_out : 0;
+    if (nl_out < 1 || nl_out * nk_out != c.nout) { eftb_set_error("eftb_plan_create: nout != nl_out*nk_out"); rc = EFTB_ERR_ARG; }
+  }
+  if (!rc) {
+    // point-major export order [l][term][k]  <-  batch-minor row (l*nk + k)*nterm + term
+    std::vector<int32_t> perm((size_t)nl_out * c.nterm * nk_out);
+    for (int l = 0; l < nl_out; ++l)
+      for (int i = 0; i < c.nterm; ++i)
+        for (int k = 0; k < nk_out; ++k) perm[((size_t)l * c.nterm + i) * nk_out + k] = (l * nk_out + k) * c.nterm + i;
+    p->perm_rows = (int)perm.size();
+    rc |= upload(&p->perm_out, perm.data(), perm.size());
+  }
+  if (rc) { eftb_plan_destroy(p); return rc < 0 ? rc : EFTB_ERR_CUDA; }
+  *out = p;
+  return EFTB_OK;
+}
+
+void eftb_plan_destroy(eftb_plan* p) {
+  if (!p) return;
+  void* ptrs[] = {p->k, p->l11, p->lct, p->lctnnlo, p->l22, p->l13, p->lr, p->lrx, p->pair_table, p->pair_offsets,
+                  p->R, p->q, p->kr2, p->knot_lo, p->basis, p->mu, p->wl, p->perm_out};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  gemm_free(&p->Wf); gemm_free(&p->Ak); gemm_free(&p->As); gemm_free(&p->Cinv); gemm_free(&p->project);
+  delete p;
+}
+
+size_t eftb_workspace_bytes(const eftb_plan* p, int B) {
+  if (!p || B < 1) return 0;
+  Sizes z = sizes(p, eftb_padded_batch(B));
+  // u | F | D (later reused for the spline coefficients and the AP output) | P22 | Cs | T | Cr | f,DA,H | out
+  size_t dreg = z.D > 2 * z.T ? z.D : 2 * z.T;
+  return (z.u + z.F + dreg + z.P22 + z.Cs + z.T + z.Cr + z.scal + z.out) * sizeof(double);
+}
+
+int eftb_to_batch_minor(const double* in, int B, int R, double* out, void* stream) {
+  if (!in || !out || B < 1 || R < 1) { eftb_set_error("eftb_to_batch_minor: bad argument"); return EFTB_ERR_ARG; }
+  return launch_to_batch_minor(in, B, eftb_padded_batch(B), R, out, (cudaStream_t)stream);
+}
+
+int eftb_to_point_major(const double* in, int B, int R, const int32_t* perm, double* out, void* stream) {
+  if (!in || !out || B < 1 || R < 1) { eftb_set_error("eftb_to_point_major: bad argument"); return EFTB_ERR_ARG; }
+  return launch_to_point_major(in, B, eftb_padded_batch(B), R, perm, out, (cudaStream_t)stream);
+}
+
+#define EFTB_NEED(cond, what)                                   \
+  if (!(cond)) {                                                \
+    eftb_set_error("%s: %s", __func__, what);                   \
+    return EFTB_ERR_ARG;                                        \
+  }
+
+int eftb_front(const eftb_plan* p, int B, const double* plin, double* u, double* F, void* stream) {
+  EFTB_NEED(p && plin && u && F && B >= 1, "NULL/invalid argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Bp = eftb_padded_batch(B);
+  int rc = launch_front_prepare(p, B, Bp, plin, u, s);
+  if (rc) return rc;
+  return gemm_run(p->Wf, u, F, Bp, 1, 1, 0, 0, 0, s);
+}
+
+int eftb_antidiag(const eftb_plan* p, int B, const double* F, double* D, void* stream) {
+  EFTB_NEED(p && F && D && B >= 1, "NULL/invalid argument");
+  return launch_antidiag(p, eftb_padded_batch(B), F, D, (cudaStream_t)stream);
+}
+
+int eftb_spectral(const eftb_plan* p, int B, const double* D, double* P22, double* Cs, void* stream) {
+  EFTB_NEED(p && D && P22 && Cs && B >= 1, "NULL/invalid argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const eftb_config& c = p->cfg;
+  const int Bp = eftb_padded_batch(B);
+  const size_t dch = (size_t)(c.Nmax + 1) * 2 * Bp;
+  int rc = gemm_run(p->Ak, D, P22, Bp, EFTB_N22, EFTB_N22, dch, 0, (size_t)c.Nk * Bp, s);
+  if (rc) return rc;
+  return gemm_run(p->As, D, Cs, Bp, c.Nl * EFTB_NCH, EFTB_NCH, dch, 0, (size_t)c.Ns * Bp, s);
+}
+
+int eftb_group(const eftb_plan* p, int B, const double* F, const double* P22, const double* Cs, const double* f, double* T,
+               double* Cr, void* stream) {
+  EFTB_NEED(p && F && P22 && Cs && f && T && Cr && B >= 1, "NULL/invalid argument");
+  return launch_group(p, eftb_padded_batch(B), F, P22, Cs, f, T, Cr, (cudaStream_t)stream);
+}
+
+int eftb_resum(const eftb_plan* p, int B, const double* F, const double* Cr, const double* f, double* T, void* stream) {
+  EFTB_NEED(p && F && Cr && f && T && B >= 1, "NULL/invalid argument");
+  if (!p->cfg.has_resum) { eftb_set_error("eftb_resum: plan built without IR resummation"); return EFTB_ERR_NOT_BUILT; }
+  return launch_resum(p, B, eftb_padded_batch(B), F, Cr, f, T, (cudaStream_t)stream);
+}
+
+int eftb_ap(const eftb_plan* p, int B, const double* Tin, const double* DA, const double* H, double* coef, double* Tout,
+            void* stream) {
+  EFTB_NEED(p && Tin && DA && H && coef && Tout && B >= 1 && Tin != Tout, "NULL/invalid argument");
+  if (!p->cfg.has_ap) { eftb_set_error("eftb_ap: plan built without AP"); return EFTB_ERR_NOT_BUILT; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const eftb_config& c = p->cfg;
+  const int Bp = eftb_padded_batch(B);
+  const size_t per_l = (size_t)c.Nk * c.nterm * Bp;
+  // B-spline coefficients of every term row: coef[l] = Cinv @ T[l]  (N = nterm*Bp columns)
+  int rc = gemm_run(p->Cinv, Tin, coef, c.nterm * Bp, c.Nl, c.Nl, per_l, 0, per_l, s);
+  if (rc) return rc;
+  if (Bp > B) {  // pad lanes are not processed by the per-cosmology kernel: keep them finite
+    EFTB_CUDA_CHECK(cudaMemcpyAsync(Tout, Tin, (size_t)c.Nl * per_l * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  return launch_ap(p, B, Bp, coef, Tin, DA, H, Tout, s);
+}
+
+int eftb_project(const eftb_plan* p, int B, const double* T, double* out, void* stream) {
+  EFTB_NEED(p && T && out && B >= 1, "NULL/invalid argument");
+  if (!p->cfg.has_project) { eftb_set_error("eftb_project: plan built without projection"); return EFTB_ERR_NOT_BUILT; }
+  const int Bp = eftb_padded_batch(B);
+  return gemm_run(p->project, T, out, p->cfg.nterm * Bp, 1, 1, 0, 0, 0, (cudaStream_t)stream);
+}
+
+int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double* f, const double* DA, const double* H,
+                    double* terms_bm, double* terms_pm, void* workspace, size_t workspace_bytes, void* stream) {
+  EFTB_NEED(p && plin && f && workspace && B >= 1, "NULL/invalid argument");
+  const eftb_config& c = p->cfg;
+  EFTB_NEED(!c.has_ap || (DA && H), "plan has AP but DA/H missing");
+  if (workspace_bytes < eftb_workspace_bytes(p, B)) { eftb_set_error("eftb_eval_terms: workspace too small"); return EFTB_ERR_WORKSPACE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Bp = eftb_padded_batch(B);
+  Sizes z = sizes(p, Bp);
+  double* w = (double*)workspace;
+  double* u = w;            w += z.u;
+  double* F = w;            w += z.F;
+  double* D = w;            w += (z.D > 2 * z.T ? z.D : 2 * z.T);
+  double* P22 = w;          w += z.P22;
+  double* Cs = w;           w += z.Cs;
+  double* T = w;            w += z.T;
+  double* Cr = w;           w += z.Cr;
+  double* scal = w;         w += z.scal;
+  double* out = w;
+  int rc;
+  if ((rc = eftb_front(p, B, plin, u, F, stream))) return rc;
+  if ((rc = launch_to_batch_minor(f, B, Bp, 1, scal, s))) return rc;
+  if (c.has_ap) {
+    if ((rc = launch_to_batch_minor(DA, B, Bp, 1, scal + Bp, s))) return rc;
+    if ((rc = launch_to_batch_minor(H, B, Bp, 1, scal + 2 * (size_t)Bp, s))) return rc;
+  }
+  if ((rc = launch_antidiag(p, Bp, F, D, s))) return rc;
+  if ((rc = eftb_spectral(p, B, D, P22, Cs, stream))) return rc;
+  if ((rc = launch_group(p, Bp, F, P22, Cs, scal, T, Cr, s))) return rc;
+  if (c.has_resum && (rc = launch_resum(p, B, Bp, F, Cr, scal, T, s))) return rc;
+  double* cur = T;
+  if (c.has_ap) {
+    double* coef = D;
+    double* T2 = D + z.T;
+    if ((rc = eftb_ap(p, B, T, scal + Bp, scal + 2 * (size_t)Bp, coef, T2, stream))) return rc;
+    cur = T2;
+  }
+  if (c.has_project) {
+    if ((rc = eftb_project(p, B, cur, out, stream))) return rc;
+    cur = out;
+  }
+  const size_t nfinal = c.has_project ? z.out : z.T;
+  if (terms_bm) EFTB_CUDA_CHECK(cudaMemcpyAsync(terms_bm, cur, nfinal * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (terms_pm && (rc = launch_to_point_major(cur, B, Bp, p->perm_rows, p->perm_out, terms_pm, s))) return rc;
+  return EFTB_OK;
+}
+
+struct eftb_operator {
+  GemmMatrix A;
+};
+
+int eftb_operator_create(int M, int K, const double* host, eftb_operator** out) {
+  if (M < 1 || K < 1 || !host || !out) { eftb_set_error("eftb_operator_create: bad argument"); return EFTB_ERR_ARG; }
+  eftb_operator* op = new eftb_operator();
+  int rc = gemm_upload(host, 1, M, K, &op->A);
+  if (rc) { delete op; return rc; }
+  *out = op;
+  return EFTB_OK;
+}
+
+void eftb_operator_destroy(eftb_operator* op) {
+  if (!op) return;
+  gemm_free(&op->A);
+  delete op;
+}
+
+int eftb_operator_apply(const eftb_operator* op, const double* X, double* C, int N, void* stream) {
+  if (!op || !X || !C || N < 32 || N % 32) { eftb_set_error("eftb_operator_apply: bad argument (N must be a multiple of 32)"); return EFTB_ERR_ARG; }
+  return gemm_run(op->A, X, C, N, 1, 1, 0, 0, 0, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Shared declarations of libeftb200 (sm_100a).  Internal header - the public ABI is include/eftb200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/eftb200.h"
+
+#define EFTB_NCH 38
+#define EFTB_N22 28
+#define EFTB_N13 10
+
+void eftb_set_error(const char* fmt, ...);
+
+#define EFTB_CUDA_CHECK(call)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      eftb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return EFTB_ERR_CUDA;                                                                \
+    }                                                                                      \
+  } while (0)
+
+#define EFTB_LAUNCH_CHECK()                                                                \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess) {                                                               \
+      eftb_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e));    \
+      return EFTB_ERR_CUDA;                                                                \
+    }                                                                                      \
+  } while (0)
+
+static inline int eftb_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- fixed-operator GEMM:  C[M][N] = A[M][K] X[K][N], A zero-padded to [Mp][Kp] on upload -------
+struct GemmMatrix {       // device copy of a fixed operator, padded for the kernel's tiles
+  double* d = nullptr;    // [nbatch][Mp][Kp]
+  int M = 0, K = 0, Mp = 0, Kp = 0, MT = 0, nbatch = 0;
+};
+int gemm_upload(const double* host, int nbatch, int M, int K, GemmMatrix* out);
+void gemm_free(GemmMatrix* m);
+// z-batch: zb in [0, nz): A matrix index = zb / zdiv (if A has >1 batch), X offset = (zb % zdiv)*xs + (zb / zdiv)*xs2,
+// C offset = zb * cs
+int gemm_run(const GemmMatrix& A, const double* X, double* C, int N, int nz, int zdiv, size_t xs, size_t xs2,
+             size_t cs, cudaStream_t stream);
+
+// ---- plan ---------------------------------------------------------------------------------------
+struct eftb_plan {
+  eftb_config cfg;
+  int K;  // nin + ntail + ntailx
+  double *k = nullptr, *l11 = nullptr, *lct = nullptr, *lctnnlo = nullptr, *l22 = nullptr, *l13 = nullptr;
+  double *lr = nullptr, *lrx = nullptr;
+  GemmMatrix Wf, Ak, As, Cinv, project;
+  double2* pair_table = nullptr;
+  int32_t* pair_offsets = nullptr;
+  double *R = nullptr, *q = nullptr, *kr2 = nullptr;
+  double *knot_lo = nullptr, *basis = nullptr, *mu = nullptr, *wl = nullptr;
+  int32_t* perm_out = nullptr;  // point-major export permutation
+  int perm_rows = 0;
+};
+
+// kernels' host launchers (defined in the respective .cu files)
+int launch_front_prepare(const eftb_plan* p, int B, int Bp, const double* plin, double* u, cudaStream_t s);
+int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cudaStream_t s);
+int launch_group(const eftb_plan* p, int Bp, const double* F, const double* P22, const double* Cs,
+                 const double* f, double* T, double* Cr, cudaStream_t s);
+int launch_resum(const eftb_plan* p, int B, int Bp, const double* F, const double* Cr, const double* f,
+                 double* T, cudaStream_t s);
+int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const double* Tin, const double* DA,
+              const double* H, double* Tout, cudaStream_t s);
+int launch_to_batch_minor(const double* in, int B, int Bp, int R, double* out, cudaStream_t s);
+int launch_to_point_major(const double* in, int B, int Bp, int R, const int32_t* perm, double* out,
+                          cudaStream_t s);

@@ -1,0 +1,194 @@
+// Fixed-operator FP64 GEMM on the DMMA tensor-core path (mma.sync m8n8k4 f64; tcgen05 has no f64 kind).
+//
+//   C[M][N] = A[M][K] * X[K][N]      A: plan constant (row-major, zero-padded to [Mp][Kp] at upload)
+//                                    X, C: batch-minor activations, N = (rows-per-point) * Bp, N % 32 == 0
+//
+// One CTA = 4 warps side by side along N (4 x 32 columns); every warp owns all MT m8-tiles of the CTA's
+// M-slab, i.e. a (8*MT) x 32 accumulator block = MT*4 DMMA tiles, so per k4-step a warp issues MT + 4
+// shared-memory fragment loads for 4*MT DMMAs.  A and X tiles are staged with 16-byte cp.async into
+// double-buffered shared memory (row pitches 20 and 132 doubles = 4 mod 16 -> conflict-free fragment
+// reads).  Used for: front operator, D -> P22/C22/C13 spectral transforms, B-spline collocation, the
+// window/binning/chained projection and the inverse-covariance product.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BK = 16;
+constexpr int BN = 128;
+constexpr int APITCH = BK + 4;
+constexpr int XPITCH = BN + 4;
+
+struct GemmArgs {
+  const double* A;
+  const double* X;
+  double* C;
+  int M, K, Kp, Mp, N;
+  int a_batched, zdiv;
+  size_t xs, xs2, cs;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int bytes = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int MT>
+__global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
+  constexpr int BM = 8 * MT;
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;                        // [2][BM][APITCH]
+  double* Xs = smem + 2 * BM * APITCH;      // [2][BK][XPITCH]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, zb = blockIdx.z;
+  const int zq = zb / g.zdiv, zr = zb % g.zdiv;
+  const double* A = g.A + (g.a_batched ? (size_t)zq * g.Mp * g.Kp : 0) + (size_t)m0 * g.Kp;
+  const double* X = g.X + (size_t)zr * g.xs + (size_t)zq * g.xs2;
+  double* C = g.C + (size_t)zb * g.cs;
+
+  double acc[MT][4][2];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nkt = g.Kp / BK;
+  auto load_stage = [&](int kt, int buf) {
+    // A tile: BM rows x 16 doubles = BM*8 chunks of 16 B
+    double* as = As + buf * BM * APITCH;
+    for (int c = tid; c < BM * 8; c += 128) {
+      int r = c >> 3, q = c & 7;
+      cp_async16(as + r * APITCH + q * 2, A + (size_t)r * g.Kp + kt * BK + q * 2, true);
+    }
+    double* xs = Xs + buf * BK * XPITCH;
+    for (int c = tid; c < BK * (BN / 2); c += 128) {
+      int r = c / (BN / 2), q = c % (BN / 2);
+      int kk = kt * BK + r, col = n0 + q * 2;
+      bool ok = (kk < g.K) && (col < g.N);
+      const double* src = ok ? X + (size_t)kk * g.N + col : X;
+      cp_async16(xs + r * XPITCH + q * 2, src, ok);
+    }
+    cp_async_commit();
+  };
+
+  load_stage(0, 0);
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nkt) {
+      load_stage(kt + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const double* as = As + buf * BM * APITCH;
+    const double* xs = Xs + buf * BK * XPITCH + warp * 32;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      double a[MT], b[4];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) a[i] = as[(i * 8 + (lane >> 2)) * APITCH + k4 * 4 + (lane & 3)];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = xs[(k4 * 4 + (lane & 3)) * XPITCH + j * 8 + (lane >> 2)];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncthreads();
+  }
+  // epilogue: each lane owns 2 adjacent columns of every tile row -> 16-byte stores
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    int row = m0 + i * 8 + (lane >> 2);
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int col = n0 + warp * 32 + j * 8 + (lane & 3) * 2;
+      if (col < g.N) *reinterpret_cast<double2*>(C + (size_t)row * g.N + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+  }
+}
+
+template <int MT>
+int launch(const GemmArgs& g, int nz, cudaStream_t s) {
+  constexpr int BM = 8 * MT;
+  size_t smem = sizeof(double) * (2 * BM * APITCH + 2 * BK * XPITCH);
+  static bool configured = false;
+  if (!configured) {
+    EFTB_CUDA_CHECK(cudaFuncSetAttribute(gemm_f64_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((g.N + BN - 1) / BN, g.Mp / BM, nz);
+  gemm_f64_kernel<MT><<<grid, 128, smem, s>>>(g);
+  EFTB_LAUNCH_CHECK();
+  return EFTB_OK;
+}
+
+// choose the slab height (in m8 tiles) minimising padding; candidates keep registers < 255
+int pick_mt(int M) {
+  const int cand[] = {10, 9, 8, 7, 6, 5, 4};
+  int best = 10;
+  double best_waste = 1e9;
+  for (int mt : cand) {
+    int bm = 8 * mt;
+    int mp = eftb_round_up(M, bm);
+    double waste = (double)(mp - M) / M + 0.02 * (10 - mt);  // mild preference for tall slabs
+    if (waste < best_waste) { best_waste = waste; best = mt; }
+  }
+  return best;
+}
+
+}  // namespace
+
+int gemm_upload(const double* host, int nbatch, int M, int K, GemmMatrix* out) {
+  int MT = pick_mt(M);
+  int Mp = eftb_round_up(M, 8 * MT), Kp = eftb_round_up(K, BK);
+  size_t n = (size_t)nbatch * Mp * Kp;
+  double* tmp = (double*)calloc(n, sizeof(double));
+  if (!tmp) return EFTB_ERR_ARG;
+  for (int b = 0; b < nbatch; ++b)
+    for (int r = 0; r < M; ++r)
+      for (int c = 0; c < K; ++c) tmp[((size_t)b * Mp + r) * Kp + c] = host[((size_t)b * M + r) * K + c];
+  double* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(d, tmp, n * sizeof(double), cudaMemcpyHostToDevice);
+  free(tmp);
+  if (e != cudaSuccess) {
+    eftb_set_error("gemm_upload: %s", cudaGetErrorString(e));
+    return EFTB_ERR_CUDA;
+  }
+  out->d = d; out->M = M; out->K = K; out->Mp = Mp; out->Kp = Kp; out->MT = MT; out->nbatch = nbatch;
+  return EFTB_OK;
+}
+
+void gemm_free(GemmMatrix* m) {
+  if (m->d) cudaFree(m->d);
+  m->d = nullptr;
+}
+
+int gemm_run(const GemmMatrix& A, const double* X, double* C, int N, int nz, int zdiv, size_t xs, size_t xs2,
+             size_t cs, cudaStream_t stream) {
+  if (!A.d || !X || !C || N % 2) { eftb_set_error("gemm_run: bad arguments"); return EFTB_ERR_ARG; }
+  GemmArgs g{A.d, X, C, A.M, A.K, A.Kp, A.Mp, N, A.nbatch > 1 ? 1 : 0, zdiv, xs, xs2, cs};
+  switch (A.MT) {
+    case 10: return launch<10>(g, nz, stream);
+    case 9: return launch<9>(g, nz, stream);
+    case 8: return launch<8>(g, nz, stream);
+    case 7: return launch<7>(g, nz, stream);
+    case 6: return launch<6>(g, nz, stream);
+    case 5: return launch<5>(g, nz, stream);
+    default: return launch<4>(g, nz, stream);
+  }
+}

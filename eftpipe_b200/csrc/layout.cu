@@ -1,0 +1,82 @@
+// Layout kernels: point-major <-> batch-minor transposes and the front-end input vector.
+#include "common.cuh"
+
+namespace {
+
+// in[B][R] -> out[R][Bp]; lanes beyond B replicate point B-1 so that padded lanes stay finite
+__global__ void to_batch_minor_kernel(const double* __restrict__ in, int B, int Bp, int R, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  int b0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int b = min(b0 + j, B - 1), r = r0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < R) ? in[(size_t)b * R + r] : 0.0;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int r = r0 + j, b = b0 + threadIdx.x;
+    if (r < R && b < Bp) out[(size_t)r * Bp + b] = tile[threadIdx.x][j];
+  }
+}
+
+// in[rows][Bp] -> out[B][R] with out[b][r] = in[perm ? perm[r] : r][b]
+__global__ void to_point_major_kernel(const double* __restrict__ in, int B, int Bp, int R,
+                                      const int32_t* __restrict__ perm, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  int b0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int r = r0 + j, b = b0 + threadIdx.x;
+    if (r < R && b < Bp) {
+      int src = perm ? perm[r] : r;
+      tile[j][threadIdx.x] = in[(size_t)src * Bp + b];
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int b = b0 + j, r = r0 + threadIdx.x;
+    if (b < B && r < R) out[(size_t)b * R + r] = tile[threadIdx.x][j];
+  }
+}
+
+// power-law tails beyond the last input sample (fftlog.py:146-151) for the loop FFTLog and for the
+// 32-point IR-filter FFTLog of P exp(-k^2/Lambda^2)/k^2 (pybird.py:1321-1325).  One lane per point.
+__global__ void front_tails_kernel(const double* __restrict__ plin, int B, int Bp, int nin, int ntail, int ntailx,
+                                   const double* __restrict__ lr, const double* __restrict__ lrx, double inv_dlog,
+                                   double wx_last, double wx_prev, double* __restrict__ u) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= Bp) return;
+  int src = min(b, B - 1);
+  double last = plin[(size_t)src * nin + nin - 1], prev = plin[(size_t)src * nin + nin - 2];
+  double slope = (log(last) - log(prev)) * inv_dlog;
+  double* ut = u + (size_t)nin * Bp + b;
+  for (int i = 0; i < ntail; ++i) ut[(size_t)i * Bp] = last * exp(slope * lr[i]);
+  double fl = last * wx_last, fp = prev * wx_prev;
+  double slx = (log(fl) - log(fp)) * inv_dlog;
+  ut += (size_t)ntail * Bp;
+  for (int i = 0; i < ntailx; ++i) ut[(size_t)i * Bp] = fl * exp(slx * lrx[i]);
+}
+
+}  // namespace
+
+int launch_to_batch_minor(const double* in, int B, int Bp, int R, double* out, cudaStream_t s) {
+  dim3 grid(Bp / 32, (R + 31) / 32), block(32, 8);
+  to_batch_minor_kernel<<<grid, block, 0, s>>>(in, B, Bp, R, out);
+  EFTB_LAUNCH_CHECK();
+  return EFTB_OK;
+}
+
+int launch_to_point_major(const double* in, int B, int Bp, int R, const int32_t* perm, double* out, cudaStream_t s) {
+  dim3 grid(Bp / 32, (R + 31) / 32), block(32, 8);
+  to_point_major_kernel<<<grid, block, 0, s>>>(in, B, Bp, R, perm, out);
+  EFTB_LAUNCH_CHECK();
+  return EFTB_OK;
+}
+
+int launch_front_prepare(const eftb_plan* p, int B, int Bp, const double* plin, double* u, cudaStream_t s) {
+  const eftb_config& c = p->cfg;
+  int rc = launch_to_batch_minor(plin, B, Bp, c.nin, u, s);
+  if (rc) return rc;
+  front_tails_kernel<<<(Bp + 127) / 128, 128, 0, s>>>(plin, B, Bp, c.nin, c.ntail, c.ntailx, p->lr, p->lrx, c.inv_dlog,
+                                                     c.wx_last, c.wx_prev, u);
+  EFTB_LAUNCH_CHECK();
+  return EFTB_OK;
+}

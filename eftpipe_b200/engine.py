@@ -1,0 +1,270 @@
+"""Device engine: uploads a host `TracerPlan` into a `libeftb200` plan and drives the CUDA stages
+on torch CUDA tensors (torch is only the allocator / stream provider here).
+
+Arrays crossing this API are torch float64 CUDA tensors.  "Batch-minor" tensors have shape
+(..., Bp) with Bp = padded_batch(B); public results are returned point-major (B, ...).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .plan import N22, NCH, TracerPlan
+
+
+def _stream_ptr(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class DevicePlan:
+    """One tracer's pipeline on the current CUDA device."""
+
+    def __init__(self, plan: TracerPlan):
+        self.torch = _lib.require_cuda()
+        self.lib = _lib.load()
+        self.host = plan
+        g, lay = plan.grid, plan.front
+        cfg = _lib.EftbConfig()
+        cfg.Nl, cfg.Nk, cfg.Ns, cfg.Nmax, cfg.nterm, cfg.with_nnlo = g.Nl, g.Nk, g.Ns, g.NFFT, g.nterm, int(g.with_NNLO)
+        cfg.nin, cfg.ntail, cfg.ntailx, cfg.front_rows = lay.nin, lay.ntail, lay.ntailx, plan.Wf.shape[0]
+        rows = lay.rows
+        cfg.row_cre, cfg.row_cim, cfg.row_p11, cfg.row_p13 = rows["cre"][0], rows["cim"][0], rows["P11"][0], rows["P13raw"][0]
+        cfg.row_c11, cfg.row_cct = rows["C11"][0], rows["Cct"][0]
+        cfg.row_cctnnlo = rows["CctNNLO"][0] if g.with_NNLO else -1
+        cfg.row_x, cfg.row_y = rows["X"][0], rows["Y"][0]
+        aux = plan.front_aux
+        cfg.inv_dlog, cfg.wx_last, cfg.wx_prev = aux["inv_dlog"], aux["wX_last"], aux["wX_prev"]
+        cfg.npair = plan.pair_table.shape[0]
+        keep = []  # host arrays must outlive the create call
+
+        def ptr(a, ctype=C.c_double, dtype=np.float64):
+            a = np.ascontiguousarray(a, dtype=dtype)
+            keep.append(a)
+            return _lib.as_ptr(a, ctype)
+
+        cst = _lib.EftbConstants()
+        cst.k, cst.l11, cst.lct, cst.lctnnlo = ptr(g.k), ptr(g.l11), ptr(g.lct), ptr(g.lctNNLO)
+        cst.l22, cst.l13 = ptr(g.l22), ptr(g.l13)
+        cst.Wf, cst.lr, cst.lrx = ptr(plan.Wf), ptr(aux["lr"]), ptr(aux["lrx"])
+        cst.pair_table = ptr(plan.pair_table.view(np.float64))
+        cst.pair_offsets = ptr(plan.pair_offsets, C.c_int32, np.int32)
+        cst.Ak, cst.As = ptr(plan.Ak), ptr(plan.As)
+        if plan.resum is not None:
+            rs = plan.resum
+            cfg.has_resum, cfg.NIR, cfg.Na, cfg.Nkr, cfg.Nklow, cfg.qdeg = 1, rs["NIR"], rs["Na"], g.Nkr, g.Nklow, rs["q"].shape[-1]
+            cst.R, cst.q, cst.kr2 = ptr(rs["R"]), ptr(rs["q"]), ptr(rs["kr2"])
+        if plan.ap is not None:
+            ap = plan.ap
+            cfg.has_ap, cfg.nmu, cfg.nint, cfg.ap_st = 1, ap["mu"].size, ap["nint"], int(plan.ap_st)
+            cfg.da_fid, cfg.h_fid = plan.ap_fid
+            cst.Cinv, cst.knot_lo, cst.basis, cst.mu, cst.wl = ptr(ap["Cinv"]), ptr(ap["knot_lo"]), ptr(ap["basis"]), ptr(ap["mu"]), ptr(ap["wl"])
+        if plan.project is not None:
+            cfg.has_project, cfg.nout, cfg.nl_out = 1, plan.project.shape[0], plan.out_shape[0]
+            cst.project = ptr(plan.project)
+        handle = C.c_void_p()
+        _lib.check(self.lib.eftb_plan_create(C.byref(cfg), C.byref(cst), C.byref(handle)), "eftb_plan_create")
+        self.handle, self.cfg = handle, cfg
+        self._ws = None
+        if plan.project is not None:
+            self.out_shape = (plan.out_shape[0], g.nterm, plan.out_shape[1])
+        else:
+            self.out_shape = (g.Nl, g.nterm, g.Nk)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.eftb_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def padded(self, B):
+        return self.lib.eftb_padded_batch(int(B))
+
+    def _empty(self, *shape):
+        return self.torch.empty(shape, dtype=self.torch.float64, device="cuda")
+
+    def _dev(self, a):
+        t = self.torch
+        if isinstance(a, t.Tensor):
+            return a.to(device="cuda", dtype=t.float64).contiguous()
+        return t.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device="cuda")
+
+    def to_batch_minor(self, x):
+        """(B, R) point-major -> (R, Bp)."""
+        x = self._dev(x)
+        if x.dim() == 1:
+            x = x[:, None]
+        B, R = x.shape
+        out = self._empty(R, self.padded(B))
+        _lib.check(self.lib.eftb_to_batch_minor(_p(x), B, R, _p(out), _stream_ptr(self.torch)), "to_batch_minor")
+        return out
+
+    def to_point_major(self, x, B):
+        """(R, Bp) -> (B, R)."""
+        R = x.shape[0]
+        out = self._empty(B, R)
+        _lib.check(self.lib.eftb_to_point_major(_p(x), B, R, C.c_void_p(0), _p(out), _stream_ptr(self.torch)), "to_point_major")
+        return out
+
+    # ------------------------------------------------------------------ stages (batch-minor tensors)
+    def front(self, plin):
+        plin = self._dev(plin)
+        B = plin.shape[0]
+        Bp = self.padded(B)
+        u = self._empty(self.host.front.K, Bp)
+        F = self._empty(self.cfg.front_rows, Bp)
+        _lib.check(self.lib.eftb_front(self.handle, B, _p(plin), _p(u), _p(F), _stream_ptr(self.torch)), "eftb_front")
+        return F
+
+    def antidiag(self, F, B):
+        D = self._empty(NCH, self.cfg.Nmax + 1, 2, self.padded(B))
+        _lib.check(self.lib.eftb_antidiag(self.handle, B, _p(F), _p(D), _stream_ptr(self.torch)), "eftb_antidiag")
+        return D
+
+    def spectral(self, D, B):
+        Bp = self.padded(B)
+        P22 = self._empty(N22, self.cfg.Nk, Bp)
+        Cs = self._empty(self.cfg.Nl, NCH, self.cfg.Ns, Bp)
+        _lib.check(self.lib.eftb_spectral(self.handle, B, _p(D), _p(P22), _p(Cs), _stream_ptr(self.torch)), "eftb_spectral")
+        return P22, Cs
+
+    def group(self, F, P22, Cs, f_bm, B):
+        Bp = self.padded(B)
+        c = self.cfg
+        T = self._empty(c.Nl, c.Nk, c.nterm, Bp)
+        Cr = self._empty(c.Nl, 14 + c.with_nnlo, c.Ns, Bp)
+        _lib.check(self.lib.eftb_group(self.handle, B, _p(F), _p(P22), _p(Cs), _p(f_bm), _p(T), _p(Cr),
+                                       _stream_ptr(self.torch)), "eftb_group")
+        return T, Cr
+
+    def resum(self, F, Cr, f_bm, T, B):
+        _lib.check(self.lib.eftb_resum(self.handle, B, _p(F), _p(Cr), _p(f_bm), _p(T), _stream_ptr(self.torch)), "eftb_resum")
+        return T
+
+    def ap(self, T, DA_bm, H_bm, B):
+        coef = self.torch.empty_like(T)
+        out = self.torch.empty_like(T)
+        _lib.check(self.lib.eftb_ap(self.handle, B, _p(T), _p(DA_bm), _p(H_bm), _p(coef), _p(out),
+                                    _stream_ptr(self.torch)), "eftb_ap")
+        return out
+
+    def project(self, T, B):
+        out = self._empty(self.cfg.nout, self.cfg.nterm, self.padded(B))
+        _lib.check(self.lib.eftb_project(self.handle, B, _p(T), _p(out), _stream_ptr(self.torch)), "eftb_project")
+        return out
+
+    # ------------------------------------------------------------------ fused pipeline
+    def workspace(self, B):
+        need = self.lib.eftb_workspace_bytes(self.handle, int(B))
+        if self._ws is None or self._ws.numel() * 8 < need:
+            self._ws = self.torch.empty((need + 7) // 8, dtype=self.torch.float64, device="cuda")
+        return self._ws, need
+
+    def eval_terms(self, plin, f, DA=None, H=None, want_bm=False, want_pm=True, out_pm=None, out_bm=None):
+        """theory.py:557-609 for a batch.  plin (B, nin), f/DA/H (B,) - device tensors or arrays.
+        Returns (terms_pm (B, Nl_out, nterm, nk_out) or None, terms_bm (rows, nterm, Bp) or None)."""
+        t = self.torch
+        plin = self._dev(plin)
+        B = plin.shape[0]
+        f = self._dev(f)
+        DA = self._dev(DA) if DA is not None else None
+        H = self._dev(H) if H is not None else None
+        ws, need = self.workspace(B)
+        Bp = self.padded(B)
+        if want_pm and out_pm is None:
+            out_pm = self._empty(B, *self.out_shape)
+        if want_bm and out_bm is None:
+            rows = self.cfg.nout if self.cfg.has_project else self.cfg.Nl * self.cfg.Nk
+            out_bm = self._empty(rows, self.cfg.nterm, Bp)
+        _lib.check(
+            self.lib.eftb_eval_terms(self.handle, B, _p(plin), _p(f), _p(DA), _p(H), _p(out_bm if want_bm else None),
+                                     _p(out_pm if want_pm else None), _p(ws), need, _stream_ptr(t)),
+            "eftb_eval_terms",
+        )
+        return (out_pm if want_pm else None), (out_bm if want_bm else None)
+
+
+class DeviceLikelihood:
+    """likelihood.py EFTLike.calculate + marginal.py for a batch of points (see likelihood.py here)."""
+
+    def __init__(self, spec: dict):
+        self.torch = _lib.require_cuda()
+        self.lib = _lib.load()
+        self.spec = spec
+        cfg = _lib.EftbLikeConfig()
+        cfg.ntracer, cfg.ndata, cfg.ngauss = spec["ntracer"], spec["ndata"], spec["ngauss"]
+        cfg.npar, cfg.jeffreys = spec["npar"], int(spec["jeffreys"])
+        keep = []
+
+        def ptr(a, ctype, dtype):
+            a = np.ascontiguousarray(a, dtype=dtype)
+            keep.append(a)
+            return _lib.as_ptr(a, ctype)
+
+        dp = lambda a: ptr(a, C.c_double, np.float64)
+        ip = lambda a: ptr(a, C.c_int32, np.int32)
+        cst = _lib.EftbLikeConstants()
+        cst.nout, cst.nterm, cst.scales, cst.par_index = ip(spec["nout"]), ip(spec["nterm"]), dp(spec["scales"]), ip(spec["par_index"])
+        cst.eastcoast, cst.d_tracer, cst.d_row = ip(spec["eastcoast"]), ip(spec["d_tracer"]), ip(spec["d_row"])
+        cst.data, cst.picc, cst.invcov = dp(spec["data"]), dp(spec["picc"]), dp(spec["invcov"])
+        ng = max(spec["ngauss"], 1)
+        cst.g_count, cst.g_tracer = ip(spec["g_count"] if spec["ngauss"] else np.zeros(1)), ip(spec["g_tracer"] if spec["ngauss"] else np.zeros(2))
+        cst.g_term = ip(spec["g_term"] if spec["ngauss"] else np.zeros(4))
+        cst.g_var = ip(spec["g_var"] if spec["ngauss"] else np.zeros(4))
+        cst.g_coef = dp(spec["g_coef"] if spec["ngauss"] else np.zeros(4))
+        cst.sigma_inv = dp(spec["sigma_inv"] if spec["ngauss"] else np.zeros((ng, ng)))
+        cst.sigma_inv_mu = dp(spec["sigma_inv_mu"] if spec["ngauss"] else np.zeros(ng))
+        cst.mu_sigma_mu = float(spec["mu_sigma_mu"])
+        handle = C.c_void_p()
+        _lib.check(self.lib.eftb_like_create(C.byref(cfg), C.byref(cst), C.byref(handle)), "eftb_like_create")
+        self.handle, self.cfg = handle, cfg
+        self._ws = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.eftb_like_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def _workspace(self, B):
+        need = self.lib.eftb_like_workspace_bytes(self.handle, int(B))
+        if self._ws is None or self._ws.numel() * 8 < need:
+            self._ws = self.torch.empty((need + 7) // 8, dtype=self.torch.float64, device="cuda")
+        return self._ws, need
+
+    def _ptr_array(self, tensors):
+        arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        return arr
+
+    def eval(self, B, terms_bm, f_bm, nuis_bm, want_bestfit=False):
+        t = self.torch
+        ws, need = self._workspace(B)
+        logp = t.empty(B, dtype=t.float64, device="cuda")
+        status = t.empty(B, dtype=t.int32, device="cuda")
+        best = t.empty((B, self.cfg.ngauss), dtype=t.float64, device="cuda") if want_bestfit else None
+        ta, fa = self._ptr_array(terms_bm), self._ptr_array(f_bm)
+        _lib.check(
+            self.lib.eftb_like_eval(self.handle, B, ta, fa, _p(nuis_bm), _p(logp), _p(best), _p(status), _p(ws), need,
+                                    _stream_ptr(t)),
+            "eftb_like_eval",
+        )
+        return logp, status, best
+
+    def vectors(self, B, terms_bm, f_bm, nuis_bm):
+        t = self.torch
+        ws, need = self._workspace(B)
+        vec = t.empty((B, self.cfg.ndata, self.cfg.ngauss + 1), dtype=t.float64, device="cuda")
+        ta, fa = self._ptr_array(terms_bm), self._ptr_array(f_bm)
+        _lib.check(self.lib.eftb_like_vectors(self.handle, B, ta, fa, _p(nuis_bm), _p(vec), _p(ws), need, _stream_ptr(t)),
+                   "eftb_like_vectors")
+        return vec

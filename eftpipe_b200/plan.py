@@ -1,0 +1,445 @@
+"""Plan construction: every cosmology-independent operator of the hot path, built once on the
+host (numpy/scipy, fp64 with extended precision where phases are involved) and uploaded to
+the GPU.  Nothing here runs per evaluation.
+
+Design: for fixed grids almost every stage of the reference pipeline is a
+fixed linear map, and the one-loop contraction  sum_{nm} c_n c_m M[n,m] x^{eta_n+eta_m}
+depends on x only through n+m.  The plan therefore holds
+
+  front      real matrix  [P_lin samples | power-law tails] -> FFTLog coefficients c_n and every
+             quantity linear in c (P11, the 13-loop in k-space, C11, Cct, IR filters X, Y)
+  antidiag   pair table  M[t][p][ch] = sym. kernel values along the anti-diagonal n+m=t, so that
+             D_ch[t] = sum_{n+m=t} c_n c_m M_ch[n,m]  (28 22-type + 10 13-type channels)
+  spectral   real matrices taking D[t] to P22(k), C22_l(s), C13_l(s)
+  resum      real matrix R[v,k,s] (spline + FFTLog-192 + Bessel back-transform, all linear)
+             and the Q^{ll'}(f) polynomial table
+  ap         not-a-knot B-spline collocation inverse, per-interval basis polynomials, the
+             mu quadrature with Legendre weights
+  project    window (+ integral constraint), binning and chained-multipole mixing composed into
+             one real matrix acting on the Nl*Nk internal nodes
+
+All per-evaluation arrays on the device are "batch-minor": the cosmology index is the fastest
+axis, so every kernel is coalesced with one lane per cosmology and every fixed operator is a
+GEMM  C[M, B] = A[M, K] X[K, B].
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+from scipy.interpolate import CubicSpline, PPoly, make_interp_spline
+
+from . import tables
+from .fftlog import FFTLog
+
+N22, N13, NCH = 28, 10, 38
+N11, NCT, NLOOP, NST, NNNLO = 3, 6, 12, 3, 3
+LAMBDA_IR = 0.2
+
+
+def cubic_matrix(xk, xq):
+    """Matrix of `interp1d(xk, ., kind="cubic", fill_value="extrapolate")(xq)`: not-a-knot cubic
+    spline, end polynomials continued outside (pybird.py:1586-1593, window.py:376-383,
+    binning.py:135-142).  Shape (len(xq), len(xk))."""
+    return CubicSpline(np.asarray(xk, float), np.eye(len(xk)), axis=0, extrapolate=True)(np.asarray(xq, float))
+
+
+# --------------------------------------------------------------------------------------------
+@dataclass
+class GridConfig:
+    """Static sizes and grids, the numeric content of `pybird.Common` (pybird.py:486-582)."""
+
+    Nl: int = 2
+    kmax: float = 0.3
+    NFFT: int = 256
+    with_NNLO: bool = False
+    k: np.ndarray = field(init=False)
+    s: np.ndarray = field(init=False)
+
+    def __post_init__(self):
+        self.k = tables.kbird(self.kmax)
+        self.s = tables.sbird()
+        self.Nk, self.Ns = self.k.size, self.s.size
+        self.kr = self.k[0.02 <= self.k]
+        self.Nkr = self.kr.size
+        self.Nklow = self.Nk - self.Nkr
+        self.l11 = tables.legendre_weights(self.Nl, tables.MU11)
+        self.lct = tables.legendre_weights(self.Nl, tables.MUCT)
+        self.lctNNLO = tables.legendre_weights(self.Nl, tables.MUNNLO)
+        self.l22 = tables.legendre_weights(self.Nl, tables.MU22)
+        self.l13 = tables.legendre_weights(self.Nl, tables.MU13)
+        self.nterm = N11 + NCT + NLOOP + NST + (NNNLO if self.with_NNLO else 0)
+
+
+# --------------------------------------------------------------------------------------------
+# loop kernels
+# --------------------------------------------------------------------------------------------
+def loop_matrices(fft: FFTLog):
+    """M22 (28,N,N) and M13 (10,N) exactly as the reference defines them (pybird.py:1005-1023)."""
+    nu = -0.5 * fft.Pow
+    M22 = tables.loop22_gamma(nu)[None] * tables.loop22_rational(nu)
+    M13 = tables.loop13_prefactor(nu)[None] * tables.loop13_rational(nu)
+    return M22, M13
+
+
+def antidiagonal_table(M22, M13):
+    """Pair table for t = n+m <= Nmax, n <= m.  For a symmetric kernel
+         D[t] = sum_{n+m=t} c_n c_m M[n,m] = sum_{n<m} c_n c_m (M[n,m]+M[m,n]) + c_n^2 M[n,n];
+    the 13-type channels carry M13[b,n] on the first index only (pybird.py:1046), which the
+    same symmetrisation handles.  Returns (table[npair, NCH] complex, offsets[Nmax+2] int32);
+    pair p of anti-diagonal t is (n, m) = (p, t-p), p = 0..t//2."""
+    N = M22.shape[-1]
+    Nmax = N - 1
+    offsets = np.zeros(Nmax + 2, dtype=np.int32)
+    rows = []
+    for t in range(Nmax + 1):
+        n = np.arange(t // 2 + 1)
+        m = t - n
+        sym = np.where(n == m, 1.0, 2.0)
+        # use the exact average of the (numerically 5e-15-symmetric) reference matrix
+        v22 = 0.5 * sym[None, :] * (M22[:, n, m] + M22[:, m, n])
+        v13 = np.where(n == m, M13[:, n], M13[:, n] + M13[:, m])
+        rows.append(np.concatenate([v22, v13], axis=0).T)
+        offsets[t + 1] = offsets[t] + n.size
+    return np.ascontiguousarray(np.concatenate(rows, axis=0)), offsets
+
+
+def _phase_ld(eta, logx):
+    """exp(eta * log x) with the (large) phase accumulated in extended precision."""
+    e = np.asarray(eta).astype(np.clongdouble)
+    lx = np.asarray(logx).astype(np.longdouble)
+    return np.exp(np.multiply.outer(e, lx))
+
+
+def spectral_matrices(fft: FFTLog, g: GridConfig):
+    """Real matrices taking the Hermitian half of D[t] (t = 0..Nmax; K index = 2t + {0: Re, 1: Im})
+    to  P22[b,k] = k^3 Re sum_t D_b[t] k^{eta2_t}  (pybird.py:1074-1078) and
+        C22[l,b,s] = Re sum_t Ml[l,t] D_b[t] s^{-eta2_t-6}  (pybird.py:1042, :1103-1113),
+    eta2_t = eta_n + eta_m for n+m=t, Ml[l,t] = MPC(2l, nu_n+nu_m-3/2) (pybird.py:1035-1038)."""
+    Nmax = fft.Nmax
+    t = np.arange(Nmax + 1)
+    delta = 2.0 * np.pi / (Nmax * fft.dx)
+    eta2 = 2.0 * fft.bias + 1j * delta * (t - Nmax)
+    herm = np.where(t == Nmax, 1.0, 2.0)
+    Ek = _phase_ld(eta2, np.log(g.k.astype(np.longdouble))) * (g.k.astype(np.longdouble) ** 3)[None, :]
+    Ak = np.empty((g.Nk, 2 * (Nmax + 1)))
+    Ak[:, 0::2] = (herm[:, None] * Ek.real).T.astype(float)
+    Ak[:, 1::2] = (-herm[:, None] * Ek.imag).T.astype(float)
+    Ml = tables.bessel_power(2 * np.arange(g.Nl)[:, None], (-0.5 * eta2 - 1.5)[None, :])
+    Es = _phase_ld(-eta2 - 6.0, np.log(g.s.astype(np.longdouble)))
+    As = np.empty((g.Nl, g.Ns, 2 * (Nmax + 1)))
+    for l in range(g.Nl):
+        G = Ml[l].astype(np.clongdouble)[:, None] * Es
+        As[l][:, 0::2] = (herm[:, None] * G.real).T.astype(float)
+        As[l][:, 1::2] = (-herm[:, None] * G.imag).T.astype(float)
+    return Ak, As
+
+
+# --------------------------------------------------------------------------------------------
+# front end: everything linear in [P_lin | tails]
+# --------------------------------------------------------------------------------------------
+@dataclass
+class FrontLayout:
+    nin: int
+    ntail: int
+    ntailx: int
+    rows: dict  # name -> (start, count)
+
+    @property
+    def K(self):
+        return self.nin + self.ntail + self.ntailx
+
+    @property
+    def M(self):
+        return max(a + b for a, b in self.rows.values())
+
+
+def front_operator(kin, g: GridConfig, fft: FFTLog, M13, window=0.2):
+    """Real matrix Wf (M, K) and layout.  Input vector u = [P_lin(kin) | tail | tailX] with
+      tail_i  = P_last exp(n lr_i),  n  from the last two samples of P_lin           (fftlog.py:146-151)
+      tailX_i = fX_last exp(nX lrx_i), fX = P_lin exp(-k^2/Lambda^2)/k^2            (pybird.py:1321-1325)
+    Output rows: Re c_n, Im c_n (n = 0..Nmax/2), P11(k), Re sum_n c_n k^{eta_n} M13[b,n], C11, Cct
+    [, CctNNLO], X(s), Y(s)."""
+    kin = np.asarray(kin, float)
+    if fft.has_low_tail(kin):
+        raise NotImplementedError("input k-grid must start below the FFTLog xmin (reference default)")
+    Nmax, Nh = fft.Nmax, fft.Nmax // 2
+    L = fft.operator(kin, window=window)  # (N, nin)
+    Lt, lr = fft.tail_operator(kin, window=window)
+    Lc = np.concatenate([L, Lt], axis=1)  # c = Lc @ [P | tail]
+    nin, ntail = kin.size, lr.size
+
+    xf = FFTLog(Nmax=32, xmin=1.5e-5, xmax=10.0, bias=-2.6)  # pybird.py:1293
+    if xf.has_low_tail(kin):
+        raise NotImplementedError
+    wX = np.exp(-(kin**2) / LAMBDA_IR**2) / kin**2
+    LX = xf.operator(kin, window=None) * wX[None, :]
+    LXt, lrx = xf.tail_operator(kin, window=None)
+    ntailx = lrx.size
+    K = nin + ntail + ntailx
+
+    def embed(mat_nl=None, mat_x=None):
+        nrow = (mat_nl if mat_nl is not None else mat_x).shape[0]
+        out = np.zeros((nrow, K), dtype=complex)
+        if mat_nl is not None:
+            out[:, : nin + ntail] = mat_nl
+        if mat_x is not None:
+            out[:, :nin] += mat_x[:, :nin]
+            out[:, nin + ntail :] = mat_x[:, nin:]
+        return out
+
+    blocks, rows, cursor = [], {}, 0
+
+    def add(name, mat):
+        nonlocal cursor
+        mat = np.ascontiguousarray(mat.reshape(-1, K))
+        blocks.append(mat)
+        rows[name] = (cursor, mat.shape[0])
+        cursor += mat.shape[0]
+
+    Cfull = embed(Lc)
+    add("cre", Cfull[: Nh + 1].real)
+    add("cim", Cfull[: Nh + 1].imag)
+    add("P11", embed(np.concatenate([cubic_matrix(kin, g.k), np.zeros((g.Nk, ntail))], axis=1)).real)
+    kPow = np.exp(np.outer(fft.Pow, np.log(g.k)))  # pybird.py:1060
+    sPow = np.exp(np.outer(-fft.Pow - 3.0, np.log(g.s)))  # pybird.py:1064
+    nu = -0.5 * fft.Pow
+    ell = 2 * np.arange(g.Nl)
+    # P13raw[b,k] = Re sum_n M13[b,n] kPow[n,k] c_n      (pybird.py:1080-1086 without k^3 P11)
+    G13 = (M13[:, None, :] * kPow.T[None, :, :]).reshape(N13 * g.Nk, -1)
+    add("P13raw", (G13 @ Cfull).real)
+    Mcf11 = tables.bessel_power(ell[:, None], nu[None, :])  # pybird.py:1029
+    add("C11", ((Mcf11[:, None, :] * sPow.T[None]).reshape(g.Nl * g.Ns, -1) @ Cfull).real)
+    Mcfct = tables.bessel_power(ell[:, None], nu[None, :] - 1.0)  # pybird.py:1052
+    Gct = (Mcfct[:, None, :] * sPow.T[None]) * (g.s**-2)[None, :, None]  # pybird.py:1092-1096
+    add("Cct", (Gct.reshape(g.Nl * g.Ns, -1) @ Cfull).real)
+    if g.with_NNLO:
+        Mn = tables.bessel_power(ell[:, None], nu[None, :] - 2.0)  # pybird.py:1056
+        Gn = (Mn[:, None, :] * sPow.T[None]) * (g.s**-4)[None, :, None]
+        add("CctNNLO", (Gn.reshape(g.Nl * g.Ns, -1) @ Cfull).real)
+    # IR filters (pybird.py:1316-1353): X = 2/3 (X0off - X0 - X2), Y = 2 X2
+    CX = embed(mat_x=np.concatenate([LX, LXt], axis=1))
+    XM = np.array([tables.bessel_power(2 * l, -0.5 * xf.Pow) for l in range(2)])
+    XsPow = np.exp(np.outer(-xf.Pow - 3.0, np.log(g.s)))
+    X02 = (XM[:, None, :] * XsPow.T[None]) @ CX  # (2, Ns, K) complex
+    off = (XM[0] @ CX)[None, :]
+    X0 = off - X02[0]
+    add("X", (2.0 / 3.0 * (X0 - X02[1])).real)
+    add("Y", (2.0 * X02[1]).real)
+    Wf = np.concatenate(blocks, axis=0)
+    layout = FrontLayout(nin=nin, ntail=ntail, ntailx=ntailx, rows=rows)
+    aux = dict(lr=lr, lrx=lrx, wX_last=wX[-1], wX_prev=wX[-2],
+               inv_dlog=1.0 / (np.log(kin[-1]) - np.log(kin[-2])))
+    return Wf, layout, aux
+
+
+# --------------------------------------------------------------------------------------------
+# IR resummation
+# --------------------------------------------------------------------------------------------
+def resum_operator(g: GridConfig, NFFT=192):
+    """R[v, k, s]: the linear chain  C(s) -> cubic spline on the FFTLog-192 grid (zero padded
+    outside [s_0, s_-1]) -> coefficients -> Bessel transform to k_r (pybird.py:1288-1308,
+    :1355-1365, :1409-1411).  IR[v,k] = sum_s R[v,k,s] (XpYp_j * C)(s)."""
+    Nl = g.Nl
+    NIR = 16 if Nl == 3 else 8  # pybird.py:1247-1258
+    Na = 3 if NIR == 16 else 2
+    fft = FFTLog(Nmax=NFFT, xmin=0.1, xmax=10000.0, bias=-0.6)
+    L = fft.operator(g.s, window=None)  # (N, Ns)
+    M = np.array([8.0 * np.pi**3 * tables.bessel_power(2 * l, -0.5 * fft.Pow) for l in range(Na)])
+    kPow = np.exp(np.outer(-fft.Pow - 3.0, np.log(g.kr)))
+    R = np.real(np.einsum("vn,nk,ns->vks", M, kPow, L))
+    return dict(R=np.ascontiguousarray(R), NIR=NIR, Na=Na, q=tables.resum_coefficients(Nl),
+                kr2=g.kr**2)
+
+
+# --------------------------------------------------------------------------------------------
+# Alcock-Paczynski
+# --------------------------------------------------------------------------------------------
+def ap_operator(g: GridConfig, nbinsmu=200, accboost=1):
+    """Constants of the AP resampling (pybird.py:1538-1548, :1581-1596).
+
+    The reference spline `interp1d(kind="cubic")` is the not-a-knot B-spline interpolant.  For
+    fixed nodes its coefficient vector is `Cinv @ values`; `basis[j, r, d]` are the monomial
+    coefficients, in (x - knot_lo[j]), of the 4 B-splines alive on interval j, so that
+        spline(x) = sum_r coef[j + r] * sum_d basis[j, r, d] (x - knot_lo[j])^d ,
+    with the first/last interval continued for extrapolation (fill_value="extrapolate")."""
+    k = g.k
+    n = k.size
+    spl = make_interp_spline(k, np.eye(n), k=3, axis=0)
+    tk = spl.t  # knots: x0*4, x2..x_{n-3}, x_{n-1}*4
+    Cinv = np.ascontiguousarray(spl.c)  # (n coef, n values)
+    nint = n - 3
+    lo = tk[3 : 3 + nint]
+    basis = np.zeros((nint, 4, 4))
+    from scipy.interpolate import BSpline
+
+    for r_abs in range(n):
+        e = np.zeros(n)
+        e[r_abs] = 1.0
+        pp = PPoly.from_spline(BSpline(tk, e, 3, extrapolate=True))
+        # pp.c[d', i] on breakpoints pp.x (with repeated end knots); map to our intervals
+        for j in range(nint):
+            r = r_abs - j
+            if 0 <= r <= 3:
+                i = j + 3  # knot interval index in pp
+                basis[j, r, :] = pp.c[::-1, i]
+    mu = np.linspace(0, 1, nbinsmu * accboost)
+    # np.trapz weights on the actual linspace values
+    d = np.diff(mu)
+    wt = np.zeros_like(mu)
+    wt[:-1] += 0.5 * d
+    wt[1:] += 0.5 * d
+    from scipy.special import eval_legendre
+
+    # 2 * trapz( (2l+1)/2 L_l(mu) * ... )   (pybird.py:1546-1548, :1595-1596)
+    wl = np.array([2.0 * wt * (2 * l + 1) / 2.0 * eval_legendre(l, mu) for l in 2 * np.arange(g.Nl)])
+    return dict(Cinv=Cinv, knot_lo=np.ascontiguousarray(lo), basis=np.ascontiguousarray(basis), mu=mu,
+                wl=np.ascontiguousarray(wl), nint=nint)
+
+
+# --------------------------------------------------------------------------------------------
+# window / ICC / binning / chained -> one projection matrix
+# --------------------------------------------------------------------------------------------
+def window_pgrid(kmax=0.3, accboost=1):
+    """window.py:27-33"""
+    return np.concatenate([np.geomspace(1e-5, 0.015, 100 * accboost, endpoint=False),
+                           np.arange(0.015, kmax, 1e-3 / accboost)])
+
+
+def window_effective_matrix(Wal, p, k, windowk=0.05, withmask=True):
+    """(Na, Nk, Nl, Nk) operator equal to mask + dp weights + cubic resampling + einsum of
+    `Window.integrWindow` (window.py:348-359, :371-387)."""
+    W = Wal
+    if withmask:
+        keep = (p[None, :] < k[:, None] + windowk) & (p[None, :] > k[:, None] - windowk)
+        W = Wal * keep[None, None]
+    dp = np.concatenate([[0.0], p[1:] - p[:-1]])
+    Waldk = W * dp
+    S = cubic_matrix(k, p)  # (Np, Nk)
+    return np.einsum("alkp,pn->akln", Waldk, S)
+
+
+def binning_matrix(k, kout, accboost=1, decimals=2, kedges=None):
+    """(nbin, Nk) operator of `Binning.integrBinning` and the effective k of each bin
+    (binning.py:100-144)."""
+    from scipy.integrate import quad
+
+    kout = np.asarray(kout, float)
+    if kedges is None:
+        dk = np.round(kout[-1] - kout[-2], decimals)
+        centre = (kout[-1] - dk * np.arange(len(kout)))[::-1]
+        bmin, bmax = centre - dk / 2, centre + dk / 2
+    else:
+        bmin, bmax = np.asarray(kedges[:-1], float), np.asarray(kedges[1:], float)
+    vol = np.array([quad(lambda x: x**2, a, b)[0] for a, b in zip(bmin, bmax)])
+    keff = np.array([quad(lambda x: x**3, a, b)[0] for a, b in zip(bmin, bmax)]) / vol
+    mat = np.zeros((len(bmin), len(k)))
+    for i, (a, b) in enumerate(zip(bmin, bmax)):
+        pts = np.linspace(a, b, 100 * accboost)
+        d = np.diff(pts)
+        wt = np.zeros_like(pts)
+        wt[:-1] += 0.5 * d
+        wt[1:] += 0.5 * d
+        mat[i] = (wt * pts**2) @ cubic_matrix(k, pts) / vol[i]
+    return mat, keff, bmin, bmax
+
+
+def chained_matrix(Nl):
+    """Q_l = P_l - A_l P_{l+2} (chained.py:13-54)."""
+    from scipy.special import eval_legendre
+
+    A = lambda l: ((2 * l + 1) * eval_legendre(l, 0.0)) / ((2 * l + 5) * eval_legendre(l + 2, 0.0))
+    m = np.zeros((Nl - 1, Nl))
+    for i in range(Nl - 1):
+        m[i, i] = 1.0
+        m[i, i + 1] = -A(2 * i)
+    return m
+
+
+# --------------------------------------------------------------------------------------------
+# assembled per-tracer plan (host arrays)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class TracerPlan:
+    """Host-side constants of one tracer's pipeline.  `upload()`-ed by `engine.Engine`."""
+
+    grid: GridConfig
+    kin: np.ndarray
+    Wf: np.ndarray
+    front: FrontLayout
+    front_aux: dict
+    pair_table: np.ndarray  # (npair, NCH) complex128
+    pair_offsets: np.ndarray  # (Nmax+2,) int32
+    Ak: np.ndarray  # (Nk, 2(Nmax+1))
+    As: np.ndarray  # (Nl, Ns, 2(Nmax+1))
+    resum: dict | None = None
+    ap: dict | None = None
+    ap_fid: tuple | None = None  # (DA_fid, H_fid)
+    ap_st: bool = False
+    project: np.ndarray | None = None  # (Nout, Nl*Nk)
+    project_st: bool = True  # apply the projection to the stochastic terms
+    picc_out: np.ndarray | None = None  # (Nout,)
+    out_shape: tuple | None = None  # (Nl_out, nk_out)
+    kout: np.ndarray | None = None
+
+    @property
+    def Nmax(self):
+        return self.grid.NFFT
+
+
+def build_tracer_plan(Nl=3, kmax=0.3, NFFT=256, with_NNLO=False, kin=None, window=0.2,
+                      with_resum=True, resum_NFFT=192, ap=None, projection=None):
+    """ap: None or dict(DA=, H=, nbinsmu=200, accboost=1, APst=False);
+    projection: None or dict(matrix=(Nout, Nl*Nk), picc=(Nout,), shape=(Nl_out, nk_out), kout=, st=True)."""
+    g = GridConfig(Nl=Nl, kmax=kmax, NFFT=NFFT, with_NNLO=with_NNLO)
+    kin = np.logspace(-5, 0, 200) if kin is None else np.asarray(kin, float)
+    fft = FFTLog(Nmax=NFFT, xmin=1.5e-5, xmax=1000.0, bias=-1.6)  # pybird.py:919
+    M22, M13 = loop_matrices(fft)
+    Wf, layout, aux = front_operator(kin, g, fft, M13, window=window)
+    table, offsets = antidiagonal_table(M22, M13)
+    Ak, As = spectral_matrices(fft, g)
+    plan = TracerPlan(grid=g, kin=kin, Wf=Wf, front=layout, front_aux=aux, pair_table=table,
+                      pair_offsets=offsets, Ak=Ak, As=As)
+    if with_resum:
+        plan.resum = resum_operator(g, NFFT=resum_NFFT)
+    if ap is not None:
+        plan.ap = ap_operator(g, nbinsmu=ap.get("nbinsmu", 200), accboost=ap.get("accboost", 1))
+        plan.ap_fid = (float(ap["DA"]), float(ap["H"]))
+        plan.ap_st = bool(ap.get("APst", False))
+    if projection is not None:
+        plan.project = np.ascontiguousarray(projection["matrix"], dtype=float)
+        plan.picc_out = np.ascontiguousarray(projection.get("picc", np.zeros(plan.project.shape[0])), dtype=float)
+        plan.out_shape = tuple(projection["shape"])
+        plan.kout = projection.get("kout")
+        plan.project_st = bool(projection.get("st", True))
+    return plan
+
+
+def compose_projection(g: GridConfig, window=None, icc=None, binning=None, chained=False, window_st=True):
+    """Compose window (+ICC), binning and chained mixing into one matrix on the Nl*Nk nodes.
+
+    window : None or (Na, Nk, Nl, Nk) effective matrix (`window_effective_matrix`)
+    icc    : None or dict(matrix=(Na,Nk,Nl,Nk), PSN_times_Pshot=(Na,Nk))    (window.py:393-405)
+    binning: None or (nbin, Nk) matrix (`binning_matrix`)
+    Returns dict(matrix=(Nout, Nl*Nk), picc=(Nout,), shape=(Nl_out, nk_out), st=window_st).
+    The stochastic terms see the same operator when `window_st` (reference default); the case
+    window_st=False with a window is handled by the caller building a second plan."""
+    Nl, Nk = g.Nl, g.Nk
+    op = np.eye(Nl * Nk).reshape(Nl, Nk, Nl, Nk)
+    picc = np.zeros((Nl, Nk))
+    if window is not None:
+        op = np.array(window, dtype=float)
+        if icc is not None:
+            op = op - icc["matrix"]
+            picc = picc - icc["PSN_times_Pshot"]
+    Na = op.shape[0]
+    if binning is not None:
+        op = np.einsum("bk,akln->abln", binning, op)
+        picc = picc @ binning.T
+    if chained:
+        cm = chained_matrix(Na)
+        op = np.einsum("ca,akln->ckln", cm, op)
+        picc = cm @ picc
+    shape = op.shape[:2]
+    return dict(matrix=op.reshape(shape[0] * shape[1], Nl * Nk), picc=picc.reshape(-1), shape=shape,
+                st=window_st)

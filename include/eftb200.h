@@ -1,0 +1,202 @@
+/*
+ * eftb200.h - C ABI of libeftb200.so, the sm_100a implementation of eftpipe's PyBird hot path.
+ *
+ * The reference (zhaoruiyang98/eftpipe) is pure Python and has NO FFI boundary for this path;
+ * its seams are Python protocols.  This header is therefore the boundary a
+ * maintainer would bind with ctypes; every entry point names the reference
+ * function(s) whose per-evaluation arithmetic it replaces (paths relative to eftpipe/).
+ *
+ * Conventions
+ *  - plain C, no torch types; all data pointers are DEVICE pointers owned by the caller unless a
+ *    parameter is documented as host memory; the library owns only the immutable plan constants.
+ *  - every call enqueues work on `stream` (a cudaStream_t passed as void*) and does not synchronise.
+ *  - return value: 0 on success, negative eftb_status on error (never throws, never aborts);
+ *    per-point numerical failures (non positive-definite F2) are reported in the `status` array.
+ *  - "batch-minor" arrays: logical shape [rows][Bp] with the cosmology index fastest and
+ *    Bp = eftb_padded_batch(B) (B rounded up to a multiple of 32; pad lanes replicate point B-1).
+ *  - all arithmetic is IEEE binary64.
+ */
+#ifndef EFTB200_H
+#define EFTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EFTB_ABI_VERSION 1
+
+typedef enum {
+  EFTB_OK = 0,
+  EFTB_ERR_ARG = -1,      /* NULL pointer / inconsistent sizes (reference: ValueError) */
+  EFTB_ERR_CUDA = -2,     /* CUDA runtime error, see eftb_last_error() */
+  EFTB_ERR_NOT_BUILT = -3,/* stage not present in this plan (e.g. AP requested, plan has none) */
+  EFTB_ERR_WORKSPACE = -4 /* workspace too small */
+} eftb_status;
+
+typedef struct eftb_plan eftb_plan; /* one tracer pipeline (pybird Common+NonLinear+Resum+APeffect+Window+Binning) */
+typedef struct eftb_like eftb_like; /* one likelihood (likelihood.py EFTLike + marginal.py) */
+
+/* ---- plan description (host memory) ------------------------------------------------------------ */
+typedef struct {
+  /* grids: pybird.Common (pybird/pybird.py:486-582) */
+  int32_t Nl, Nk, Ns, Nmax, nterm, with_nnlo;
+  /* front operator layout (eftpipe_b200/plan.py front_operator; fftlog.py:84-166, pybird.py:1316-1353) */
+  int32_t nin, ntail, ntailx, front_rows;
+  int32_t row_cre, row_cim, row_p11, row_p13, row_c11, row_cct, row_cctnnlo, row_x, row_y;
+  double inv_dlog, wx_last, wx_prev;
+  /* anti-diagonal pair table */
+  int32_t npair;
+  /* IR resummation (pybird.py:1174-1464) */
+  int32_t has_resum, NIR, Na, Nkr, Nklow, qdeg;
+  /* Alcock-Paczynski (pybird.py:1467-1628) */
+  int32_t has_ap, nmu, nint, ap_st;
+  double da_fid, h_fid;
+  /* window (+ICC) / binning / chained projection (window.py:371-415, icc.py:471-484,
+     binning.py:131-162, chained.py:32-68) */
+  int32_t has_project, nout, nl_out; /* nout = nl_out * nk_out */
+} eftb_config;
+
+typedef struct {
+  const double* k;          /* [Nk]                      co.k */
+  const double* l11;        /* [Nl][3]   pybird.py:570   */
+  const double* lct;        /* [Nl][6]   pybird.py:571   */
+  const double* lctnnlo;    /* [Nl][3]   pybird.py:572   */
+  const double* l22;        /* [Nl][28]  pybird.py:573-581 */
+  const double* l13;        /* [Nl][10]  pybird.py:582   */
+  const double* Wf;         /* [front_rows][nin+ntail+ntailx] */
+  const double* lr;         /* [ntail]  log(x_i/x_last) of the FFTLog-NFFT tail nodes */
+  const double* lrx;        /* [ntailx] same for the 32-point IR-filter FFTLog */
+  const double* pair_table; /* [npair][38][2] (re,im) */
+  const int32_t* pair_offsets; /* [Nmax+2] */
+  const double* Ak;         /* [Nk][2(Nmax+1)] */
+  const double* As;         /* [Nl][Ns][2(Nmax+1)] */
+  const double* R;          /* [Na][Nkr][Ns]              resum operator */
+  const double* q;          /* [2][Nl][Nl][2*NIR*Na][qdeg] Q^{ll'}(f) polynomial coefficients */
+  const double* kr2;        /* [Nkr] */
+  const double* Cinv;       /* [Nk][Nk]   B-spline collocation inverse */
+  const double* knot_lo;    /* [nint] */
+  const double* basis;      /* [nint][4][4] */
+  const double* mu;         /* [nmu] */
+  const double* wl;         /* [Nl][nmu]  2*trapz weight*(2l+1)/2*L_l(mu) */
+  const double* project;    /* [nout][Nl*Nk] */
+} eftb_constants;
+
+/* ---- library ----------------------------------------------------------------------------------- */
+int eftb_abi_version(void);
+const char* eftb_last_error(void);
+int eftb_padded_batch(int B);
+/* FP64 FMA-pipe peak probe: runs `iters` dependent-chain DFMA bundles on every SM and returns the
+   measured TFLOP/s through *tflops (synchronises; used by bench.py for the roofline denominator) */
+int eftb_probe_fp64(int iters, double* tflops, void* stream);
+
+/* ---- plan -------------------------------------------------------------------------------------- */
+int eftb_plan_create(const eftb_config* cfg, const eftb_constants* host_constants, eftb_plan** out);
+void eftb_plan_destroy(eftb_plan* plan);
+/* bytes of scratch `eftb_eval_terms` needs for a batch of B points */
+size_t eftb_workspace_bytes(const eftb_plan* plan, int B);
+
+/* ---- layout helpers ---------------------------------------------------------------------------- */
+/* out[r][Bp] (batch-minor) <- in[B][R] (point-major); pad lanes replicate point B-1 */
+int eftb_to_batch_minor(const double* in, int B, int R, double* out, void* stream);
+/* out[B][R] (point-major) <- in[perm ? perm[r] : r][Bp]; perm is a DEVICE int32 array or NULL */
+int eftb_to_point_major(const double* in, int B, int R, const int32_t* perm, double* out, void* stream);
+
+/* ---- stage entry points (batch-minor device arrays) ---------------------------------------------
+ * F    [front_rows][Bp]           front-end products: c_n (Hermitian half), P11, 13-loop, C11, Cct, X, Y
+ * D    [38][Nmax+1][2][Bp]        anti-diagonal sums of c_n c_m M_ch[n,m]
+ * P22  [28][Nk][Bp]               bird.P22          (pybird.py:1074-1078)
+ * Cs   [Nl][38][Ns][Bp]           bird.C22 (ch<28), bird.C13 (ch>=28), before Legendre weights
+ * T    [Nl][Nk][nterm][Bp]        term index: 0-2 P11l, 3-8 Pctl, 9-20 Ploopl, 21-23 Pstl, 24-26 PctNNLOl
+ * Cr   [Nl][ncr][Ns][Bp]          rows: C11, Cct, Cloopl x12 [, CctNNLO]; ncr = 14 + with_nnlo
+ */
+/* Bird.__init__ interpolation + FFTLog.Coef + IRFilters + makeP13/C11/Cct (pybird.py:694-695,
+   :1127-1141, :1080-1101, :1316-1353; fftlog.py:84-166).  plin: point-major [B][nin]. */
+int eftb_front(const eftb_plan*, int B, const double* plin, double* u_scratch, double* F, void* stream);
+/* the quadratic part of makeP22 / makeC22 / makeC13 (pybird.py:1074-1078, :1103-1125) */
+int eftb_antidiag(const eftb_plan*, int B, const double* F, double* D, void* stream);
+int eftb_spectral(const eftb_plan*, int B, const double* D, double* P22, double* Cs, void* stream);
+/* Bird.setPsCfl / reducePsCfl / setPstl / subtractShotNoise (pybird.py:737-866); f: [Bp] */
+int eftb_group(const eftb_plan*, int B, const double* F, const double* P22, const double* Cs,
+               const double* f, double* T, double* Cr, void* stream);
+/* Resum.Ps (pybird.py:1413-1464), in place on T */
+int eftb_resum(const eftb_plan*, int B, const double* F, const double* Cr, const double* f, double* T,
+               void* stream);
+/* APeffect.AP (pybird.py:1598-1621); DA,H: [Bp]; coef_scratch: [Nl][Nk][nterm][Bp]; Tout may not alias Tin */
+int eftb_ap(const eftb_plan*, int B, const double* Tin, const double* DA, const double* H,
+            double* coef_scratch, double* Tout, void* stream);
+/* Window.Window (+ICC) -> Binning.transform -> Chained.transform as one operator; out: [nout][nterm][Bp] */
+int eftb_project(const eftb_plan*, int B, const double* T, double* out, void* stream);
+
+/* ---- fused pipeline ------------------------------------------------------------------------------
+ * theory.py:557-609 `calculate_power_spectrum` for a batch: plin [B][nin], f/DA/H [B] (point-major,
+ * device).  Results (either may be NULL):
+ *   terms_bm : batch-minor, [nout][nterm][Bp] if the plan has a projection else [Nl][Nk][nterm][Bp]
+ *   terms_pm : point-major [B][Nl_out][nterm][nk_out] (the reference's Bird/PlainBird array order,
+ *              concatenated P11l|Pctl|Ploopl|Pstl[|PctNNLOl] along the term axis)
+ */
+int eftb_eval_terms(const eftb_plan*, int B, const double* plin, const double* f, const double* DA,
+                    const double* H, double* terms_bm, double* terms_pm, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ---- standalone fixed operators -------------------------------------------------------------------
+ * A single stage of the projection chain applied on its own (Window.integrWindow window.py:371-387,
+ * IntegralConstraint.integrWindow icc.py:471-484, Binning.integrBinning binning.py:131-144,
+ * Chained.transform chained.py:56-68): C[M][N] = A[M][K] X[K][N] with X, C batch-minor, N % 32 == 0. */
+typedef struct eftb_operator eftb_operator;
+int eftb_operator_create(int M, int K, const double* host_matrix, eftb_operator** out);
+void eftb_operator_destroy(eftb_operator*);
+int eftb_operator_apply(const eftb_operator*, const double* X, double* C, int N, void* stream);
+
+/* ---- likelihood (parambasis.py:42-136,:249-316; likelihood.py:483-594; marginal.py:79-196) ------- */
+typedef struct {
+  int32_t ntracer, ndata, ngauss, npar, jeffreys;
+} eftb_like_config;
+
+typedef struct {
+  /* per tracer */
+  const int32_t* nout;        /* [ntracer] rows of that tracer's projected terms */
+  const int32_t* nterm;       /* [ntracer] */
+  const double* scales;       /* [ntracer][6] kmA, krA, ndA, kmB, krB, ndB (parambasis.py:68-75) */
+  const int32_t* par_index;   /* [ntracer][17] columns of the nuisance array holding
+                                 b1A,b2A,b3A,b4A,cctA,cr1A,cr2A, b1B..cr2B, ce0,cemono,cequad; -1 = 0.0 */
+  const int32_t* eastcoast;   /* [ntracer] counterform flag (parambasis.py:102) */
+  /* per data point */
+  const int32_t* d_tracer;    /* [ndata] */
+  const int32_t* d_row;       /* [ndata] row of the tracer's projected terms */
+  const double* data;         /* [ndata] */
+  const double* picc;         /* [ndata] constant integral-constraint contribution */
+  const double* invcov;       /* [ndata][ndata] */
+  /* gaussian (marginalised) parameters: dP/dg = c1*v1*term[i1] + c2*v2*term[i2] on tracer g_tracer,
+     v in {0: 1, 1: b1A, 2: b1B, 3: f} (parambasis.py:249-316) */
+  const int32_t* g_count;     /* [ngauss] number of (tracer) entries, <= 2 */
+  const int32_t* g_tracer;    /* [ngauss][2] */
+  const int32_t* g_term;      /* [ngauss][2][2] */
+  const int32_t* g_var;       /* [ngauss][2][2] */
+  const double* g_coef;       /* [ngauss][2][2] */
+  const double* sigma_inv;    /* [ngauss][ngauss]  (marginal.py:69-77) */
+  const double* sigma_inv_mu; /* [ngauss] */
+  double mu_sigma_mu;
+} eftb_like_constants;
+
+int eftb_like_create(const eftb_like_config*, const eftb_like_constants* host, eftb_like** out);
+void eftb_like_destroy(eftb_like*);
+size_t eftb_like_workspace_bytes(const eftb_like*, int B);
+/* terms[t]: batch-minor projected terms of tracer t ([nout_t][nterm_t][Bp]); fgrowth[t]: [Bp];
+ * nuis: batch-minor [npar][Bp].  Outputs (device, [B]): logp, chi2-like pieces and status
+ * (0 ok, 1 = F2 not positive definite -> logp = -inf; marginal.py:113-116 raises there).
+ * bestfit (optional, point-major [B][ngauss]) = F2^-1 F1 (marginal.py:117). */
+int eftb_like_eval(const eftb_like*, int B, const double* const* terms, const double* const* fgrowth,
+                   const double* nuis, double* logp, double* bestfit, int32_t* status, void* workspace,
+                   size_t workspace_bytes, void* stream);
+/* un-marginalised pieces for parity tests: vec [B][ndata][ngauss+1] (point-major) with
+ * vec[.,d,0] = PNG[d] - data[d] (likelihood.py:528-549) and vec[.,d,1+g] = PG[g][d] (likelihood.py:483-525) */
+int eftb_like_vectors(const eftb_like*, int B, const double* const* terms, const double* const* fgrowth,
+                      const double* nuis, double* vec, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFTB200_H */
