@@ -105,14 +105,14 @@ __global__ void __launch_bounds__(128) like_vectors_kernel(VecArgs a) {
   const int nc = a.ngauss + 1;
   double* out = a.V + ((size_t)d * nc) * Bp + b;
   out[0] = (plin + ploop + pct + pst + a.picc[d]) - a.data[d];
-  const double vars[4] = {1.0, b1A, b1B, f};
+  const double vars[5] = {1.0, b1A, b1B, f, f * f};
   for (int g = 0; g < a.ngauss; ++g) {
     double v = 0.0;
     for (int e = 0; e < a.g_count[g]; ++e) {
       if (a.g_tracer[g * 2 + e] != tr) continue;
-      const int base = (g * 2 + e) * 2;
+      const int base = (g * 2 + e) * 3;
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < 3; ++q) {
         const double c = a.g_coef[base + q];
         if (c != 0.0) v += c * vars[a.g_var[base + q]] * term[(size_t)a.g_term[base + q] * Bp];
       }
@@ -260,9 +260,9 @@ int eftb_like_create(const eftb_like_config* cfg, const eftb_like_constants* h, 
   rc |= gemm_upload(h->invcov, 1, nd, nd, &L->invcov);
   rc |= upload(&L->g_count, h->g_count, ng);
   rc |= upload(&L->g_tracer, h->g_tracer, (size_t)ng * 2);
-  rc |= upload(&L->g_term, h->g_term, (size_t)ng * 4);
-  rc |= upload(&L->g_var, h->g_var, (size_t)ng * 4);
-  rc |= upload(&L->g_coef, h->g_coef, (size_t)ng * 4);
+  rc |= upload(&L->g_term, h->g_term, (size_t)ng * 6);
+  rc |= upload(&L->g_var, h->g_var, (size_t)ng * 6);
+  rc |= upload(&L->g_coef, h->g_coef, (size_t)ng * 6);
   rc |= upload(&L->sigma_inv, h->sigma_inv, (size_t)ng * ng);
   rc |= upload(&L->sigma_inv_mu, h->sigma_inv_mu, ng);
   L->mu_sigma_mu = h->mu_sigma_mu;

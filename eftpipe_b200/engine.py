@@ -217,9 +217,9 @@ class DeviceLikelihood:
         cst.data, cst.picc, cst.invcov = dp(spec["data"]), dp(spec["picc"]), dp(spec["invcov"])
         ng = max(spec["ngauss"], 1)
         cst.g_count, cst.g_tracer = ip(spec["g_count"] if spec["ngauss"] else np.zeros(1)), ip(spec["g_tracer"] if spec["ngauss"] else np.zeros(2))
-        cst.g_term = ip(spec["g_term"] if spec["ngauss"] else np.zeros(4))
-        cst.g_var = ip(spec["g_var"] if spec["ngauss"] else np.zeros(4))
-        cst.g_coef = dp(spec["g_coef"] if spec["ngauss"] else np.zeros(4))
+        cst.g_term = ip(spec["g_term"] if spec["ngauss"] else np.zeros(6))
+        cst.g_var = ip(spec["g_var"] if spec["ngauss"] else np.zeros(6))
+        cst.g_coef = dp(spec["g_coef"] if spec["ngauss"] else np.zeros(6))
         cst.sigma_inv = dp(spec["sigma_inv"] if spec["ngauss"] else np.zeros((ng, ng)))
         cst.sigma_inv_mu = dp(spec["sigma_inv_mu"] if spec["ngauss"] else np.zeros(ng))
         cst.mu_sigma_mu = float(spec["mu_sigma_mu"])

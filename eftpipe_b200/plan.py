@@ -388,13 +388,13 @@ class TracerPlan:
 
 
 def build_tracer_plan(Nl=3, kmax=0.3, NFFT=256, with_NNLO=False, kin=None, window=0.2,
-                      with_resum=True, resum_NFFT=192, ap=None, projection=None):
+                      with_resum=True, resum_NFFT=192, ap=None, projection=None, loop_cache=None):
     """ap: None or dict(DA=, H=, nbinsmu=200, accboost=1, APst=False);
     projection: None or dict(matrix=(Nout, Nl*Nk), picc=(Nout,), shape=(Nl_out, nk_out), kout=, st=True)."""
     g = GridConfig(Nl=Nl, kmax=kmax, NFFT=NFFT, with_NNLO=with_NNLO)
     kin = np.logspace(-5, 0, 200) if kin is None else np.asarray(kin, float)
     fft = FFTLog(Nmax=NFFT, xmin=1.5e-5, xmax=1000.0, bias=-1.6)  # pybird.py:919
-    M22, M13 = loop_matrices(fft)
+    M22, M13 = loop_cache if loop_cache is not None else loop_matrices(fft)
     Wf, layout, aux = front_operator(kin, g, fft, M13, window=window)
     table, offsets = antidiagonal_table(M22, M13)
     Ak, As = spectral_matrices(fft, g)

@@ -1,0 +1,185 @@
+"""Batched theory driver - the numeric content of `eftpipe.theory.EFTLSS / EFTLeafKernel / EFTLeaf`
+(theory.py:116-886) without the Cobaya plumbing: same per-tracer configuration keys (theory.py:356-388,
+eftlss.yaml), same `default` block deep-merge (theory.py:133-138), same stage order
+(`calculate_power_spectrum`, theory.py:557-609), same product getters (theory.py:244-267), for a batch of
+points per call.  Cobaya's `Theory` protocol cannot be exercised in this image (no cobaya); INTEGRATION.md
+shows the thin adapter a maintainer adds on top of this class.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+
+import numpy as np
+
+from . import plan as P
+from .binning import Binning
+from .engine import DevicePlan
+from .icc import IntegralConstraint
+from .marginal import LoggedError
+from .parambasis import find_param_basis
+from .pybird import APeffect, Common, DAfunc, Hubble
+from .window import Window
+
+_KNOWN = {"prefix", "z", "nd", "km", "kr", "cross", "provider", "use_cb", "with_IRresum", "with_APeffect",
+          "with_window", "with_fiber", "with_NNLO", "with_RSD", "kmax", "IRresum", "APeffect", "window", "icc",
+          "binning", "basis", "chained", "ls", "Nl"}
+
+
+def _merge(default, cfg):
+    out = deepcopy(default)
+    for k, v in cfg.items():
+        if isinstance(v, dict) and isinstance(out.get(k), dict):
+            out[k] = _merge(out[k], v)
+        else:
+            out[k] = deepcopy(v)
+    return out
+
+
+class EFTLSS:
+    def __init__(self, tracers: dict, cache_dir_path=None):
+        tracers = deepcopy(tracers)
+        default = tracers.pop("default", {})
+        self.tracers = {name: _merge(default, cfg or {}) for name, cfg in tracers.items()}
+        for name, cfg in self.tracers.items():
+            unknown = set(cfg) - _KNOWN
+            if unknown:
+                raise LoggedError(f"tracer {name}: unknown configuration keys {sorted(unknown)}")
+            if cfg.get("with_fiber"):
+                raise NotImplementedError("fibre-collision correction is not part of this build (SURVEY 8f #1)")
+        self.cache_dir_path = cache_dir_path
+        self.requirements = {}
+        self.bases, self.commons, self.plans, self.info = {}, {}, {}, {}
+        self._state = {}
+        self.B = 0
+
+    # ---- requirements (theory.py:773-799) ----
+    def must_provide(self, requirements: dict):
+        for product, per_tracer in requirements.items():
+            if product not in ("nonlinear_Plk_grid", "nonlinear_Plk_gaussian_grid"):
+                raise LoggedError(f"unsupported requirement {product} on the batched path")
+            for tracer, req in per_tracer.items():
+                if tracer not in self.tracers:
+                    raise LoggedError(f"unknown tracer {tracer}")
+                old = self.requirements.get(tracer)
+                new = dict(ls=sorted(req["ls"]), chained=bool(req.get("chained", False)),
+                           binned=bool(req.get("binned", False)), binning=req.get("binning"))
+                if old is not None and (old["ls"], old["chained"], old["binned"]) != (new["ls"], new["chained"], new["binned"]):
+                    raise LoggedError("does not support multiple different product requirements per tracer")
+                self.requirements[tracer] = new
+        return self
+
+    # ---- plan construction (theory.py:399-495) ----
+    def _scales(self, name):
+        """kmA, krA, ndA, kmB, krB, ndB (theory.py:663-699)."""
+        cfg = self.tracers[name]
+        cross = cfg.get("cross")
+        def own(c):
+            try:
+                km, nd = c["km"], c["nd"]
+            except KeyError:
+                raise LoggedError("must specify km, kr and nd")
+            return km, c.get("kr") or km, nd
+        if isinstance(cross, (list, tuple)):
+            a, b = (self.tracers[t] for t in cross)
+            return own(a) + own(b)
+        return own(cfg) + own(cfg)
+
+    def initialize(self):
+        for name, cfg in self.tracers.items():
+            req = self.requirements.get(name)
+            if req is None:
+                continue
+            ls = req["ls"]
+            No = max(ls) // 2 + 1 + (1 if req["chained"] else 0)
+            Nl = max(cfg.get("Nl", No), No)
+            kmA, krA, ndA, kmB, krB, ndB = self._scales(name)
+            basis_cls = find_param_basis(cfg.get("basis", "westcoast"))
+            cross = cfg.get("cross")
+            cross_prefix = [self.tracers[t]["prefix"] for t in cross] if isinstance(cross, (list, tuple)) else []
+            basis = basis_cls(prefix=cfg.get("prefix", ""), cross_prefix=cross_prefix)
+            co = Common(Nl=Nl, No=No, kmax=cfg.get("kmax", 0.3), kmA=kmA, krA=krA, ndA=ndA, kmB=kmB, krB=krB, ndB=ndB,
+                        counterform=basis.counterform(), with_NNLO=bool(cfg.get("with_NNLO", False)))
+            ap = None
+            if cfg.get("with_APeffect"):
+                apc = dict(cfg.get("APeffect") or {})
+                apc.setdefault("z_AP", cfg["z"])  # theory.py:458: z_AP defaults to the tracer's z
+                apo = APeffect(co=Common(Nl=Nl), **apc)
+                ap = dict(DA=apo.DA, H=apo.H, nbinsmu=apc.get("nbinsmu", 200), accboost=apc.get("accboost", 1), APst=apo.APst)
+                self.info.setdefault(name, {})["ap"] = apo
+            window = icc = None
+            if cfg.get("with_window"):
+                wc = dict(cfg.get("window") or {})
+                if cfg.get("icc"):
+                    icc = IntegralConstraint(co=co, **cfg["icc"])
+                window = Window(co=co, icc=icc, **wc)
+            binm = None
+            keff = co.k
+            if req["binned"]:
+                bo = Binning(co=co, **(req["binning"] or cfg.get("binning") or {}))
+                binm, keff = bo.matrix, bo.keff
+            g = P.GridConfig(Nl=Nl, kmax=cfg.get("kmax", 0.3), with_NNLO=co.with_NNLO)
+            proj = None
+            if window is not None or binm is not None or req["chained"]:
+                proj = P.compose_projection(
+                    g, window=None if window is None else window_matrix(window),
+                    icc=None if icc is None else dict(matrix=icc.effective_matrix(), PSN_times_Pshot=icc.PSN),
+                    binning=binm, chained=req["chained"], window_st=True if window is None else window.window_st)
+                proj["kout"] = keff
+            rs = cfg.get("IRresum") or {}
+            host = P.build_tracer_plan(Nl=Nl, kmax=cfg.get("kmax", 0.3), with_NNLO=co.with_NNLO,
+                                       with_resum=bool(cfg.get("with_IRresum", True)), resum_NFFT=rs.get("NFFT", 192),
+                                       ap=ap, projection=proj)
+            self.bases[name], self.commons[name] = basis, co
+            self.plans[name] = DevicePlan(host)
+            nl_out, nk = host.out_shape if proj is not None else (Nl, g.Nk)
+            picc = host.picc_out if proj is not None else np.zeros(Nl * g.Nk)
+            self.info.setdefault(name, {}).update(nout=nl_out * nk, nterm=g.nterm, nk=nk, picc=picc, kout=keff,
+                                                  ls=[2 * i for i in range(nl_out)], No=No)
+        return self
+
+    def product_info(self, tracer, chained=False, binned=True):
+        return self.info[tracer]
+
+    # ---- per batch (theory.py:557-609) ----
+    def calculate(self, cosmo: dict):
+        """cosmo[tracer] = dict(pkh=(B, 200) on kh = logspace(-5, 0, 200), f=, DA=, H= (B,) [, rdrag, h])."""
+        self._state = {}
+        for name, dp in self.plans.items():
+            c = cosmo[name]
+            pm, bm = dp.eval_terms(c["pkh"], c["f"], c.get("DA"), c.get("H"), want_bm=True, want_pm=False)
+            f_bm = dp.to_batch_minor(c["f"])[0]
+            self._state[name] = (bm, f_bm)
+            self.B = bm.shape[-1] if not hasattr(c["pkh"], "shape") else c["pkh"].shape[0]
+        return self
+
+    def get_nonlinear_Plk_terms(self, tracer, chained=False, binned=True):
+        return self._state[tracer]
+
+    def get_nonlinear_Plk_grid(self, tracer, params, chained=False, binned=True):
+        """(ls, k, Plk (B, No, nk)) - theory.py:244-252 + EFTLeaf reduction (theory.py:846-860)."""
+        bird = self._view(tracer)
+        comp = self.bases[tracer].reduce_Plk(bird, params)
+        info = self.info[tracer]
+        return info["ls"], info["kout"], comp.sum()
+
+    def get_nonlinear_Plk_gaussian_grid(self, tracer, params, chained=False, binned=True):
+        bird = self._view(tracer)
+        info = self.info[tracer]
+        return info["ls"], info["kout"], self.bases[tracer].reduce_Plk_gaussian_table(bird, params)
+
+    def _view(self, tracer):
+        from .transformer import PlainBird
+
+        bm, f_bm = self._state[tracer]
+        info = self.info[tracer]
+        nl_out = len(info["ls"])
+        T = bm.reshape(nl_out, info["nk"], info["nterm"], bm.shape[-1])
+        co = self.commons[tracer]
+        view = PlainBird(None, co, T, np.asarray(info["picc"]).reshape(nl_out, info["nk"]), self.B, False, f_bm)
+        # the reduction honours co.No: chained products expose one multipole fewer (theory.py:599-602)
+        return view
+
+
+def window_matrix(window: Window):
+    """effective matrix WITHOUT the ICC part (compose_projection subtracts it)."""
+    return P.window_effective_matrix(window.Wal, window.p, window.co.k, windowk=window.windowk, withmask=window.withmask)

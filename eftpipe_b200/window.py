@@ -1,0 +1,189 @@
+"""Survey window convolution - mirror of `eftpipe.window.Window` (window.py:40-415).
+
+Precompute (host, once per plan; same cache files as the reference: `<window_fourier_file>.npy` + a
+`.json` meta sidecar with strict equality check, window.py:204-260, :361-369):
+    Wal[a, l, k, p] = p^2 Re sum_n Coef[a,l,k,n] p^{-eta_n - 3} M[l,n]      (window.py:262-346)
+from the configuration-space multipoles Q_q(s) through a 4096-point FFTLog with a spherical-Bessel
+kernel.  Per evaluation the reference resamples every term onto the p grid with a cubic spline and
+contracts with `Waldk` (window.py:371-387); for the fixed internal nodes that is one fixed real matrix
+on the Nl*Nk nodes (`effective_matrix`), which the CUDA path applies as a DMMA GEMM over the batch.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+from scipy.special import spherical_jn
+
+from . import tables
+from .fftlog import FFTLog
+from .plan import window_effective_matrix, window_pgrid
+
+window_kgrid = window_pgrid  # reference name (window.py:27)
+
+
+class MetaInfoError(Exception):
+    pass
+
+
+# (2a+1) (a l q; 0 0 0)^2 coupling of window multipoles (window.py:286-303), indices a, l, q in units of 2
+_CALQ = np.array([
+    [[1, 0, 0, 0], [0, 1 / 5, 0, 0], [0, 0, 1 / 9, 0], [0, 0, 0, 1 / 13]],
+    [[0, 1, 0, 0], [1, 2 / 7, 2 / 7, 0], [0, 2 / 7, 100 / 693, 25 / 143], [0, 0, 25 / 143, 14 / 143]],
+    [[0, 0, 1, 0], [0, 18 / 35, 20 / 77, 45 / 143], [1, 20 / 77, 162 / 1001, 20 / 143],
+     [0, 45 / 143, 20 / 143, 252 / 2431]],
+    [[0, 0, 0, 1], [0, 0, 5 / 11, 14 / 55], [0, 5 / 11, 20 / 99, 28 / 187], [1, 14 / 55, 28 / 187, 400 / 3553]],
+])
+
+
+def compute_Wal(s_Q, k, Na, Nl, Nq=3, pmax=None, accboost=1, Nmax=4096, xmin_factor=1.0, xmax_factor=100.0,
+                bias=-1.6, window_param=1):
+    """Fourier-space window matrix (window.py:262-346).  s_Q: (ns, 1+nq) columns s, Q0, Q2, ..."""
+    k = np.asarray(k, float)
+    pmax = float(k.max()) if pmax is None else pmax
+    p = window_pgrid(pmax, accboost)
+    tab = np.asarray(s_Q, float)
+    while tab[0, 0] == 0.0:  # remove s = 0 (window.py:275-276)
+        tab = tab[1:]
+    tab = tab[:, : 1 + Nq]
+    sw, Qq = tab[:, 0], tab[:, 1:].T
+    Qal = np.einsum("alq,qs->als", _CALQ[..., :Nq], Qq)[:Na, :Nl]
+    fft = FFTLog(Nmax=Nmax, xmin=sw[0] * xmin_factor, xmax=sw[-1] * xmax_factor, bias=bias)
+    pPow = np.exp(np.outer(-fft.Pow - 3.0, np.log(p)))
+    M = np.array([4 * np.pi * tables.bessel_power(2 * l, -0.5 * fft.Pow) for l in range(Nl)])
+    Wal = np.empty((Na, Nl, k.size, p.size))
+    for a in range(Na):  # one output multipole at a time keeps the (k, n, p) work arrays small
+        kern = lambda x, a=a: spherical_jn(2 * a, x[None, None, :] * k[None, :, None])
+        coef = fft.coef_host(sw, Qal[a][:, None, :], extrap="padding", window=window_param, kernel=kern)
+        phase = ((-1j) ** (2 * a)) * ((1j) ** (2 * np.arange(Nl)))[:, None, None]
+        coef = phase * coef  # (Nl, Nk, N)
+        Wal[a] = p**2 * np.real(np.einsum("lkn,np,ln->lkp", coef, pPow, M))
+    return Wal, p
+
+
+class Window:
+    """Same constructor keywords, cache files and errors as the reference class."""
+
+    def __init__(self, window_fourier_file=None, window_configspace_file=None, co=None, load=True, save=True,
+                 check_meta=True, Na=None, Nl=None, Nq=3, pmax=None, accboost=1, withmask=True, windowk=0.05,
+                 Nmax=4096, xmin_factor=1.0, xmax_factor=100.0, bias=-1.6, window_param=1, window_st=True,
+                 icc=None, name="pybird.window", snapshot=False, window_configspace_array=None):
+        from .pybird import common
+
+        self.co = co if co is not None else common
+        if window_fourier_file is None and window_configspace_file is None and window_configspace_array is None:
+            raise ValueError("Window requires window_fourier_file or window_configspace_file or both")
+        self.window_fourier_file = Path(window_fourier_file).resolve() if window_fourier_file else None
+        self.window_configspace_file = Path(window_configspace_file).resolve() if window_configspace_file else None
+        self._array = window_configspace_array
+        self._load = load
+        self._save = save if self.window_fourier_file else False
+        self.check_meta = check_meta
+        self._create_meta = True
+        self.window_st, self.withmask, self.windowk = window_st, withmask, windowk
+        Na = Na if Na else self.co.Nl
+        Nl = Nl if Nl else self.co.Nl
+        if Na > self.co.Nl or Nl > self.co.Nl:
+            raise ValueError(f"request Na={Na}, Nl={Nl} while bird only compute Nl up to {self.co.Nl}")
+        if Na > Nl:
+            raise ValueError(f"dangerous settings Na={Na}, Nl={Nl}")
+        if pmax is None:
+            pmax = float(self.co.k.max())
+        self.p = window_pgrid(kmax=pmax, accboost=accboost)
+        self.meta = dict(Na=Na, Nl=Nl, Nq=Nq, pmax=pmax, accboost=accboost, Nmax=Nmax, xmin_factor=xmin_factor,
+                         xmax_factor=xmax_factor, bias=bias, window_param=window_param,
+                         window_configspace_file=str(self.window_configspace_file) if self.window_configspace_file else None,
+                         k=self.co.k.tolist())
+        self.Wal = self._load_Wal()
+        if self.Wal is None:
+            self.Wal = self._compute_Wal()
+        if self._save:
+            self._save_Wal()
+        self.icc = icc
+        self.snapshot = snapshot
+        self._op = None
+
+    # ---- cache handling (window.py:204-260, :361-369) ----
+    def _load_Wal(self):
+        Wal, path = None, self.window_fourier_file
+        if self._load and path is not None:
+            try:
+                Wal = np.load(path)
+            except (OSError, TypeError):
+                Wal = None
+            else:
+                if Wal.shape[1] != self.meta["Nl"]:
+                    Wal = None
+                    self.window_fourier_file = path = path.with_name(path.stem + f'_Nl{self.meta["Nl"]}.npy')
+                    try:
+                        Wal = np.load(path)
+                    except OSError:
+                        Wal = None
+            if Wal is not None and self.check_meta:
+                meta_file = path.with_suffix(".json")
+                if not meta_file.exists():
+                    self._create_meta = False
+                else:
+                    with meta_file.open("r") as fh:
+                        meta = json.load(fh)
+                    if self.meta["window_configspace_file"] is None:
+                        self.meta["window_configspace_file"] = meta["window_configspace_file"]
+                    if meta != self.meta:
+                        raise MetaInfoError(f"inconsistent meta info\nloaded matrix's meta:\n{meta}\nexpect:\n{self.meta}")
+        if Wal is not None:
+            self._save = False
+        return Wal
+
+    def _compute_Wal(self):
+        if self._array is not None:
+            tab = np.asarray(self._array, float)
+        else:
+            if self.window_configspace_file is None:
+                raise ValueError("please specify a configuration space mask file")
+            try:
+                tab = np.loadtxt(self.window_configspace_file)
+            except OSError:
+                raise OSError(f"Error: can't load mask file: {self.window_configspace_file}")
+        m = self.meta
+        Wal, _ = compute_Wal(tab, self.co.k, m["Na"], m["Nl"], Nq=m["Nq"], pmax=m["pmax"], accboost=m["accboost"],
+                             Nmax=m["Nmax"], xmin_factor=m["xmin_factor"], xmax_factor=m["xmax_factor"], bias=m["bias"],
+                             window_param=m["window_param"])
+        return Wal
+
+    def _save_Wal(self):
+        np.save(self.window_fourier_file, self.Wal)
+        if self._create_meta:
+            with self.window_fourier_file.with_suffix(".json").open("w") as fh:
+                json.dump(self.meta, fh, indent=2)
+
+    # ---- operators ----
+    @property
+    def Waldk(self):
+        """Masked, dp-weighted matrix (window.py:348-359)."""
+        W = self.Wal
+        if self.withmask:
+            keep = (self.p[None, :] < self.co.k[:, None] + self.windowk) & (self.p[None, :] > self.co.k[:, None] - self.windowk)
+            W = W * keep[None, None]
+        return W * np.concatenate([[0.0], self.p[1:] - self.p[:-1]])
+
+    def effective_matrix(self):
+        """(Na, Nk, Nl, Nk): `integrWindow` on the internal nodes; ICC subtracted when attached
+        (window.py:393-404)."""
+        op = window_effective_matrix(self.Wal, self.p, self.co.k, windowk=self.windowk, withmask=self.withmask)
+        if self.icc is not None:
+            op = op - self.icc.effective_matrix()
+        return op
+
+    def Window(self, bird):
+        """Apply the window (and ICC) to a batched Bird in place (window.py:389-415)."""
+        from .pybird import apply_node_operator
+
+        if self._op is None:
+            op = self.effective_matrix()
+            self._op = (np.ascontiguousarray(op.reshape(op.shape[0] * op.shape[1], -1)), op.shape[0])
+        apply_node_operator(bird, self._op[0], self._op[1], stochastic=self.window_st, cache_owner=self)
+        if self.icc is not None:
+            bird.add_Picc(-self.icc.PSN)  # window.py:405
+        if self.snapshot:
+            bird.create_snapshot("window")

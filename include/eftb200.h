@@ -169,13 +169,13 @@ typedef struct {
   const double* data;         /* [ndata] */
   const double* picc;         /* [ndata] constant integral-constraint contribution */
   const double* invcov;       /* [ndata][ndata] */
-  /* gaussian (marginalised) parameters: dP/dg = c1*v1*term[i1] + c2*v2*term[i2] on tracer g_tracer,
-     v in {0: 1, 1: b1A, 2: b1B, 3: f} (parambasis.py:249-316) */
+  /* gaussian (marginalised) parameters: dP/dg = sum_{q<3} c_q * v_q * term[i_q] on tracer g_tracer,
+     v in {0: 1, 1: b1A, 2: b1B, 3: f, 4: f^2} (parambasis.py:249-316, :403-454) */
   const int32_t* g_count;     /* [ngauss] number of (tracer) entries, <= 2 */
   const int32_t* g_tracer;    /* [ngauss][2] */
-  const int32_t* g_term;      /* [ngauss][2][2] */
-  const int32_t* g_var;       /* [ngauss][2][2] */
-  const double* g_coef;       /* [ngauss][2][2] */
+  const int32_t* g_term;      /* [ngauss][2][3] */
+  const int32_t* g_var;       /* [ngauss][2][3] */
+  const double* g_coef;       /* [ngauss][2][3] (0 = unused slot) */
   const double* sigma_inv;    /* [ngauss][ngauss]  (marginal.py:69-77) */
   const double* sigma_inv_mu; /* [ngauss] */
   double mu_sigma_mu;

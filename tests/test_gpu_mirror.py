@@ -1,0 +1,294 @@
+"""GPU: the reference-shaped host API (Common / Bird / NonLinear / Resum / APeffect / Window /
+IntegralConstraint / Binning / Chained / WestCoastBasis / EFTLSS / EFTLike) driven exactly like the
+reference's own call sequence (theory.py:557-609), against goldens and the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rowmax_rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "eftpipe_b200", "data", "dr16_ngc.npz")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def dr16():
+    return dict(np.load(DATA))
+
+
+@pytest.fixture(scope="module")
+def chain(golden2, dr16):
+    from eftpipe_b200 import binning, chained, icc, pybird, window
+
+    g = golden2
+    co = pybird.Common(**json.loads(str(g["common"])))
+    nl = pybird.NonLinear(load=False, save=False, co=co)
+    rs = pybird.Resum(co=co)
+    ap = pybird.APeffect(co=co, **json.loads(str(g["ap"])))
+    win = window.Window(window_configspace_array=dr16["win_LRG"], co=co, accboost=4, windowk=0.1)
+    ic = icc.IntegralConstraint(Pshot=float(g["Pshot"]), PSN=g["PSN"], Wal=0.05 * win.Wal, co=co, accboost=4, windowk=0.1)
+    win.icc = ic
+    bird = pybird.Bird(g["kin"], g["plin"], g["f"], g["DA"], g["H"], float(g["z"]), co=co)
+    out = {}
+    nl.PsCf(bird)
+    out.update(P11=_np(bird.P11), P22=_np(bird.P22), P13=_np(bird.P13), C11=_np(bird.C11), Cct=_np(bird.Cct),
+               C22=_np(bird.C22), C13=_np(bird.C13))
+    bird.setPsCfl()
+    out.update({"pre_" + n: _np(getattr(bird, n)) for n in ("P11l", "Pctl", "Ploopl", "Pstl", "Cloopl")})
+    rs.Ps(bird)
+    out.update({"res_" + n: _np(getattr(bird, n)) for n in ("P11l", "Pctl", "Ploopl")})
+    ap.AP(bird)
+    out.update({"ap_" + n: _np(getattr(bird, n)) for n in ("P11l", "Pctl", "Ploopl", "Pstl")})
+    win.Window(bird)
+    out.update({"win_" + n: _np(getattr(bird, n)) for n in ("P11l", "Pctl", "Ploopl", "Pstl", "Picc")})
+    binned = binning.Binning(g["kout"], co=co).transform(bird)
+    out.update({"bin_" + n: _np(getattr(binned, n)) for n in ("P11l", "Pctl", "Ploopl", "Pstl", "Picc")})
+    ch = chained.Chained().transform(binned)
+    out.update({"chn_" + n: _np(getattr(ch, n)) for n in ("P11l", "Pctl", "Ploopl", "Pstl", "Picc")})
+    return dict(out=out, binned=binned, chained=ch, co=co, bird=bird)
+
+
+def test_reference_call_sequence_matches_goldens(chain, golden2):
+    for key, got in chain["out"].items():
+        assert got.shape == golden2[key].shape, key
+        assert rowmax_rel(got, golden2[key]) <= TOL, key
+
+
+def test_unbatched_bird_keeps_reference_shapes(golden2):
+    from eftpipe_b200 import pybird
+
+    g = golden2
+    co = pybird.Common(Nl=3)
+    nl, rs = pybird.NonLinear(load=False, save=False, co=co), pybird.Resum(co=co)
+    bird = pybird.Bird(g["kin"], g["plin"][0], float(g["f"][0]), co=co)
+    nl.PsCf(bird)
+    bird.setPsCfl()
+    rs.Ps(bird)
+    assert tuple(bird.Ploopl.shape) == (3, 12, 50) and tuple(bird.P22.shape) == (28, 50)
+    assert rowmax_rel(_np(bird.Ploopl), g["res_Ploopl"][0]) <= TOL
+    with pytest.raises(RuntimeError):
+        pybird.Bird(g["kin"], g["plin"][0], 0.8, co=pybird.Common(Nl=3)).setPsCfl()
+
+
+def _params(nuis_row):
+    from eftpipe_b200 import synthetic
+
+    b1, c2, b3, c4, cct, cr1, cr2, ce0, cemono, cequad = nuis_row.T
+    b2, b4 = synthetic.c2c4_to_b2b4(c2, c4)
+    return dict(b1=b1, b2=b2, b3=b3, b4=b4, cct=cct, cr1=cr1, cr2=cr2, ce0=ce0, cemono=cemono, cequad=cequad)
+
+
+def test_bias_reduction_and_gaussian_table(chain, golden2):
+    from eftpipe_b200 import parambasis
+
+    basis = parambasis.WestCoastBasis(prefix="")
+    params = _params(golden2["nuisance"])
+    got = _np(basis.reduce_Plk(chain["binned"], params).sum())
+    assert rowmax_rel(got, golden2["reduced_binned"]) <= TOL
+    got = _np(basis.reduce_Plk(chain["chained"], params).sum())
+    assert rowmax_rel(got, golden2["reduced_chained"]) <= TOL
+    table = basis.reduce_Plk_gaussian_table(chain["binned"], params)
+    for i, name in enumerate(("b3", "cct", "cr1", "cr2", "ce0", "cemono", "cequad")):
+        assert rowmax_rel(_np(table[name]), golden2["gaussian_table_binned"][:, i]) <= TOL, name
+    # function form with explicit lists (parambasis.py:42-136), first cosmology only
+    p0 = {k: float(v[0]) for k, v in params.items()}
+    one = parambasis.reduce_Plk(chain["binned"], [p0[n] for n in ("b1", "b2", "b3", "b4", "cct", "cr1", "cr2")],
+                                es=[p0[n] for n in ("ce0", "cemono", "cequad")]).sum()
+    assert rowmax_rel(_np(one)[0], golden2["reduced_binned"][0]) <= TOL
+
+
+def test_eastcoast_basis_against_oracle(chain):
+    import pybird_oracle as orc
+    from eftpipe_b200 import parambasis
+
+    binned = chain["binned"]
+    f = _np(chain["bird"]._f)
+    basis = parambasis.EastCoastBasis(prefix="e_")
+    vals = dict(e_b1=2.0, e_b2=0.3, e_bG2=-0.2, e_bGamma3=0.1, e_c0=5.0, e_c2=10.0, e_c4=-3.0, e_Pshot=0.4, e_a0=0.2, e_a2=-0.1)
+    # counterform is a Common property (pybird.py:526): east-coast needs its own Common
+    from eftpipe_b200 import pybird
+    from eftpipe_b200.transformer import PlainBird
+
+    co_e = pybird.Common(Nl=3, kmA=0.7, krA=0.25, ndA=4.5e-5, counterform="eastcoast")
+    view = PlainBird(None, co_e, binned._T, binned._picc, binned.B, False, binned._f_bm)
+    got = _np(basis.reduce_Plk(view, vals).sum())
+    table = basis.reduce_Plk_gaussian_table(view, vals)
+    oco = orc.Common(Nl=3, kmA=0.7, krA=0.25, ndA=4.5e-5, counterform="eastcoast")
+    for i in range(binned.B):
+        terms = {n: _np(getattr(binned, n))[i] for n in ("P11l", "Ploopl", "Pctl", "Pstl", "Picc")}
+        b1, b2, bG2, bG3, c0, c2, c4 = (vals["e_" + n] for n in ("b1", "b2", "bG2", "bGamma3", "c0", "c2", "c4"))
+        fi = f[i]
+        bsA = [b1, b1 + 3.5 * bG2, b1 + 15 * bG2 + 6 * bG3, 0.5 * b2 - 3.5 * bG2, c0 - fi / 3 * c2 + 3 / 35 * fi**2 * c4,
+               c2 - 6 / 7 * fi * c4, c4]
+        es = [vals["e_Pshot"], vals["e_a0"] + vals["e_a2"] / 3, 2 / 3 * vals["e_a2"]]
+        ref = orc.reduce_Plk(oco, fi, terms, bsA, es=es)
+        assert rowmax_rel(got[i], ref) <= TOL
+        # parambasis.py:433-437: dP/dc4
+        ref_c4 = -6 / 35 * fi**2 * terms["Pctl"][:, 0] + 12 / 7 * fi**2 * terms["Pctl"][:, 1] - 2.0 * fi**2 * terms["Pctl"][:, 2]
+        assert rowmax_rel(_np(table["e_c4"])[i], ref_c4) <= TOL
+
+
+def test_single_tracer_marginalised_likelihood(chain, golden2, dr16):
+    """EFTLike on the DR16 NGC LRG data/covariance: logp (Jeffreys and Gaussian priors), best fit."""
+    from eftpipe_b200 import likelihood, parambasis
+
+    g = golden2
+    basis = parambasis.WestCoastBasis(prefix="")
+    binned = chain["binned"]
+    nk = g["kout"].size
+    rows = np.arange(3 * nk, dtype=np.int32)
+    names = ["b3", "cct", "cr1", "cr2", "ce0", "cequad"]
+    tr = dict(basis=basis, co=chain["co"], nout=3 * nk, nterm=24, rows=rows, picc=binned._picc.reshape(-1))
+    params = _params(g["nuisance"])
+    sampled = {k: params[k] for k in ("b1", "b2", "b4")}
+    import torch
+    from eftpipe_b200.engine import DeviceLikelihood
+
+    for jeff, scales, col in ((True, None, 0), (False, [4, 2, 4, 4, 2, 2], 8)):
+        sig = None if scales is None else np.diag(1.0 / np.array(scales, float) ** 2)
+        spec = likelihood.build_spec([tr], g["lrg_data"], g["lrg_invcov"], gaussian=names, sigma_inv=sig, jeffreys=jeff)
+        dev = DeviceLikelihood(spec)
+        nuis = likelihood.pack_nuisance(torch, [basis], sampled, [binned._f_bm], binned.B, binned._T.shape[-1])
+        logp, status, best = dev.eval(binned.B, [binned._T.contiguous()], [binned._f_bm], nuis, want_bestfit=True)
+        ref = g["marg_out"]
+        np.testing.assert_allclose(_np(logp), ref[:, col], rtol=1e-6)  # north star: chi^2 to 1e-6
+        np.testing.assert_allclose(_np(best), ref[:, col + 2 : col + 8], rtol=1e-5, atol=1e-8)
+        assert not _np(status).any()
+        vec = _np(dev.vectors(binned.B, [binned._T.contiguous()], [binned._f_bm], nuis))
+        assert rowmax_rel(vec[:, :, 0] + g["lrg_data"], g["marg_PNG"]) <= TOL
+
+
+def test_non_positive_definite_is_flagged_not_fatal(chain, golden2):
+    """marginal.py:113-116 raises; the batch path flags the point and keeps going."""
+    import torch
+    from eftpipe_b200 import likelihood, parambasis
+    from eftpipe_b200.engine import DeviceLikelihood
+
+    basis = parambasis.WestCoastBasis(prefix="")
+    binned = chain["binned"]
+    nk = golden2["kout"].size
+    tr = dict(basis=basis, co=chain["co"], nout=3 * nk, nterm=24, rows=np.arange(3 * nk, dtype=np.int32),
+              picc=binned._picc.reshape(-1))
+    spec = likelihood.build_spec([tr], golden2["lrg_data"], -golden2["lrg_invcov"], gaussian=["b3", "cct"], jeffreys=True)
+    nuis = likelihood.pack_nuisance(torch, [basis], dict(b1=2.0), [binned._f_bm], binned.B, binned._T.shape[-1])
+    logp, status, _ = DeviceLikelihood(spec).eval(binned.B, [binned._T.contiguous()], [binned._f_bm], nuis)
+    assert (_np(status) == 1).all() and np.isneginf(_np(logp)).all()
+
+
+@pytest.fixture(scope="module")
+def dr16_setup(dr16):
+    """BASELINE config 3: LRG x ELG x cross, DR16 NGC production yaml
+    (cobaya/yamls/DR16_noric_LEX_..._kmax0.20.yaml:7-111)."""
+    from eftpipe_b200 import likelihood, synthetic, theory
+
+    ap = dict(Om_AP=0.307115, rdrag_AP=147.66, h_AP=0.6777, APst=True)
+    tracers = {
+        "LRG_NGC": dict(prefix="LRG_NGC_", z=0.696, nd=4.5e-5, window=dict(window_configspace_array=dr16["win_LRG"])),
+        "ELG_NGC": dict(prefix="ELG_NGC_", z=0.849, nd=2.3e-4, window=dict(window_configspace_array=dr16["win_ELG"])),
+        "X_NGC": dict(prefix="X_NGC_", z=0.763, cross=["LRG_NGC", "ELG_NGC"], window=dict(window_configspace_array=dr16["win_X"])),
+        "default": dict(km=0.7, kr=0.25, with_IRresum=True, with_APeffect=True, with_window=True, APeffect=ap,
+                        window=dict(accboost=4, windowk=0.1)),
+    }
+    west = {n: {"scale": None} for n in ("b3", "cct", "cr1", "cr2", "ce0", "cequad")}
+    marg = {"LRG_NGC_": west, "ELG_NGC_": dict(west), "X_NGC_ce0": {"scale": None}, "X_NGC_cequad": {"scale": None}}
+    like = likelihood.EFTLike(
+        tracers=["LRG_NGC", "ELG_NGC", "X_NGC"], chained=[False, True, False],
+        data={"LRG_NGC": dict(table=dr16["NGC_LRG_P"], ls=[0, 2, 4], kmin=0.02, kmax=0.20),
+              "ELG_NGC": dict(table=dr16["NGC_ELG_Q"], ls=[0, 2], kmin=0.03, kmax=0.20, symbol="Q"),
+              "X_NGC": dict(table=dr16["NGC_X_P"], ls=[0, 2, 4], kmin=0.02, kmax=0.20)},
+        cov=dict(matrix=dr16["cov_NGC_L024E02X024_PQP"], Nreal=1000), with_binning=True, jeffreys=True, marg=marg)
+    th = theory.EFTLSS(tracers).must_provide(like.get_requirements()).initialize()
+    like.initialize_with_provider(th)
+    B = 6
+    cosmo, batches = {}, {}
+    for name, z in (("LRG_NGC", 0.696), ("ELG_NGC", 0.849), ("X_NGC", 0.763)):
+        b = synthetic.make_batch(B, z, seed=20261018 + 3)
+        batches[name] = b
+        cosmo[name] = dict(pkh=b.plin, f=b.f, DA=b.DA, H=b.H)
+    rng = np.random.default_rng(11)
+    params = {}
+    for pre, b1 in (("LRG_NGC_", 2.1), ("ELG_NGC_", 1.4)):
+        params[pre + "b1"] = b1 + 0.05 * rng.standard_normal(B)
+        c2 = 0.7 + 0.1 * rng.standard_normal(B)
+        params[pre + "b2"], params[pre + "b4"] = c2 / np.sqrt(2), c2 / np.sqrt(2)
+    return dict(th=th, like=like, cosmo=cosmo, batches=batches, params=params, B=B, tracers=tracers)
+
+
+def test_multitracer_likelihood_against_oracle(dr16_setup, dr16):
+    """Config 3 end to end (3 tracers, 142 data points, 14 marginalised parameters): GPU logp vs the
+    oracle assembled exactly as the reference does (EFTLike.PNG/PG + marginalized_logp)."""
+    import pybird_oracle as orc
+
+    S = dr16_setup
+    th, like = S["th"], S["like"]
+    assert like.ndata == 142 and len(like.gaussian_names) == 14
+    assert like.hartlap == pytest.approx((1000 - 142 - 2) / 999)
+    th.calculate(S["cosmo"])
+    res = like.calculate(S["params"], want_bestfit=True)
+    logp = _np(res["logp"])
+    png, pg = like.PNG_PG(S["params"])
+    png, pg = _np(png), _np(pg)
+
+    # ---- oracle: per tracer pipeline, then the reference's flatten / marginalisation ----
+    names = like.gaussian_names
+    scal = {"LRG_NGC": (0.7, 0.25, 4.5e-5), "ELG_NGC": (0.7, 0.25, 2.3e-4)}
+    worst_png = worst_pg = 0.0
+    for i in (0, S["B"] - 1):
+        PNG, PG = [], {n: [] for n in names}
+        for name, z in (("LRG_NGC", 0.696), ("ELG_NGC", 0.849), ("X_NGC", 0.763)):
+            if name == "X_NGC":
+                (kmA, krA, ndA), (kmB, krB, ndB) = scal["LRG_NGC"], scal["ELG_NGC"]
+            else:
+                kmA, krA, ndA = kmB, krB, ndB = scal[name]
+            co = orc.Common(Nl=3, kmA=kmA, krA=krA, ndA=ndA, kmB=kmB, krB=krB, ndB=ndB)
+            nl, rs = orc.NonLinear(co), orc.Resum(co)
+            apo = orc.APeffect(co, Om_AP=0.307115, z_AP=z, APst=True)
+            b = S["batches"][name]
+            bird = orc.Bird(co, b.kin, b.plin[i], b.f[i], b.DA[i], b.H[i], z)
+            nl.PsCf(bird)
+            orc.set_PsCfl(bird)
+            rs.Ps(bird)
+            apo.AP(bird)
+            wplan = th.plans[name].host  # window matrices are validated against the reference in test_host_mirror
+            win = S["tracers"]
+            from eftpipe_b200 import window as W, pybird as pb
+
+            wobj = W.Window(window_configspace_array=dr16["win_" + name.split("_")[0]], co=pb.Common(Nl=3), accboost=4, windowk=0.1)
+            orc.apply_window(bird, orc.mask_and_measure(wobj.Wal, wobj.p, co.k, 0.1), wobj.p, window_st=True)
+            m = like.minfodict[name]
+            terms = orc.Binning(m.kout, co).transform(orc.bird_terms(bird))
+            if like.chained[name]:
+                terms = orc.chained_transform(terms, 3)
+            p = S["params"]
+            pa = lambda pre: [p[pre + "b1"][i], p[pre + "b2"][i], 0.0, p[pre + "b4"][i], 0.0, 0.0, 0.0]
+            if name == "X_NGC":
+                bsA, bsB = pa("LRG_NGC_"), pa("ELG_NGC_")
+                plk = orc.reduce_Plk(co, b.f[i], terms, bsA, bsB)
+                tab = orc.gaussian_table_west(co, b.f[i], terms, bsA[0], bsB[0], cross=True)
+                tab = {**{"LRG_NGC_" + k[2:]: v for k, v in tab.items() if k.startswith("A_")},
+                       **{"ELG_NGC_" + k[2:]: v for k, v in tab.items() if k.startswith("B_")},
+                       **{"X_NGC_" + k: v for k, v in tab.items() if k in ("ce0", "cemono", "cequad")}}
+            else:
+                pre = name + "_"
+                plk = orc.reduce_Plk(co, b.f[i], terms, pa(pre))
+                tab = {pre + k: v for k, v in orc.gaussian_table_west(co, b.f[i], terms, p[pre + "b1"][i]).items()}
+            flat = lambda arr: np.hstack([arr[ell // 2, m.kout_mask[ell]] for ell in m.ls])
+            PNG.append(flat(plk))
+            for n in names:
+                PG[n].append(flat(tab[n]) if n in tab else np.zeros(m.data_vector.size))
+        PNG = np.hstack(PNG)
+        PGm = np.array([np.hstack(PG[n]) for n in names])
+        worst_png = max(worst_png, rowmax_rel(png[i], PNG))
+        worst_pg = max(worst_pg, rowmax_rel(pg[i], PGm))
+        ref_logp, _, ref_best = orc.marginalized_logp(PNG, PGm, like.data_vector, like.invcov, jeffreys=True, return_bestfit=True)
+        assert logp[i] == pytest.approx(ref_logp, rel=1e-6), i
+        best = np.array([_np(res["bestfit"]["marg_" + n])[i] for n in names])
+        np.testing.assert_allclose(best, ref_best, rtol=1e-4, atol=1e-6)
+    assert worst_png <= TOL and worst_pg <= TOL

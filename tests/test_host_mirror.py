@@ -1,0 +1,116 @@
+"""CPU: host-side mirror of the reference interface - precompute and configuration logic that needs no GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rowmax_rel
+from eftpipe_b200 import binning, chained, fftlog, likelihood, marginal, parambasis, plan as P, pybird, window
+
+DATA = os.path.join(os.path.dirname(os.path.abspath(pybird.__file__)), "data", "dr16_ngc.npz")
+
+
+@pytest.fixture(scope="module")
+def dr16():
+    return dict(np.load(DATA))
+
+
+def test_common_validation():
+    with pytest.raises(ValueError):
+        pybird.Common(Nl=2, No=3)  # pybird.py:543-544
+    with pytest.raises(ValueError):
+        pybird.Common(IRcutoff=True)  # pybird.py:528-529
+    co = pybird.Common(Nl=3, kmA=0.7, krA=0.25, ndA=4.5e-5)
+    assert (co.Nk, co.Ns, co.Nkr, co.Nklow) == (50, 80, 43, 7)
+    assert co.kmB == 0.7 and co.ndB == 4.5e-5
+    assert pybird.Common(kmax=0.4).Nk == 84  # pybird.py:473-477
+
+
+def test_fftlog_class_matches_reference_semantics(fftlog_kat):
+    with pytest.raises(ValueError):
+        fftlog.FFTLog(Nmax=255, xmin=1e-5, xmax=10, bias=-0.3)  # fftlog.py:61-62
+    fl = fftlog.FFTLog(Nmax=256, xmin=1e-5, xmax=10, bias=-0.3)
+    x, rows = fftlog_kat["x"], fftlog_kat["rows"]
+    c = fl.coef_host(x, rows, extrap="padding", window=0.3)
+    assert np.abs(c - fftlog_kat["coef"]).max() <= 1e-13 * np.abs(fftlog_kat["coef"]).max()
+    # the linear operator reproduces the transform
+    L = fl.operator(x, window=0.3)
+    assert np.abs(rows @ L.T - fftlog_kat["coef"]).max() <= 1e-12 * np.abs(fftlog_kat["coef"]).max()
+
+
+def test_window_precompute_matches_reference(dr16, golden2, tmp_path):
+    co = pybird.Common(Nl=3, kmA=0.7, krA=0.25, ndA=4.5e-5)
+    cache = tmp_path / "win_lrg.npy"
+    w = window.Window(window_fourier_file=cache, window_configspace_array=dr16["win_LRG"], co=co, accboost=4, windowk=0.1)
+    assert rowmax_rel(w.effective_matrix().reshape(150, 150), golden2["Weff_LRG"].reshape(150, 150)) <= 1e-9
+    # cache round trip + strict meta check (window.py:204-260)
+    assert cache.exists() and cache.with_suffix(".json").exists()
+    w2 = window.Window(window_fourier_file=cache, window_configspace_array=dr16["win_LRG"], co=co, accboost=4, windowk=0.1)
+    np.testing.assert_array_equal(w2.Wal, w.Wal)
+    with pytest.raises(window.MetaInfoError):
+        window.Window(window_fourier_file=cache, window_configspace_array=dr16["win_LRG"], co=co, accboost=4, bias=-1.5)
+    with pytest.raises(ValueError):
+        window.Window(co=co)
+
+
+def test_binning_and_chained_operators(golden2):
+    co = pybird.Common(Nl=3)
+    b = binning.Binning(golden2["kout"], co=co)
+    assert b.nbin == golden2["kout"].size == 18
+    got = np.einsum("bk,nlik->nlib", b.matrix, golden2["win_Ploopl"])
+    assert rowmax_rel(got, golden2["bin_Ploopl"]) <= 1e-9
+    with pytest.raises(ValueError):
+        binning.Binning(golden2["kout"], co=co, kstart=0.0)  # binning.py:89-90
+    assert chained.chain_coeff(0) == pytest.approx(-0.4) and chained.chain_coeff(2) == pytest.approx(-20 / 27)
+    with pytest.raises(NotImplementedError):
+        chained.Chained().chained_matrix(5)
+
+
+def test_likelihood_host_helpers(dr16):
+    k = dr16["NGC_LRG_P"][:, 0]
+    m = likelihood.parse_kmask(k, [0, 2, 4], 0.02, 0.20)
+    assert all(s.stop - s.start == 18 for s in m.values())
+    with pytest.raises(ValueError):
+        likelihood.parse_kmask(k, [0, 2], [0.02], 0.2)
+    cov = dr16["cov_NGC_L024E02X024_PQP"]
+    kq = dr16["NGC_ELG_Q"][:, 0]
+    masked = likelihood.mask_covariance(cov, [0, 2, 4], [0, 2, 4], k, 0.02, 0.2, [0, 2], [0, 2], kq, 0.03, 0.2,
+                                        [0, 2, 4], [0, 2, 4], k, 0.02, 0.2)
+    assert masked.shape == (142, 142)  # DR16 NGC production data vector
+    with pytest.raises(ValueError):
+        likelihood.mask_covariance(cov[:10, :10], [0], [0], k, None, None)
+    assert likelihood.hartlap(1000, 142) == pytest.approx(0.8568568568568569)
+    info = likelihood.MultipoleInfo.load(dr16["NGC_ELG_Q"], ls=[0, 2], kmin=0.03, kmax=0.20, symbol="Q")
+    assert info.data_vector.size == 34 and info.kout.size == 17
+
+
+def test_prior_handling():
+    class M(marginal.Marginalizable):
+        def marginalizable_params(self):
+            return ["a", "b", "c"]
+
+    m = M()
+    m.setup_prior({"c": {"scale": 2}, "a": {"loc": 1, "scale": 4}})
+    assert list(m.valid_prior) == ["a", "c"]  # sorted by marginalizable order (marginal.py:222-226)
+    np.testing.assert_allclose(m.sigma_inv, np.diag([1 / 16, 1 / 4]))
+    np.testing.assert_allclose(m.mu_G, [1, 0])
+    m.setup_prior({"a": None, "b": {"scale": None}})
+    assert not m.sigma_inv.any()  # infinite scales -> zero precision (marginal.py:74-75)
+    with pytest.raises(marginal.LoggedError):
+        m.setup_prior({"zzz": None})
+    with pytest.raises(marginal.LoggedError):
+        m.setup_prior({"a": {"scale": 1}, "b": None})  # marginal.py:227-231
+
+
+def test_basis_names_and_descriptors():
+    w = parambasis.WestCoastBasis(prefix="X_", cross_prefix=["L_", "E_"])
+    assert w.non_gaussian_params() == ["L_b1", "L_b2", "L_b4", "E_b1", "E_b2", "E_b4"]
+    assert w.gaussian_params()[-3:] == ["X_ce0", "X_cemono", "X_cequad"]
+    co = pybird.Common(Nl=3, kmA=0.7, krA=0.25, ndA=4.5e-5, kmB=0.7, krB=0.25, ndB=2.3e-4)
+    d = w.gaussian_descriptors(co)
+    assert set(d) == set(w.gaussian_params())
+    assert d["L_b3"][1][1] == parambasis.VAR_B1B and d["E_b3"][1][1] == parambasis.VAR_B1A
+    with pytest.raises(NotImplementedError):
+        parambasis.EastCoastBasis(prefix="a", cross_prefix=["b", "c"])
+    assert parambasis.find_param_basis("eastcoast") is parambasis.EastCoastBasis
