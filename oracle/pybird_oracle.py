@@ -262,6 +262,7 @@ class NonLinear:
         ell = 2 * np.arange(co.Nl)
         self.Mcf11 = mpc(ell[:, None], nu[None, :])  # :1029
         self.Ml = mpc(ell[:, None, None], a[None] + b[None] - 1.5)  # :1035-1038
+        self.Mcf22 = self.Ml[:, None] * self.M22[None]  # :1042 (axis order l,b,n,m)
         self.Mcfct = mpc(ell[:, None], nu - 1.0)  # :1052
         self.McfctNNLO = mpc(ell[:, None], nu - 2.0)  # :1056
         self.kPow = np.exp(np.outer(self.grid.Pow, np.log(co.k)))  # :1060
@@ -277,8 +278,10 @@ class NonLinear:
         bird.coef = c
         v = c[:, None] * self.kPow  # (N, Nk)
         u = c[:, None] * self.sPow  # (N, Ns)
-        # P22[b,k] = k^3 Re sum_nm v_nk v_mk M22[b,n,m]   (:1074-1078)
-        tmp = np.einsum("bnm,mk->bnk", self.M22, v)
+        # P22[b,k] = k^3 Re sum_nm v_nk v_mk M22[b,n,m]   (:1074-1078); contraction order of the reference's
+        # einsum path: matrix times panel first (one zgemm), then the dot with the second panel
+        N = c.size
+        tmp = (self.M22.reshape(28 * N, N) @ v).reshape(28, N, co.Nk)
         bird.P22 = co.k**3 * np.real(np.einsum("nk,bnk->bk", v, tmp))
         bird.P13 = co.k**3 * bird.P11 * np.real(self.M13 @ v)  # :1080-1086
         bird.C11 = np.real(self.Mcf11 @ u)  # :1088-1090
@@ -286,14 +289,11 @@ class NonLinear:
         if co.with_NNLO:
             bird.CctNNLO = co.s**-4 * np.real(self.McfctNNLO @ u)  # :1098-1101
         # C22[l,b,s] = Re sum_nm u_ns u_ms Ml[l,n,m] M22[b,n,m]   (:1042, :1103-1113)
-        C22 = np.empty((co.Nl, 28, co.Ns))
-        C13 = np.empty((co.Nl, 10, co.Ns))
-        for l in range(co.Nl):
-            t = np.einsum("bnm,ms->bns", self.M22 * self.Ml[l][None], u)
-            C22[l] = np.real(np.einsum("ns,bns->bs", u, t))
-            # C13[l,b,s] = Re sum_nm u_ns u_ms Ml[l,n,m] M13[b,n]   (:1046, :1115-1125)
-            w = self.Ml[l] @ u  # (n, s)
-            C13[l] = np.real(np.einsum("bn,ns,ns->bs", self.M13, u, w))
+        t = (self.Mcf22.reshape(co.Nl * 28 * N, N) @ u).reshape(co.Nl, 28, N, co.Ns)
+        C22 = np.real(np.einsum("ns,lbns->lbs", u, t))
+        # C13[l,b,s] = Re sum_nm u_ns u_ms Ml[l,n,m] M13[b,n]   (:1046, :1115-1125)
+        w = (self.Ml.reshape(co.Nl * N, N) @ u).reshape(co.Nl, N, co.Ns)
+        C13 = np.real(np.einsum("bn,ns,lns->lbs", self.M13, u, w))
         bird.C22, bird.C13 = C22, C13
 
 

@@ -50,3 +50,12 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(_lib.EftbError):
         _lib.require_cuda()
+
+
+def test_library_is_not_older_than_its_sources():
+    """guards against shipping a stale in-tree .so to the GPU box"""
+    import glob
+
+    src = glob.glob(os.path.join(ROOT, "eftpipe_b200", "csrc", "*.cu*")) + [os.path.join(ROOT, "include", "eftb200.h")]
+    newest = max(os.path.getmtime(p) for p in src)
+    assert os.path.getmtime(_lib.LIB_PATH) >= newest, "libeftb200.so is stale: run eftpipe_b200/csrc/build.sh"
