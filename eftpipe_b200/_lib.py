@@ -74,6 +74,7 @@ SIGNATURES = {
     "eftb_group": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "eftb_resum": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP]),
     "eftb_ap": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "eftb_ap_scratch_bytes": (C.c_size_t, [_VP, _I]),
     "eftb_project": (C.c_int, [_VP, _I, _VP, _VP, _VP]),
     "eftb_eval_terms": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "eftb_operator_create": (C.c_int, [_I, _I, c_double_p, C.POINTER(_VP)]),

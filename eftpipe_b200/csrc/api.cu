@@ -25,7 +25,7 @@ int upload(T** dst, const T* src, size_t n) {
 }
 
 struct Sizes {
-  size_t u, F, D, P22, Cs, T, Cr, scal, out;
+  size_t u, F, D, P22, Cs, T, Cr, scal, out, ap;
 };
 
 Sizes sizes(const eftb_plan* p, int Bp) {
@@ -40,6 +40,7 @@ Sizes sizes(const eftb_plan* p, int Bp) {
   z.Cr = (size_t)c.Nl * (14 + (c.with_nnlo ? 1 : 0)) * c.Ns * Bp;
   z.scal = (size_t)3 * Bp;
   z.out = c.has_project ? (size_t)c.nout * c.nterm * Bp : 0;
+  z.ap = c.has_ap ? ap_scratch_doubles(p, Bp) : 0;
   return z;
 }
 
@@ -163,9 +164,9 @@ void eftb_plan_destroy(eftb_plan* p) {
 size_t eftb_workspace_bytes(const eftb_plan* p, int B) {
   if (!p || B < 1) return 0;
   Sizes z = sizes(p, eftb_padded_batch(B));
-  // u | F | D (later reused for the spline coefficients and the AP output) | P22 | Cs | T | Cr | f,DA,H | out
+  // u | F | D (later reused for the spline coefficients and the AP output) | P22 | Cs | T | Cr | f,DA,H | out | AP operator
   size_t dreg = z.D > 2 * z.T ? z.D : 2 * z.T;
-  return (z.u + z.F + dreg + z.P22 + z.Cs + z.T + z.Cr + z.scal + z.out) * sizeof(double);
+  return (z.u + z.F + dreg + z.P22 + z.Cs + z.T + z.Cr + z.scal + z.out + z.ap) * sizeof(double);
 }
 
 int eftb_to_batch_minor(const double* in, int B, int R, double* out, void* stream) {
@@ -221,21 +222,33 @@ int eftb_resum(const eftb_plan* p, int B, const double* F, const double* Cr, con
   return launch_resum(p, B, eftb_padded_batch(B), F, Cr, f, T, (cudaStream_t)stream);
 }
 
-int eftb_ap(const eftb_plan* p, int B, const double* Tin, const double* DA, const double* H, double* coef, double* Tout,
-            void* stream) {
-  EFTB_NEED(p && Tin && DA && H && coef && Tout && B >= 1 && Tin != Tout, "NULL/invalid argument");
-  if (!p->cfg.has_ap) { eftb_set_error("eftb_ap: plan built without AP"); return EFTB_ERR_NOT_BUILT; }
-  cudaStream_t s = (cudaStream_t)stream;
+size_t eftb_ap_scratch_bytes(const eftb_plan* p, int B) {
+  if (!p || B < 1 || !p->cfg.has_ap) return 0;
+  const int Bp = eftb_padded_batch(B);
+  return ((size_t)p->cfg.Nl * p->cfg.Nk * p->cfg.nterm * Bp + ap_scratch_doubles(p, Bp)) * sizeof(double);
+}
+
+static int ap_stage(const eftb_plan* p, int B, const double* Tin, const double* DA, const double* H, double* coef,
+                    double* gscratch, double* Tout, cudaStream_t s) {
   const eftb_config& c = p->cfg;
   const int Bp = eftb_padded_batch(B);
   const size_t per_l = (size_t)c.Nk * c.nterm * Bp;
   // B-spline coefficients of every term row: coef[l] = Cinv @ T[l]  (N = nterm*Bp columns)
   int rc = gemm_run(p->Cinv, Tin, coef, c.nterm * Bp, c.Nl, c.Nl, per_l, 0, per_l, s);
   if (rc) return rc;
-  if (Bp > B) {  // pad lanes are not processed by the per-cosmology kernel: keep them finite
+  if (Bp > B) {  // pad lanes are not processed by the per-cosmology kernels: keep them finite
     EFTB_CUDA_CHECK(cudaMemcpyAsync(Tout, Tin, (size_t)c.Nl * per_l * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
-  return launch_ap(p, B, Bp, coef, Tin, DA, H, Tout, s);
+  return launch_ap(p, B, Bp, coef, Tin, DA, H, gscratch, Tout, s);
+}
+
+int eftb_ap(const eftb_plan* p, int B, const double* Tin, const double* DA, const double* H, double* scratch, double* Tout,
+            void* stream) {
+  EFTB_NEED(p && Tin && DA && H && scratch && Tout && B >= 1 && Tin != Tout, "NULL/invalid argument");
+  if (!p->cfg.has_ap) { eftb_set_error("eftb_ap: plan built without AP"); return EFTB_ERR_NOT_BUILT; }
+  const eftb_config& c = p->cfg;
+  const size_t nT = (size_t)c.Nl * c.Nk * c.nterm * eftb_padded_batch(B);
+  return ap_stage(p, B, Tin, DA, H, scratch, scratch + nT, Tout, (cudaStream_t)stream);
 }
 
 int eftb_project(const eftb_plan* p, int B, const double* T, double* out, void* stream) {
@@ -279,7 +292,7 @@ int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double*
   if (c.has_ap) {
     double* coef = D;
     double* T2 = D + z.T;
-    if ((rc = eftb_ap(p, B, T, scal + Bp, scal + 2 * (size_t)Bp, coef, T2, stream))) return rc;
+    if ((rc = ap_stage(p, B, T, scal + Bp, scal + 2 * (size_t)Bp, coef, out + z.out, T2, s))) return rc;
     cur = T2;
   }
   if (c.has_project) {

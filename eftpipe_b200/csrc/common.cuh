@@ -66,7 +66,8 @@ int launch_group(const eftb_plan* p, int Bp, const double* F, const double* P22,
 int launch_resum(const eftb_plan* p, int B, int Bp, const double* F, const double* Cr, const double* f,
                  double* T, cudaStream_t s);
 int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const double* Tin, const double* DA,
-              const double* H, double* Tout, cudaStream_t s);
+              const double* H, double* scratch, double* Tout, cudaStream_t s);
+size_t ap_scratch_doubles(const eftb_plan* p, int B);  // banded AP operator G + window metadata
 int launch_to_batch_minor(const double* in, int B, int Bp, int R, double* out, cudaStream_t s);
 int launch_to_point_major(const double* in, int B, int Bp, int R, const int32_t* perm, double* out,
                           cudaStream_t s);

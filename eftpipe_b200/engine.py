@@ -71,6 +71,7 @@ class DevicePlan:
         _lib.check(self.lib.eftb_plan_create(C.byref(cfg), C.byref(cst), C.byref(handle)), "eftb_plan_create")
         self.handle, self.cfg = handle, cfg
         self._ws = None
+        self._ap_scratch = None
         if plan.project is not None:
             self.out_shape = (plan.out_shape[0], g.nterm, plan.out_shape[1])
         else:
@@ -150,9 +151,11 @@ class DevicePlan:
         return T
 
     def ap(self, T, DA_bm, H_bm, B):
-        coef = self.torch.empty_like(T)
+        need = self.lib.eftb_ap_scratch_bytes(self.handle, int(B))
+        if self._ap_scratch is None or self._ap_scratch.numel() * 8 < need:
+            self._ap_scratch = self.torch.empty((need + 7) // 8, dtype=self.torch.float64, device="cuda")
         out = self.torch.empty_like(T)
-        _lib.check(self.lib.eftb_ap(self.handle, B, _p(T), _p(DA_bm), _p(H_bm), _p(coef), _p(out),
+        _lib.check(self.lib.eftb_ap(self.handle, B, _p(T), _p(DA_bm), _p(H_bm), _p(self._ap_scratch), _p(out),
                                     _stream_ptr(self.torch)), "eftb_ap")
         return out
 

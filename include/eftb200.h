@@ -124,9 +124,11 @@ int eftb_group(const eftb_plan*, int B, const double* F, const double* P22, cons
 /* Resum.Ps (pybird.py:1413-1464), in place on T */
 int eftb_resum(const eftb_plan*, int B, const double* F, const double* Cr, const double* f, double* T,
                void* stream);
-/* APeffect.AP (pybird.py:1598-1621); DA,H: [Bp]; coef_scratch: [Nl][Nk][nterm][Bp]; Tout may not alias Tin */
+/* APeffect.AP (pybird.py:1598-1621); DA,H: [Bp]; scratch: eftb_ap_scratch_bytes(plan, B) bytes (B-spline
+   coefficients [Nl][Nk][nterm][Bp] + the per-cosmology banded resampling operator); Tout may not alias Tin */
+size_t eftb_ap_scratch_bytes(const eftb_plan*, int B);
 int eftb_ap(const eftb_plan*, int B, const double* Tin, const double* DA, const double* H,
-            double* coef_scratch, double* Tout, void* stream);
+            double* scratch, double* Tout, void* stream);
 /* Window.Window (+ICC) -> Binning.transform -> Chained.transform as one operator; out: [nout][nterm][Bp] */
 int eftb_project(const eftb_plan*, int B, const double* T, double* out, void* stream);
 
