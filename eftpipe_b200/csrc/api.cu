@@ -120,8 +120,8 @@ int eftb_plan_create(const eftb_config* cfg, const eftb_constants* h, eftb_plan*
   rc |= gemm_upload(h->Ak, 1, c.Nk, 2 * (c.Nmax + 1), &p->Ak);
   rc |= gemm_upload(h->As, c.Nl, c.Ns, 2 * (c.Nmax + 1), &p->As);
   if (c.has_resum) {
-    rc |= upload(&p->R, h->R, (size_t)c.Na * c.Nkr * c.Ns);
-    rc |= upload(&p->q, h->q, (size_t)2 * c.Nl * c.Nl * 2 * c.NIR * c.Na * c.qdeg);
+    if (!h->R || !h->q) { eftb_set_error("eftb_plan_create: resummation constants missing"); rc = EFTB_ERR_ARG; }
+    else rc |= resum_pack(p, h->R, h->q);
     rc |= upload(&p->kr2, h->kr2, c.Nkr);
   }
   if (c.has_ap) {
@@ -155,7 +155,7 @@ int eftb_plan_create(const eftb_config* cfg, const eftb_constants* h, eftb_plan*
 void eftb_plan_destroy(eftb_plan* p) {
   if (!p) return;
   void* ptrs[] = {p->k, p->l11, p->lct, p->lctnnlo, p->l22, p->l13, p->lr, p->lrx, p->pair_table, p->pair_offsets,
-                  p->R, p->q, p->kr2, p->knot_lo, p->basis, p->mu, p->wl, p->perm_out};
+                  p->rs.Rt, p->rs.qpack, p->kr2, p->knot_lo, p->basis, p->mu, p->wl, p->perm_out};
   for (void* q : ptrs) if (q) cudaFree(q);
   gemm_free(&p->Wf); gemm_free(&p->Ak); gemm_free(&p->As); gemm_free(&p->Cinv); gemm_free(&p->project);
   delete p;

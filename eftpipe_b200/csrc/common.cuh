@@ -43,6 +43,13 @@ void gemm_free(GemmMatrix* m);
 int gemm_run(const GemmMatrix& A, const double* X, double* C, int N, int nz, int zdiv, size_t xs, size_t xs2,
              size_t cs, cudaStream_t stream);
 
+// IR-resummation constants in kernel layout (resum.cu resum_pack)
+struct ResumPack {
+  double *qpack = nullptr, *Rt = nullptr;  // [qdeg][2][Nl][Nl][NIR][4],  [Na][NsP][Nkr]
+  int NsP = 0;
+  int slot_v[3][4] = {}, slot_kind[3][4] = {}, nslot[3] = {};
+};
+
 // ---- plan ---------------------------------------------------------------------------------------
 struct eftb_plan {
   eftb_config cfg;
@@ -52,13 +59,15 @@ struct eftb_plan {
   GemmMatrix Wf, Ak, As, Cinv, project;
   double2* pair_table = nullptr;
   int32_t* pair_offsets = nullptr;
-  double *R = nullptr, *q = nullptr, *kr2 = nullptr;
+  double* kr2 = nullptr;
+  ResumPack rs;
   double *knot_lo = nullptr, *basis = nullptr, *mu = nullptr, *wl = nullptr;
   int32_t* perm_out = nullptr;  // point-major export permutation
   int perm_rows = 0;
 };
 
 // kernels' host launchers (defined in the respective .cu files)
+int resum_pack(eftb_plan* p, const double* R, const double* q);
 int launch_front_prepare(const eftb_plan* p, int B, int Bp, const double* plin, double* u, cudaStream_t s);
 int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cudaStream_t s);
 int launch_group(const eftb_plan* p, int Bp, const double* F, const double* P22, const double* Cs,

@@ -9,155 +9,302 @@
 //   T_a[l,l',k,s] = sum_v R[v,k,s] * ( z * A(z) + Y k^2 * B(z) ),   A, B: degree NIR-1 polynomials in z whose
 //                   coefficients are Q_a[l,l',p*Na+v](f) and Q_a[l,l',(NIR+p)*Na+v](f).
 //
-// One CTA per cosmology: Q(f) is expanded once into shared memory, then each thread owns one (a, l, k)
-// output column and sweeps s in chunks of 4 (Horner in z with broadcast coefficient loads, 8 DFMA per
-// 16-byte shared load).  FP64-FMA bound: ~7e6 DFMA per cosmology at Nl=3.
+// Most of those polynomials vanish identically (the X^{p+1} terms of Q^{ll'} couple to a single Bessel order
+// v, the Y X^p terms to 2-3): plan creation keeps, per l', the <= 4 non-zero (kind, v) "slots" (11 of 18
+// polynomials at Nl=3).  One CTA (128 threads) per cosmology: Q(f) is expanded once into shared memory, then
+// each thread owns one (l, k) output column for BOTH a = 0 (linear) and a = 1 (counterterm + loop) and sweeps
+// s in chunks of 4: 2 x 4 slots x 4 points = 32 independent Horner chains fed by broadcast 16-byte shared
+// loads (1 load per 4 DFMA).  A task count that is not a multiple of 128 (3 x 43 = 129) leaves <= 4 tasks
+// over; each is swept by one warp with the s-chunks spread over its lanes and a shuffle reduction.
+// FP64-FMA bound: ~4.6e6 DFMA per cosmology at Nl=3.
+#include <vector>
 #include "common.cuh"
 
 namespace {
 
+constexpr int RS_THREADS = 128;
+constexpr int RS_C = 4;      // s points per chunk
+constexpr int RS_SLOTS = 4;  // polynomial slots per l'
+
 struct ResumArgs {
-  const double *F, *Cr, *f, *R, *q, *kr2, *l11, *lct, *lctnnlo;
+  const double *F, *Cr, *f, *Rt, *qpack, *kr2, *l11, *lct, *lctnnlo;
   double* T;
-  int B, Bp, Nk, Ns, nterm, ncr, with_nnlo, Nkr, Nklow, qdeg, row_x, row_y;
+  int B, Bp, Nk, Ns, NsP, nterm, ncr, Nkr, Nklow, qdeg, row_x, row_y;
+  int slot_v[3][RS_SLOTS], slot_kind[3][RS_SLOTS], nslot[3];
 };
 
-template <int NL, int NIR, int NA>
-__global__ void __launch_bounds__(288) resum_kernel(ResumArgs a) {
-  extern __shared__ __align__(16) double sm[];
-  constexpr int NN = 2 * NIR * NA;
-  double2* Qf = reinterpret_cast<double2*>(sm);       // [2][NL][NL][NA][NIR] (x: X^{p+1} coefficient, y: Y X^p)
-  double* Xs = sm + 2 * (2 * NL * NL * NA * NIR);     // [Ns]
-  double* Ys = Xs + a.Ns;                             // [Ns]
-  double* Cs = Ys + a.Ns;                             // [NL][ncr][Ns]
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const size_t Bp = a.Bp;
-  const double f1 = a.f[b];
-
-  for (int s = tid; s < a.Ns; s += blockDim.x) {
-    Xs[s] = a.F[(size_t)(a.row_x + s) * Bp + b];
-    Ys[s] = a.F[(size_t)(a.row_y + s) * Bp + b];
+template <int NL, bool NNLO>
+struct Accum {
+  double lin0[NL], lin1[NL], loop[12], nnlo[NNLO ? NL : 1];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < NL; ++i) lin0[i] = lin1[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) loop[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < (NNLO ? NL : 1); ++i) nnlo[i] = 0.0;
   }
-  for (int i = tid; i < NL * a.ncr * a.Ns; i += blockDim.x) Cs[i] = a.Cr[(size_t)i * Bp + b];
-  // Q^{ll'}_u(f): polynomial in f (pybird.py:1367-1380 evaluates the reference's lambdas)
-  for (int i = tid; i < 2 * NL * NL * NN; i += blockDim.x) {
-    const double* qc = a.q + (size_t)i * a.qdeg;
-    double v = 0.0;
-    for (int d = a.qdeg - 1; d >= 0; --d) v = fma(v, f1, qc[d]);
-    const int u = i % NN, all = i / NN;  // all = (a*NL + l)*NL + lp
-    const int j = u / NA, vv = u % NA;
-    double* dst = reinterpret_cast<double*>(Qf + ((size_t)all * NA + vv) * NIR + (j < NIR ? j : j - NIR));
-    dst[j < NIR ? 0 : 1] = v;
-  }
-  __syncthreads();
+};
 
-  const int ntask = 2 * NL * a.Nkr;
-  for (int task = tid; task < ntask; task += blockDim.x) {
-    const int ia = task / (NL * a.Nkr), l = (task / a.Nkr) % NL, ik = task % a.Nkr;
-    const double k2 = a.kr2[ik];
-    double acc[12], lin[NL], nnlo[NL];
+// Horner sweep of NS polynomial slots for a = 0 and a = 1 over the RS_C points of a chunk, then the weighted
+// slot sum  T_a[c] = sum_slot w[slot][c] P_a[slot][c]
+template <int NIR, int NS>
+__device__ __forceinline__ void horner(const double* __restrict__ q0, const double* __restrict__ q1, const double (&z)[RS_C],
+                                       const double (&w)[RS_SLOTS][RS_C], double (&T0)[RS_C], double (&T1)[RS_C]) {
+  double P0[NS][RS_C], P1[NS][RS_C];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) acc[i] = 0.0;
+  for (int s = 0; s < NS; ++s)
 #pragma unroll
-    for (int i = 0; i < NL; ++i) lin[i] = nnlo[i] = 0.0;
-    for (int s0 = 0; s0 < a.Ns; s0 += 4) {
-      double z[4], yk[4];
+    for (int c = 0; c < RS_C; ++c) P0[s][c] = P1[s][c] = 0.0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const bool ok = s0 + c < a.Ns;
-        z[c] = ok ? k2 * Xs[s0 + c] : 0.0;
-        yk[c] = ok ? k2 * Ys[s0 + c] : 0.0;
+  for (int p = NIR - 1; p >= 0; --p) {
+    const double2 a01 = *reinterpret_cast<const double2*>(q0 + p * RS_SLOTS);
+    const double2 a23 = *reinterpret_cast<const double2*>(q0 + p * RS_SLOTS + 2);
+    const double2 b01 = *reinterpret_cast<const double2*>(q1 + p * RS_SLOTS);
+    const double2 b23 = *reinterpret_cast<const double2*>(q1 + p * RS_SLOTS + 2);
+    const double qa[4] = {a01.x, a01.y, a23.x, a23.y}, qb[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int c = 0; c < RS_C; ++c) {
+        P0[s][c] = fma(P0[s][c], z[c], qa[s]);
+        P1[s][c] = fma(P1[s][c], z[c], qb[s]);
       }
+  }
 #pragma unroll
-      for (int lp = 0; lp < NL; ++lp) {
-        double Tl[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int c = 0; c < RS_C; ++c) {
+    double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-        for (int v = 0; v < NA; ++v) {
-          const double2* qv = Qf + ((size_t)((ia * NL + l) * NL + lp) * NA + v) * NIR;
-          double A[4] = {0.0, 0.0, 0.0, 0.0}, Bq[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-          for (int p = NIR - 1; p >= 0; --p) {
-            const double2 qq = qv[p];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              A[c] = fma(A[c], z[c], qq.x);
-              Bq[c] = fma(Bq[c], z[c], qq.y);
-            }
-          }
-          const double* rr = a.R + ((size_t)v * a.Nkr + ik) * a.Ns + s0;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const double r = (s0 + c < a.Ns) ? __ldg(rr + c) : 0.0;
-            Tl[c] = fma(r, fma(z[c], A[c], yk[c] * Bq[c]), Tl[c]);
-          }
-        }
-        const double* crow = Cs + (size_t)lp * a.ncr * a.Ns + s0;
-        const int ns = min(4, a.Ns - s0);
-        if (ia == 0) {
-          for (int c = 0; c < ns; ++c) lin[lp] = fma(Tl[c], crow[c], lin[lp]);
-        } else {
-          for (int c = 0; c < ns; ++c) lin[lp] = fma(Tl[c], crow[a.Ns + c], lin[lp]);
-#pragma unroll
-          for (int i = 0; i < 12; ++i)
-            for (int c = 0; c < ns; ++c) acc[i] = fma(Tl[c], crow[(size_t)(2 + i) * a.Ns + c], acc[i]);
-          if (a.with_nnlo)
-            for (int c = 0; c < ns; ++c) nnlo[lp] = fma(Tl[c], crow[(size_t)14 * a.Ns + c], nnlo[lp]);
-        }
-      }
+    for (int s = 0; s < NS; ++s) {
+      t0 = fma(w[s][c], P0[s][c], t0);
+      t1 = fma(w[s][c], P1[s][c], t1);
     }
-    double* out = a.T + ((size_t)(l * a.Nk + a.Nklow + ik) * a.nterm) * Bp + b;
-    if (ia == 0) {
-      for (int i = 0; i < 3; ++i) {
-        double v = 0.0;
+    T0[c] = t0;
+    T1[c] = t1;
+  }
+}
+
+template <int NL, int NIR, bool NNLO>
+__device__ __forceinline__ void sweep_chunk(const ResumArgs& a, const double* Qs, const double* Xs, const double* Ys,
+                                            const double* Cs, int l, int ik, double k2, int s0, Accum<NL, NNLO>& A) {
+  double z[RS_C], yk[RS_C];
+  {
+    const double2 x01 = *reinterpret_cast<const double2*>(Xs + s0), x23 = *reinterpret_cast<const double2*>(Xs + s0 + 2);
+    const double2 y01 = *reinterpret_cast<const double2*>(Ys + s0), y23 = *reinterpret_cast<const double2*>(Ys + s0 + 2);
+    z[0] = k2 * x01.x; z[1] = k2 * x01.y; z[2] = k2 * x23.x; z[3] = k2 * x23.y;
+    yk[0] = k2 * y01.x; yk[1] = k2 * y01.y; yk[2] = k2 * y23.x; yk[3] = k2 * y23.y;
+  }
 #pragma unroll
-        for (int lp = 0; lp < NL; ++lp) v = fma(a.l11[lp * 3 + i], lin[lp], v);
-        out[(size_t)i * Bp] += v;  // pybird.py:1442, :1445
-      }
-    } else {
-      for (int i = 0; i < 6; ++i) {
-        double v = 0.0;
+  for (int lp = 0; lp < NL; ++lp) {
+    // slot weights R[v,k,s] * (z | Y k^2); Rt is [v][s][k] so that the lanes (k) read contiguously
+    double w[RS_SLOTS][RS_C];
 #pragma unroll
-        for (int lp = 0; lp < NL; ++lp) v = fma(a.lct[lp * 6 + i], lin[lp], v);
-        out[(size_t)(3 + i) * Bp] += v;  // pybird.py:1443, :1446
-      }
+    for (int sl = 0; sl < RS_SLOTS; ++sl) {
+      const bool on = sl < a.nslot[lp];
+      const double* rr = a.Rt + ((size_t)(on ? a.slot_v[lp][sl] : 0) * a.NsP + s0) * a.Nkr + ik;
+      const bool isy = a.slot_kind[lp][sl] != 0;
 #pragma unroll
-      for (int i = 0; i < 12; ++i) out[(size_t)(9 + i) * Bp] += acc[i];  // pybird.py:1444, :1462
-      if (a.with_nnlo)
-        for (int i = 0; i < 3; ++i) {
-          double v = 0.0;
+      for (int c = 0; c < RS_C; ++c) w[sl][c] = on ? __ldg(rr + (size_t)c * a.Nkr) * (isy ? yk[c] : z[c]) : 0.0;
+    }
+    const double* q0 = Qs + (size_t)(((0 * NL + l) * NL + lp) * NIR) * RS_SLOTS;
+    const double* q1 = Qs + (size_t)(((1 * NL + l) * NL + lp) * NIR) * RS_SLOTS;
+    double T0[RS_C], T1[RS_C];
+    if (a.nslot[lp] > 3) horner<NIR, 4>(q0, q1, z, w, T0, T1);
+    else horner<NIR, 3>(q0, q1, z, w, T0, T1);
+    const double* crow = Cs + (size_t)lp * a.ncr * a.NsP + s0;
+    {
+      const double2 c01 = *reinterpret_cast<const double2*>(crow), c23 = *reinterpret_cast<const double2*>(crow + 2);
+      A.lin0[lp] = fma(T0[3], c23.y, fma(T0[2], c23.x, fma(T0[1], c01.y, fma(T0[0], c01.x, A.lin0[lp]))));
+    }
+    {
+      const double2 c01 = *reinterpret_cast<const double2*>(crow + a.NsP), c23 = *reinterpret_cast<const double2*>(crow + a.NsP + 2);
+      A.lin1[lp] = fma(T1[3], c23.y, fma(T1[2], c23.x, fma(T1[1], c01.y, fma(T1[0], c01.x, A.lin1[lp]))));
+    }
 #pragma unroll
-          for (int lp = 0; lp < NL; ++lp) v = fma(a.lctnnlo[lp * 3 + i], nnlo[lp], v);
-          out[(size_t)(24 + i) * Bp] += v;  // pybird.py:1455-1458
-        }
+    for (int i = 0; i < 12; ++i) {
+      const double* cr = crow + (size_t)(2 + i) * a.NsP;
+      const double2 c01 = *reinterpret_cast<const double2*>(cr), c23 = *reinterpret_cast<const double2*>(cr + 2);
+      A.loop[i] = fma(T1[3], c23.y, fma(T1[2], c23.x, fma(T1[1], c01.y, fma(T1[0], c01.x, A.loop[i]))));
+    }
+    if (NNLO) {
+      const double* cr = crow + (size_t)14 * a.NsP;
+      const double2 c01 = *reinterpret_cast<const double2*>(cr), c23 = *reinterpret_cast<const double2*>(cr + 2);
+      A.nnlo[lp] = fma(T1[3], c23.y, fma(T1[2], c23.x, fma(T1[1], c01.y, fma(T1[0], c01.x, A.nnlo[lp]))));
     }
   }
 }
 
-template <int NL, int NIR, int NA>
-int run(const ResumArgs& a, cudaStream_t s) {
-  size_t smem = sizeof(double) * (2 * (2 * NL * NL * NA * NIR) + 2 * a.Ns + (size_t)NL * a.ncr * a.Ns);
-  static bool configured = false;
-  if (!configured) {
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+template <int NL, bool NNLO>
+__device__ __forceinline__ void write_out(const ResumArgs& a, int b, int l, int ik, const Accum<NL, NNLO>& A) {
+  double* out = a.T + ((size_t)(l * a.Nk + a.Nklow + ik) * a.nterm) * a.Bp + b;
+  const size_t Bp = a.Bp;
+  for (int i = 0; i < 3; ++i) {
+    double v = 0.0;
+#pragma unroll
+    for (int lp = 0; lp < NL; ++lp) v = fma(a.l11[lp * 3 + i], A.lin0[lp], v);
+    out[(size_t)i * Bp] += v;  // pybird.py:1442, :1445
   }
-  resum_kernel<NL, NIR, NA><<<a.B, 288, smem, s>>>(a);
+  for (int i = 0; i < 6; ++i) {
+    double v = 0.0;
+#pragma unroll
+    for (int lp = 0; lp < NL; ++lp) v = fma(a.lct[lp * 6 + i], A.lin1[lp], v);
+    out[(size_t)(3 + i) * Bp] += v;  // pybird.py:1443, :1446
+  }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) out[(size_t)(9 + i) * Bp] += A.loop[i];  // pybird.py:1444, :1462
+  if (NNLO)
+    for (int i = 0; i < 3; ++i) {
+      double v = 0.0;
+#pragma unroll
+      for (int lp = 0; lp < NL; ++lp) v = fma(a.lctnnlo[lp * 3 + i], A.nnlo[lp], v);
+      out[(size_t)(24 + i) * Bp] += v;  // pybird.py:1455-1458
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NL, int NIR, bool NNLO>
+__global__ void __launch_bounds__(RS_THREADS, 2) resum_kernel(ResumArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int NQ = 2 * NL * NL * NIR * RS_SLOTS;
+  double* Qs = sm;                       // [2][NL][NL][NIR][4]
+  double* Xs = Qs + NQ;                  // [NsP]
+  double* Ys = Xs + a.NsP;               // [NsP]
+  double* Cs = Ys + a.NsP;               // [NL][ncr][NsP]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const size_t Bp = a.Bp;
+  const double f1 = a.f[b];
+
+  for (int s = tid; s < a.NsP; s += RS_THREADS) {
+    const bool ok = s < a.Ns;
+    Xs[s] = ok ? a.F[(size_t)(a.row_x + s) * Bp + b] : 0.0;
+    Ys[s] = ok ? a.F[(size_t)(a.row_y + s) * Bp + b] : 0.0;
+  }
+  for (int i = tid; i < NL * a.ncr * a.NsP; i += RS_THREADS) {
+    const int s = i % a.NsP, r = i / a.NsP;
+    Cs[i] = s < a.Ns ? a.Cr[((size_t)r * a.Ns + s) * Bp + b] : 0.0;
+  }
+  // Q^{ll'}(f): polynomials in f (pybird.py:1367-1380 evaluates the reference's lambdas); qpack is [qdeg][NQ]
+  for (int i = tid; i < NQ; i += RS_THREADS) {
+    double v = 0.0;
+    for (int d = a.qdeg - 1; d >= 0; --d) v = fma(v, f1, __ldg(a.qpack + (size_t)d * NQ + i));
+    Qs[i] = v;
+  }
+  __syncthreads();
+
+  const int ntask = NL * a.Nkr, nchunk = a.NsP / RS_C;
+  const int rem = ntask % RS_THREADS;
+  const bool coop = rem > 0 && rem <= RS_THREADS / 32;
+  const int nmain = coop ? ntask - rem : ntask;
+  Accum<NL, NNLO> A;
+  for (int task = tid; task < nmain; task += RS_THREADS) {
+    const int l = task / a.Nkr, ik = task - l * a.Nkr;
+    const double k2 = a.kr2[ik];
+    A.zero();
+    for (int ch = 0; ch < nchunk; ++ch) sweep_chunk<NL, NIR, NNLO>(a, Qs, Xs, Ys, Cs, l, ik, k2, ch * RS_C, A);
+    write_out<NL, NNLO>(a, b, l, ik, A);
+  }
+  const int warp = tid >> 5, lane = tid & 31;
+  if (coop && warp < rem) {
+    const int task = nmain + warp;
+    const int l = task / a.Nkr, ik = task - l * a.Nkr;
+    const double k2 = a.kr2[ik];
+    A.zero();
+    for (int ch = lane; ch < nchunk; ch += 32) sweep_chunk<NL, NIR, NNLO>(a, Qs, Xs, Ys, Cs, l, ik, k2, ch * RS_C, A);
+#pragma unroll
+    for (int i = 0; i < NL; ++i) { A.lin0[i] = warp_sum(A.lin0[i]); A.lin1[i] = warp_sum(A.lin1[i]); }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) A.loop[i] = warp_sum(A.loop[i]);
+    if (NNLO) {
+#pragma unroll
+      for (int i = 0; i < NL; ++i) A.nnlo[i] = warp_sum(A.nnlo[i]);
+    }
+    if (lane == 0) write_out<NL, NNLO>(a, b, l, ik, A);
+  }
+}
+
+template <int NL, int NIR, bool NNLO>
+int run(const ResumArgs& a, cudaStream_t s) {
+  size_t smem = sizeof(double) * ((size_t)2 * NL * NL * NIR * RS_SLOTS + 2 * a.NsP + (size_t)NL * a.ncr * a.NsP);
+  static size_t configured = 0;
+  if (smem > configured) {
+    EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NNLO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  resum_kernel<NL, NIR, NNLO><<<a.B, RS_THREADS, smem, s>>>(a);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;
 }
 
 }  // namespace
 
+// Host-side packing at plan creation: transposed, s-padded operator Rt[v][NsP][Nkr]; per-l' slot list of the
+// non-vanishing polynomials; coefficient table qpack[d][a][l][l'][p][slot].
+int resum_pack(eftb_plan* p, const double* R, const double* q) {
+  const eftb_config& c = p->cfg;
+  const int Nl = c.Nl, NIR = c.NIR, Na = c.Na, Nn = 2 * NIR * Na, NsP = eftb_round_up(c.Ns, RS_C);
+  if (Nl > 3) { eftb_set_error("resum: Nl > 3 unsupported"); return EFTB_ERR_ARG; }
+  auto qat = [&](int a, int l, int lp, int u, int d) { return q[((((size_t)a * Nl + l) * Nl + lp) * Nn + u) * c.qdeg + d]; };
+  ResumPack& P = p->rs;
+  for (int lp = 0; lp < Nl; ++lp) {
+    int ns = 0;
+    for (int kind = 0; kind < 2; ++kind)
+      for (int v = 0; v < Na; ++v) {
+        bool any = false;
+        for (int a = 0; a < 2 && !any; ++a)
+          for (int l = 0; l < Nl && !any; ++l)
+            for (int pp = 0; pp < NIR && !any; ++pp)
+              for (int d = 0; d < c.qdeg && !any; ++d) any = qat(a, l, lp, (kind * NIR + pp) * Na + v, d) != 0.0;
+        if (!any) continue;
+        if (ns == RS_SLOTS) { eftb_set_error("resum: more than %d non-zero (kind, v) polynomials for l'=%d", RS_SLOTS, lp); return EFTB_ERR_ARG; }
+        P.slot_v[lp][ns] = v;
+        P.slot_kind[lp][ns] = kind;
+        ++ns;
+      }
+    P.nslot[lp] = ns;
+    for (int s = ns; s < RS_SLOTS; ++s) P.slot_v[lp][s] = P.slot_kind[lp][s] = 0;
+  }
+  const size_t NQ = (size_t)2 * Nl * Nl * NIR * RS_SLOTS;
+  std::vector<double> qp(NQ * c.qdeg, 0.0), rt((size_t)Na * NsP * c.Nkr, 0.0);
+  for (int a = 0; a < 2; ++a)
+    for (int l = 0; l < Nl; ++l)
+      for (int lp = 0; lp < Nl; ++lp)
+        for (int pp = 0; pp < NIR; ++pp)
+          for (int s = 0; s < P.nslot[lp]; ++s) {
+            const size_t e = ((((size_t)a * Nl + l) * Nl + lp) * NIR + pp) * RS_SLOTS + s;
+            const int u = (P.slot_kind[lp][s] * NIR + pp) * Na + P.slot_v[lp][s];
+            for (int d = 0; d < c.qdeg; ++d) qp[(size_t)d * NQ + e] = qat(a, l, lp, u, d);
+          }
+  for (int v = 0; v < Na; ++v)
+    for (int k = 0; k < c.Nkr; ++k)
+      for (int s = 0; s < c.Ns; ++s) rt[((size_t)v * NsP + s) * c.Nkr + k] = R[((size_t)v * c.Nkr + k) * c.Ns + s];
+  P.NsP = NsP;
+  EFTB_CUDA_CHECK(cudaMalloc((void**)&P.qpack, qp.size() * sizeof(double)));
+  EFTB_CUDA_CHECK(cudaMemcpy(P.qpack, qp.data(), qp.size() * sizeof(double), cudaMemcpyHostToDevice));
+  EFTB_CUDA_CHECK(cudaMalloc((void**)&P.Rt, rt.size() * sizeof(double)));
+  EFTB_CUDA_CHECK(cudaMemcpy(P.Rt, rt.data(), rt.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return EFTB_OK;
+}
+
 int launch_resum(const eftb_plan* p, int B, int Bp, const double* F, const double* Cr, const double* f, double* T,
                  cudaStream_t s) {
   const eftb_config& c = p->cfg;
   ResumArgs a;
-  a.F = F; a.Cr = Cr; a.f = f; a.R = p->R; a.q = p->q; a.kr2 = p->kr2; a.l11 = p->l11; a.lct = p->lct;
-  a.lctnnlo = p->lctnnlo; a.T = T; a.B = B; a.Bp = Bp; a.Nk = c.Nk; a.Ns = c.Ns; a.nterm = c.nterm;
-  a.ncr = 14 + (c.with_nnlo ? 1 : 0); a.with_nnlo = c.with_nnlo; a.Nkr = c.Nkr; a.Nklow = c.Nklow; a.qdeg = c.qdeg;
+  a.F = F; a.Cr = Cr; a.f = f; a.Rt = p->rs.Rt; a.qpack = p->rs.qpack; a.kr2 = p->kr2; a.l11 = p->l11; a.lct = p->lct;
+  a.lctnnlo = p->lctnnlo; a.T = T; a.B = B; a.Bp = Bp; a.Nk = c.Nk; a.Ns = c.Ns; a.NsP = p->rs.NsP; a.nterm = c.nterm;
+  a.ncr = 14 + (c.with_nnlo ? 1 : 0); a.Nkr = c.Nkr; a.Nklow = c.Nklow; a.qdeg = c.qdeg;
   a.row_x = c.row_x; a.row_y = c.row_y;
-  if (c.Nl == 3 && c.NIR == 16 && c.Na == 3) return run<3, 16, 3>(a, s);
-  if (c.Nl == 2 && c.NIR == 8 && c.Na == 2) return run<2, 8, 2>(a, s);
+  for (int lp = 0; lp < 3; ++lp) {
+    a.nslot[lp] = lp < c.Nl ? p->rs.nslot[lp] : 0;
+    for (int sl = 0; sl < RS_SLOTS; ++sl) { a.slot_v[lp][sl] = p->rs.slot_v[lp][sl]; a.slot_kind[lp][sl] = p->rs.slot_kind[lp][sl]; }
+  }
+  const bool nnlo = c.with_nnlo != 0;
+  if (c.Nl == 3 && c.NIR == 16 && c.Na == 3) return nnlo ? run<3, 16, true>(a, s) : run<3, 16, false>(a, s);
+  if (c.Nl == 2 && c.NIR == 8 && c.Na == 2) return nnlo ? run<2, 8, true>(a, s) : run<2, 8, false>(a, s);
   eftb_set_error("resum: unsupported (Nl, NIR, Na) = (%d, %d, %d)", c.Nl, c.NIR, c.Na);
   return EFTB_ERR_ARG;
 }
