@@ -1,72 +1,182 @@
-// Anti-diagonal reduction of the one-loop kernels.
+// Anti-diagonal reduction of the one-loop kernels on the FP64 tensor-core (DMMA) path.
 //
 // The reference contracts  sum_{n,m} c_n c_m M_b[n,m] x^{eta_n + eta_m}  separately for every k and s node
 // (pybird.py:1074-1078, :1103-1125): 28 (+30) complex 257x257 quadratic forms per node.  Because
 // eta_n + eta_m depends on n+m only, and so does the Bessel factor Ml[l,n,m] (pybird.py:1035-1038), all
 // of them follow from
 //        D_ch[t] = sum_{n+m=t} c_n c_m M_ch[n,m],      t = 0 .. 2 Nmax,
-// which is what this kernel computes (Hermitian half t <= Nmax, symmetric pairs n <= m folded into the
-// table on the host).  One lane = one cosmology, one warp = 32 cosmologies, 76 FP64 accumulators (38
-// complex channels: 28 22-type, 10 13-type) per lane; the pair table is read with warp-uniform 16-byte
-// loads (one L1 transaction per warp) and the coefficients with coalesced loads over the batch.
-// Work is FP64-FMA bound: 4 + 38*4 DFMA per (pair, cosmology), 16641 pairs at NFFT=256.
+// (Hermitian half t <= Nmax, symmetric pairs n <= m folded into the table on the host).  For one
+// anti-diagonal t this is a real GEMM
+//        [Re D; Im D] (76 x B) = [[Mr, -Mi], [Mi, Mr]] (76 x 2 np(t)) * [Re(c_p c_{t-p}); Im(c_p c_{t-p})] (2 np(t) x B)
+// whose right-hand operand (the coefficient products) is formed in registers directly in the DMMA B-fragment
+// layout, so only the kernel table streams from memory.
+//
+// Work decomposition: one warp = 32 cosmologies (4 n-tiles) x all 38 complex channels (10 m-tiles of 8 rows =
+// 4 channels x {re, im}) = 80 FP64 accumulators per lane; a k-step of `mma.sync.m8n8k4` consumes 2 pairs.
+// The 4 warps of a CTA share the FFTLog coefficients of their 32 cosmologies in shared memory and each
+// works through its own list of anti-diagonals (host-balanced by pair count, longest-first).  The table is
+// stored in fragment order (1280 B per k-step, compact complex) and streamed through a per-warp ring of
+// shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), two stages ahead.
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 
 namespace {
 
 constexpr int AD_WARPS = 4;
+constexpr int AD_MT = 10;                    // m-tiles: 80 rows >= 2 * 38
+constexpr int AD_NT = 4;                     // n-tiles per warp: 32 cosmologies
+constexpr int AD_KSTEP_BYTES = AD_MT * 8 * 16;  // 10 m-tiles x (2 pairs x 4 channels) complex = 1280 B
+constexpr int AD_S = 2;                      // k-steps per stage
+constexpr int AD_NST = 3;                    // stages in the ring
 
-__global__ void __launch_bounds__(AD_WARPS * 32) antidiag_kernel(const double* __restrict__ cre, const double* __restrict__ cim,
-                                                                const double2* __restrict__ table,
-                                                                const int32_t* __restrict__ offsets, int Nmax, int Bp,
-                                                                int npair, double* __restrict__ D) {
-  const int lane_b = (blockIdx.x * AD_WARPS + (threadIdx.x >> 5)) * 32 + (threadIdx.x & 31);
-  const bool live = lane_b < Bp;
-  const int b = live ? lane_b : Bp - 1;
-  const int Nh = Nmax >> 1;
-  // this block's range of anti-diagonals, balanced by pair count
-  const long lo = (long)npair * blockIdx.y / gridDim.y, hi = (long)npair * (blockIdx.y + 1) / gridDim.y;
-  int t0 = 0, t1 = 0;
-  {
-    // first t with offsets[t] >= lo  (offsets is increasing, offsets[0] = 0, offsets[Nmax+1] = npair)
-    int a = 0, z = Nmax + 1;
-    while (a < z) { int m = (a + z) >> 1; if (offsets[m] >= lo) z = m; else a = m + 1; }
-    t0 = a;
-    a = 0; z = Nmax + 1;
-    while (a < z) { int m = (a + z) >> 1; if (offsets[m] >= hi) z = m; else a = m + 1; }
-    t1 = a;
+struct AdArgs {
+  const double* cre;      // F rows: Re c_n, n = 0..Nmax/2, batch-minor [.][Bp]
+  const double* cim;
+  const double2* tab;     // fragment-ordered table
+  const int4* descs;      // stage descriptors {first k-step, count | last<<8, t, first pair}
+  const int32_t* bin_off; // [nbins + 1]
+  double* D;
+  int Nmax, Bp;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double flip_sign(double v, uint32_t mask) {  // mask = 0 or 0x80000000
+  return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
+}
+
+__global__ void __launch_bounds__(AD_WARPS * 32) antidiag_kernel(AdArgs a) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int Nh = a.Nmax >> 1;
+  const int nrow = 2 * (Nh + 1);
+  double* cs = reinterpret_cast<double*>(smraw);                                   // [Nh+1][2][32]
+  unsigned char* ring0 = smraw + (size_t)nrow * 32 * sizeof(double);               // [warps][NST][S * 1280]
+  uint64_t* bars0 = reinterpret_cast<uint64_t*>(ring0 + (size_t)AD_WARPS * AD_NST * AD_S * AD_KSTEP_BYTES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b0 = blockIdx.x * 32;
+  unsigned char* ring = ring0 + (size_t)warp * AD_NST * AD_S * AD_KSTEP_BYTES;
+  uint64_t* bars = bars0 + warp * AD_NST;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < AD_NST; ++i) mbar_init(bars + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  const size_t tstride = (size_t)2 * Bp, chstride = (size_t)(Nmax + 1) * 2 * Bp;
-  for (int t = t0; t < t1; ++t) {
-    double ar[EFTB_NCH], ai[EFTB_NCH];
+  // FFTLog coefficients of this CTA's 32 cosmologies: rows (n, re), (n, im)
+  for (int i = tid; i < nrow * 32; i += AD_WARPS * 32) {
+    const int row = i >> 5, n = i & 31, idx = row >> 1;
+    const double* src = (row & 1) ? a.cim : a.cre;
+    cs[i] = src[(size_t)idx * a.Bp + b0 + n];
+  }
+  __syncthreads();
+
+  const int bin = blockIdx.y * AD_WARPS + warp;
+  const int d0 = a.bin_off[bin], d1 = a.bin_off[bin + 1];
+  if (d0 >= d1) return;
+
+  auto issue = [&](int d) {  // lane 0 only
+    const int4 ds = __ldg(a.descs + d);
+    const int slot = (d - d0) % AD_NST;
+    const uint32_t bytes = (uint32_t)(ds.y & 0xff) * AD_KSTEP_BYTES;
+    mbar_expect_tx(bars + slot, bytes);
+    tma_bulk_load(ring + (size_t)slot * AD_S * AD_KSTEP_BYTES, reinterpret_cast<const unsigned char*>(a.tab) + (size_t)ds.x * AD_KSTEP_BYTES,
+                  bytes, bars + slot);
+  };
+  if (lane == 0)
+    for (int i = 0; i < AD_NST && d0 + i < d1; ++i) issue(d0 + i);
+
+  // lane roles inside the fragments
+  const int grp = lane >> 2, col = lane & 3;
+  const int a_cc = grp >> 1, a_part = grp & 1;      // A row: channel-in-tile, {re, im}
+  const int q = col >> 1, comp = col & 1;           // A col / B row: pair-in-step, {re, im} of the product
+  const bool a_same = a_part == comp;
+  const uint32_t a_neg = a_part ? 0u : 0x80000000u; // row re, col im -> -Mi ; row im, col re -> +Mi
+  const int a_word = q * 4 + a_cc;                  // double2 index inside an m-tile block
+
+  double acc[AD_MT][AD_NT][2];
 #pragma unroll
-    for (int c = 0; c < EFTB_NCH; ++c) ar[c] = ai[c] = 0.0;
-    const double2* row = table + (size_t)offsets[t] * EFTB_NCH;
-    const int np = (t >> 1) + 1;
-    for (int p = 0; p < np; ++p) {
+  for (int i = 0; i < AD_MT; ++i)
+#pragma unroll
+    for (int j = 0; j < AD_NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int d = d0; d < d1; ++d) {
+    const int it = d - d0, slot = it % AD_NST;
+    const int4 ds = __ldg(a.descs + d);
+    const int cnt = ds.y & 0xff, last = ds.y >> 8, t = ds.z;
+    mbar_wait(bars + slot, (uint32_t)((it / AD_NST) & 1));
+    const double2* stage = reinterpret_cast<const double2*>(ring + (size_t)slot * AD_S * AD_KSTEP_BYTES);
+    const int half = t >> 1;
+    for (int ks = 0; ks < cnt; ++ks) {
+      // B fragments: element (row = col, column = grp) of [Re(c_p c_m); Im(c_p c_m)] for pairs p0+0, p0+1
+      const int p = min(ds.w + 2 * ks + q, half);   // a padded second pair multiplies zero table entries
       const int m = t - p;
-      const int mi = m <= Nh ? m : Nmax - m;  // c_m = conj(c_{Nmax-m}) for m > Nmax/2
-      const double xr = cre[(size_t)p * Bp + b], xi = cim[(size_t)p * Bp + b];
-      const double yr = cre[(size_t)mi * Bp + b];
-      double yi = cim[(size_t)mi * Bp + b];
-      yi = m <= Nh ? yi : -yi;
-      const double pr = xr * yr - xi * yi, pi = xr * yi + xi * yr;
-      const double2* mrow = row + (size_t)p * EFTB_NCH;
+      const bool folded = m > Nh;                    // c_m = conj(c_{Nmax-m})
+      const int mi = folded ? a.Nmax - m : m;
+      // value = xr * (comp ? yi : yr) + (comp ? xi : -xi) * (comp ? yr : yi),   yi carries the fold sign
+      const double* xrow = cs + (size_t)(2 * p) * 32 + grp;
+      const double* yrow = cs + (size_t)(2 * mi) * 32 + grp;
+      const uint32_t s1 = (comp && folded) ? 0x80000000u : 0u;
+      const uint32_t s2 = (comp ? 0u : 0x80000000u) ^ ((!comp && folded) ? 0x80000000u : 0u);
+      double bf[AD_NT];
 #pragma unroll
-      for (int c = 0; c < EFTB_NCH; ++c) {
-        const double2 mv = __ldg(mrow + c);
-        ar[c] = fma(pr, mv.x, ar[c]);
-        ar[c] = fma(-pi, mv.y, ar[c]);
-        ai[c] = fma(pr, mv.y, ai[c]);
-        ai[c] = fma(pi, mv.x, ai[c]);
+      for (int j = 0; j < AD_NT; ++j) {
+        const double xr = xrow[j * 8], xi = xrow[32 + j * 8];
+        const double y1 = yrow[(comp ? 32 : 0) + j * 8], y2 = yrow[(comp ? 0 : 32) + j * 8];
+        bf[j] = fma(xr, flip_sign(y1, s1), flip_sign(xi, s2) * y2);
+      }
+      const double2* blk = stage + (size_t)ks * (AD_KSTEP_BYTES / 16) + a_word;
+#pragma unroll
+      for (int i = 0; i < AD_MT; ++i) {
+        const double2 mv = blk[i * 8];
+        const double af = a_same ? mv.x : flip_sign(mv.y, a_neg);
+#pragma unroll
+        for (int j = 0; j < AD_NT; ++j) dmma(acc[i][j][0], acc[i][j][1], af, bf[j]);
       }
     }
-    if (live) {
-      double* out = D + (size_t)t * tstride + b;
+    __syncwarp();
+    if (lane == 0 && d + AD_NST < d1) issue(d + AD_NST);
+    if (last) {
+      // D[ch][t][part][b]: row R = 8 i + grp -> channel R >> 1, part R & 1; columns 8 j + 2 col + {0, 1}
+      const size_t tstride = (size_t)2 * a.Bp, chstride = (size_t)(a.Nmax + 1) * tstride;
 #pragma unroll
-      for (int c = 0; c < EFTB_NCH; ++c) {
-        out[(size_t)c * chstride] = ar[c];
-        out[(size_t)c * chstride + Bp] = ai[c];
+      for (int i = 0; i < AD_MT; ++i) {
+        const int ch = 4 * i + a_cc;
+        if (ch < EFTB_NCH) {
+          double* out = a.D + (size_t)ch * chstride + (size_t)t * tstride + (size_t)a_part * a.Bp + b0 + 2 * col;
+#pragma unroll
+          for (int j = 0; j < AD_NT; ++j) *reinterpret_cast<double2*>(out + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+#pragma unroll
+        for (int j = 0; j < AD_NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
       }
     }
   }
@@ -74,16 +184,128 @@ __global__ void __launch_bounds__(AD_WARPS * 32) antidiag_kernel(const double* _
 
 }  // namespace
 
+// schedule of anti-diagonals over `nbins` warps (longest-first greedy), as TMA stage descriptors
+struct AdSchedule {
+  int4* descs = nullptr;
+  int32_t* bin_off = nullptr;
+};
+
+struct AntidiagPack {
+  double2* tab = nullptr;
+  std::vector<int> kstart;  // first k-step of anti-diagonal t, [Nmax + 2]
+  std::map<int, AdSchedule> sched;
+  std::mutex mu;
+};
+
+int antidiag_pack(eftb_plan* p, const double* pair_table, const int32_t* offsets) {
+  const int Nmax = p->cfg.Nmax;
+  AntidiagPack* P = new AntidiagPack();
+  p->ad = P;
+  P->kstart.assign(Nmax + 2, 0);
+  for (int t = 0; t <= Nmax; ++t) P->kstart[t + 1] = P->kstart[t] + ((t / 2 + 1) + 1) / 2;
+  const size_t nks = P->kstart[Nmax + 1];
+  std::vector<double> tab(nks * (AD_KSTEP_BYTES / 8), 0.0);
+  for (int t = 0; t <= Nmax; ++t) {
+    const int np = t / 2 + 1;
+    for (int pi = 0; pi < np; ++pi) {
+      const size_t ks = P->kstart[t] + pi / 2;
+      const int j = pi & 1;
+      const double* src = pair_table + ((size_t)offsets[t] + pi) * EFTB_NCH * 2;
+      for (int ch = 0; ch < EFTB_NCH; ++ch) {
+        const size_t w = (ks * AD_MT + ch / 4) * 8 + j * 4 + (ch & 3);
+        tab[2 * w] = src[2 * ch];
+        tab[2 * w + 1] = src[2 * ch + 1];
+      }
+    }
+  }
+  EFTB_CUDA_CHECK(cudaMalloc((void**)&P->tab, tab.size() * sizeof(double)));
+  EFTB_CUDA_CHECK(cudaMemcpy(P->tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return EFTB_OK;
+}
+
+void antidiag_free(eftb_plan* p) {
+  AntidiagPack* P = p->ad;
+  if (!P) return;
+  if (P->tab) cudaFree(P->tab);
+  for (auto& kv : P->sched) {
+    if (kv.second.descs) cudaFree(kv.second.descs);
+    if (kv.second.bin_off) cudaFree(kv.second.bin_off);
+  }
+  delete P;
+  p->ad = nullptr;
+}
+
+static int get_schedule(AntidiagPack* P, int Nmax, int nbins, AdSchedule* out) {
+  std::lock_guard<std::mutex> lock(P->mu);
+  auto it = P->sched.find(nbins);
+  if (it != P->sched.end()) { *out = it->second; return EFTB_OK; }
+  std::vector<int> order(Nmax + 1);
+  for (int t = 0; t <= Nmax; ++t) order[t] = t;
+  auto nk = [&](int t) { return P->kstart[t + 1] - P->kstart[t]; };
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return nk(x) > nk(y); });
+  std::vector<std::vector<int>> bins(nbins);
+  std::vector<long> load(nbins, 0);
+  for (int t : order) {
+    int best = 0;
+    for (int b = 1; b < nbins; ++b) if (load[b] < load[best]) best = b;
+    bins[best].push_back(t);
+    load[best] += nk(t) + 2;  // + epilogue cost of one anti-diagonal, in k-step units
+  }
+  std::vector<int4> descs;
+  std::vector<int32_t> off(nbins + 1, 0);
+  for (int b = 0; b < nbins; ++b) {
+    for (int t : bins[b]) {
+      const int n = nk(t);
+      for (int k0 = 0; k0 < n; k0 += AD_S) {
+        const int cnt = std::min(AD_S, n - k0);
+        const int last = k0 + cnt >= n;
+        descs.push_back(make_int4(P->kstart[t] + k0, cnt | (last << 8), t, 2 * k0));
+      }
+    }
+    off[b + 1] = (int32_t)descs.size();
+  }
+  AdSchedule s;
+  EFTB_CUDA_CHECK(cudaMalloc((void**)&s.descs, descs.size() * sizeof(int4)));
+  EFTB_CUDA_CHECK(cudaMemcpy(s.descs, descs.data(), descs.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  EFTB_CUDA_CHECK(cudaMalloc((void**)&s.bin_off, off.size() * sizeof(int32_t)));
+  EFTB_CUDA_CHECK(cudaMemcpy(s.bin_off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  P->sched[nbins] = s;
+  *out = s;
+  return EFTB_OK;
+}
+
 int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cudaStream_t s) {
   const eftb_config& c = p->cfg;
-  const double* cre = F + (size_t)c.row_cre * Bp;
-  const double* cim = F + (size_t)c.row_cim * Bp;
-  int nbx = (Bp / 32 + AD_WARPS - 1) / AD_WARPS;
-  // enough t-chunks to put >= ~3 CTAs on each of the 148 SMs, at most one chunk per anti-diagonal pair of rows
-  int want = (3 * 148 + nbx - 1) / nbx;
-  int nchunk = want < 1 ? 1 : (want > (c.Nmax + 1) / 2 ? (c.Nmax + 1) / 2 : want);
-  dim3 grid(nbx, nchunk);
-  antidiag_kernel<<<grid, AD_WARPS * 32, 0, s>>>(cre, cim, p->pair_table, p->pair_offsets, c.Nmax, Bp, c.npair, D);
+  AntidiagPack* P = p->ad;
+  if (!P) { eftb_set_error("antidiag: plan has no pair table"); return EFTB_ERR_ARG; }
+  const int ngroups = Bp / 32;
+  const size_t smem = (size_t)2 * (c.Nmax / 2 + 1) * 32 * sizeof(double) + (size_t)AD_WARPS * AD_NST * AD_S * AD_KSTEP_BYTES +
+                      AD_WARPS * AD_NST * sizeof(uint64_t);
+  if (smem > 227 * 1024) { eftb_set_error("antidiag: Nmax=%d needs %zu bytes of shared memory", c.Nmax, smem); return EFTB_ERR_ARG; }
+  static size_t configured = 0;
+  static int sms = 0;
+  if (smem > configured) {
+    EFTB_CUDA_CHECK(cudaFuncSetAttribute(antidiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  if (!sms) {
+    int dev = 0;
+    EFTB_CUDA_CHECK(cudaGetDevice(&dev));
+    EFTB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // one wave: CTAs per SM limited by shared memory (and 2 by registers)
+  const int per_sm = std::max(1, std::min(2, (int)((227 * 1024) / (smem + 1024))));
+  int ctas_per_group = std::max(1, (sms * per_sm) / ngroups);
+  ctas_per_group = std::min(ctas_per_group, (c.Nmax + 1 + AD_WARPS - 1) / AD_WARPS);
+  AdSchedule sc;
+  int rc = get_schedule(P, c.Nmax, ctas_per_group * AD_WARPS, &sc);
+  if (rc) return rc;
+  AdArgs a;
+  a.cre = F + (size_t)c.row_cre * Bp;
+  a.cim = F + (size_t)c.row_cim * Bp;
+  a.tab = P->tab; a.descs = sc.descs; a.bin_off = sc.bin_off; a.D = D; a.Nmax = c.Nmax; a.Bp = Bp;
+  dim3 grid(ngroups, ctas_per_group);
+  antidiag_kernel<<<grid, AD_WARPS * 32, smem, s>>>(a);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;
 }

@@ -115,8 +115,8 @@ int eftb_plan_create(const eftb_config* cfg, const eftb_constants* h, eftb_plan*
   rc |= upload(&p->lr, h->lr, c.ntail);
   rc |= upload(&p->lrx, h->lrx, c.ntailx);
   rc |= gemm_upload(h->Wf, 1, c.front_rows, p->K, &p->Wf);
-  rc |= upload(&p->pair_table, reinterpret_cast<const double2*>(h->pair_table), (size_t)c.npair * EFTB_NCH);
-  rc |= upload(&p->pair_offsets, h->pair_offsets, (size_t)c.Nmax + 2);
+  if (!h->pair_table || !h->pair_offsets) { eftb_set_error("eftb_plan_create: pair table missing"); rc = EFTB_ERR_ARG; }
+  else rc |= antidiag_pack(p, h->pair_table, h->pair_offsets);
   rc |= gemm_upload(h->Ak, 1, c.Nk, 2 * (c.Nmax + 1), &p->Ak);
   rc |= gemm_upload(h->As, c.Nl, c.Ns, 2 * (c.Nmax + 1), &p->As);
   if (c.has_resum) {
@@ -154,9 +154,10 @@ int eftb_plan_create(const eftb_config* cfg, const eftb_constants* h, eftb_plan*
 
 void eftb_plan_destroy(eftb_plan* p) {
   if (!p) return;
-  void* ptrs[] = {p->k, p->l11, p->lct, p->lctnnlo, p->l22, p->l13, p->lr, p->lrx, p->pair_table, p->pair_offsets,
+  void* ptrs[] = {p->k, p->l11, p->lct, p->lctnnlo, p->l22, p->l13, p->lr, p->lrx,
                   p->rs.Rt, p->rs.qpack, p->kr2, p->knot_lo, p->basis, p->mu, p->wl, p->perm_out};
   for (void* q : ptrs) if (q) cudaFree(q);
+  antidiag_free(p);
   gemm_free(&p->Wf); gemm_free(&p->Ak); gemm_free(&p->As); gemm_free(&p->Cinv); gemm_free(&p->project);
   delete p;
 }

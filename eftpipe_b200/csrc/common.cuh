@@ -43,6 +43,8 @@ void gemm_free(GemmMatrix* m);
 int gemm_run(const GemmMatrix& A, const double* X, double* C, int N, int nz, int zdiv, size_t xs, size_t xs2,
              size_t cs, cudaStream_t stream);
 
+struct AntidiagPack;  // fragment-ordered pair table + warp schedules (antidiag.cu)
+
 // IR-resummation constants in kernel layout (resum.cu resum_pack)
 struct ResumPack {
   double *qpack = nullptr, *Rt = nullptr;  // [qdeg][2][Nl][Nl][NIR][4],  [Na][NsP][Nkr]
@@ -57,8 +59,7 @@ struct eftb_plan {
   double *k = nullptr, *l11 = nullptr, *lct = nullptr, *lctnnlo = nullptr, *l22 = nullptr, *l13 = nullptr;
   double *lr = nullptr, *lrx = nullptr;
   GemmMatrix Wf, Ak, As, Cinv, project;
-  double2* pair_table = nullptr;
-  int32_t* pair_offsets = nullptr;
+  AntidiagPack* ad = nullptr;
   double* kr2 = nullptr;
   ResumPack rs;
   double *knot_lo = nullptr, *basis = nullptr, *mu = nullptr, *wl = nullptr;
@@ -68,6 +69,8 @@ struct eftb_plan {
 
 // kernels' host launchers (defined in the respective .cu files)
 int resum_pack(eftb_plan* p, const double* R, const double* q);
+int antidiag_pack(eftb_plan* p, const double* pair_table, const int32_t* offsets);
+void antidiag_free(eftb_plan* p);
 int launch_front_prepare(const eftb_plan* p, int B, int Bp, const double* plin, double* u, cudaStream_t s);
 int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cudaStream_t s);
 int launch_group(const eftb_plan* p, int Bp, const double* F, const double* P22, const double* Cs,
