@@ -395,9 +395,9 @@ def stage_profile(dp, like, lib, S, d_plin, d_f, d_DA, d_H, d_cols, terms_bm, B,
     reps = max(3, min(args.steps, 10))
     F = dp.front(d_plin)
     D = dp.antidiag(F, B)
-    P22, Cs = dp.spectral(D, B)
     f_bm, DA_bm, H_bm = (dp.to_batch_minor(x)[0] for x in (d_f, d_DA, d_H))
-    T, Cr = dp.group(F, P22, Cs, f_bm, B)
+    P22, Cr = dp.spectral_grouped(D, f_bm, B)
+    T, Cr = dp.group(F, P22, None, f_bm, B, Cr=Cr)
     T0 = T.clone()
     dp.resum(F, Cr, f_bm, T, B)
     Tap = dp.ap(T, DA_bm, H_bm, B)
@@ -417,8 +417,8 @@ def stage_profile(dp, like, lib, S, d_plin, d_f, d_DA, d_H, d_cols, terms_bm, B,
     ms = {
         "front": timed(lambda: dp.front(d_plin)),
         "antidiag": timed(lambda: dp.antidiag(F, B)),
-        "spectral": timed(lambda: dp.spectral(D, B)),
-        "group": timed(lambda: dp.group(F, P22, Cs, f_bm, B)),
+        "spectral": timed(lambda: dp.spectral_grouped(D, f_bm, B)),
+        "group": timed(lambda: dp.group(F, P22, None, f_bm, B, Cr=Cr)),
         "resum": timed(lambda: dp.resum(F, Cr, f_bm, T0, B)),
         "ap": timed(lambda: dp.ap(T, DA_bm, H_bm, B)),
         "project": timed(lambda: dp.project(Tap, B)),
@@ -440,13 +440,15 @@ def stage_profile(dp, like, lib, S, d_plin, d_f, d_DA, d_H, d_cols, terms_bm, B,
     g = dp.host.grid
     npair = dp.host.pair_table.shape[0]
     Nmax = g.NFFT
+    nslots = P.resum_slot_count(dp.host.resum)
     # algorithmic FP64 flops per evaluation of each stage, as implemented
     flops = {
         "front": 2.0 * dp.host.Wf.size,
         "antidiag": 2.0 * npair * (4 + 4 * P.NCH),
-        "spectral": 2.0 * (28 * g.Nk + g.Nl * 38 * g.Ns) * 2 * (Nmax + 1),
-        "resum": 2.0 * (2 * g.Nl * g.Nkr) * g.Ns * (g.Nl * dp.host.resum["Na"] * (2 * dp.host.resum["NIR"] + 3) + 13 * g.Nl / 2),
-        "ap": 2.0 * g.Nk * dp.host.ap["mu"].size * (g.nterm * (4 * g.Nl + g.Nl) + 40),
+        "spectral": 2.0 * (28 * g.Nk + g.Nl * 12 * g.Ns + g.Nl * 38) * 2 * (Nmax + 1),
+        "resum": 2.0 * g.Nl * g.Nkr * g.Ns * (2 * dp.host.resum["NIR"] * nslots + 2 * nslots + 14 * g.Nl),
+        "ap": 2.0 * (g.Nl * g.Nk * g.Nk * g.nterm + g.Nk * dp.host.ap["mu"].size * (4 * g.Nl * g.Nl + g.Nl * g.Nl + 40)
+                     + g.Nl * g.Nk * g.nterm * g.Nl * 8),
         "project": 2.0 * dp.host.project.size * g.nterm,
         "likelihood": 2.0 * like.cfg.ndata * (like.cfg.ndata * (like.cfg.ngauss + 1) + (like.cfg.ngauss + 1) * (like.cfg.ngauss + 2) / 2 + 30),
     }

@@ -71,8 +71,10 @@ SIGNATURES = {
     "eftb_front": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP]),
     "eftb_antidiag": (C.c_int, [_VP, _I, _VP, _VP, _VP]),
     "eftb_spectral": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP]),
+    "eftb_spectral_grouped": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "eftb_group": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
-    "eftb_resum": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP]),
+    "eftb_resum": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "eftb_resum_scratch_bytes": (C.c_size_t, [_VP, _I]),
     "eftb_ap": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "eftb_ap_scratch_bytes": (C.c_size_t, [_VP, _I]),
     "eftb_project": (C.c_int, [_VP, _I, _VP, _VP, _VP]),

@@ -63,14 +63,16 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
     }
     return lo;
   };
-  const int jfirst = locate(kq * sqrt(fma(mu2s[0], iF2m1, 1.0)));
-  const int jlast = locate(kq * sqrt(fma(mu2s[a.nmu - 1], iF2m1, 1.0)));
+  auto kprime = [&](int t) { const double root = fma(mu2s[t], iF2m1, 1.0); return kq * (root * rsqrt(root)); };
+  const int jfirst = locate(kprime(0));
+  const int jlast = locate(kprime(a.nmu - 1));
   const int jlo = min(jfirst, jlast), jhi = max(jfirst, jlast);
   const int wn = jhi - jlo + 4;
   double* Grow = a.G + ((size_t)bl * a.Nk + ik) * NQ * a.wcap;
   for (int q = 0; q < NQ; ++q)
     for (int c = 0; c < wn; ++c) Grow[q * a.wcap + c] = 0.0;
   a.meta[(size_t)bl * a.Nk + ik] = make_int2(jlo, wn);
+  __threadfence();  // the zeroes must reach L2 before this thread's reductions (RED) on the same words
 
   double acc[NQ][4];
 #pragma unroll
@@ -86,13 +88,14 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
   for (int t = 0; t < a.nmu; ++t) {
     const double m2 = mu2s[t];
     const double root = fma(m2, iF2m1, 1.0);
-    const double kp = kq * sqrt(root);  // pybird.py:1608
+    const double rs = rsqrt(root);           // one reciprocal square root serves k' and mu'^2
+    const double kp = kq * (root * rs);      // pybird.py:1608
     // k' is monotone in mu: j moves (rarely) in one direction inside [jlo, jhi]
     while (j < jhi && kp >= knots[j + 1]) {
       double* g = Grow + (j - jlo);     // B-spline j has no support beyond this knot: retire its column
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        g[q * a.wcap] += acc[q][0];
+        atomicAdd(g + q * a.wcap, acc[q][0]);  // fire-and-forget RED: this row belongs to this thread alone
         acc[q][0] = acc[q][1]; acc[q][1] = acc[q][2]; acc[q][2] = acc[q][3]; acc[q][3] = 0.0;
       }
       ++j;
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
       double* g = Grow + (j + 3 - jlo);
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        g[q * a.wcap] += acc[q][3];
+        atomicAdd(g + q * a.wcap, acc[q][3]);
         acc[q][3] = acc[q][2]; acc[q][2] = acc[q][1]; acc[q][1] = acc[q][0]; acc[q][0] = 0.0;
       }
       --j;
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) bv[r] = fma(fma(fma(bc[r * 4 + 3], x, bc[r * 4 + 2]), x, bc[r * 4 + 1]), x, bc[r * 4]);
     // even Legendre polynomials of mu' = mu / F / sqrt(root) (pybird.py:1609) need mu'^2 only
-    const double mp2 = m2 * invF2 / root;
+    const double mp2 = m2 * invF2 * (rs * rs);
     double L[3];
     L[0] = 1.0;
     L[1] = 0.5 * (3.0 * mp2 - 1.0);
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) g[q * a.wcap + r] += acc[q][r];
+    for (int r = 0; r < 4; ++r) atomicAdd(g + q * a.wcap + r, acc[q][r]);
 }
 
 template <int NL>
@@ -169,7 +172,14 @@ __global__ void __launch_bounds__(APPLY_THREADS) ap_apply_kernel(ApArgs a) {
     for (int lp = 0; lp < NL; ++lp) {
       const double* cf = coefs + ((size_t)lp * a.Nk + mw.x) * a.nterm + i;
       const double* gq = Gk + lp * a.wcap;
-      for (int c = 0; c < mw.y; ++c) acc = fma(__ldg(gq + c), cf[(size_t)c * a.nterm], acc);
+      for (int c0 = 0; c0 < mw.y; c0 += 4) {  // 4 independent loads in flight per step
+        double gv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gv[c] = c0 + c < mw.y ? __ldg(gq + c0 + c) : 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c0 + c < mw.y) acc = fma(gv[c], cf[(size_t)(c0 + c) * a.nterm], acc);
+      }
     }
     a.Tout[o] = norm * acc;
   }

@@ -25,7 +25,7 @@ int upload(T** dst, const T* src, size_t n) {
 }
 
 struct Sizes {
-  size_t u, F, D, P22, Cs, T, Cr, scal, out, ap;
+  size_t u, F, D, P22, Dg, T, Cr, scal, out, ap, rs;
 };
 
 Sizes sizes(const eftb_plan* p, int Bp) {
@@ -35,12 +35,13 @@ Sizes sizes(const eftb_plan* p, int Bp) {
   z.F = (size_t)c.front_rows * Bp;
   z.D = (size_t)EFTB_NCH * (c.Nmax + 1) * 2 * Bp;
   z.P22 = (size_t)EFTB_N22 * c.Nk * Bp;
-  z.Cs = (size_t)c.Nl * EFTB_NCH * c.Ns * Bp;
+  z.Dg = (size_t)c.Nl * 12 * (c.Nmax + 1) * 2 * Bp;
   z.T = (size_t)c.Nl * c.Nk * c.nterm * Bp;
   z.Cr = (size_t)c.Nl * (14 + (c.with_nnlo ? 1 : 0)) * c.Ns * Bp;
   z.scal = (size_t)3 * Bp;
   z.out = c.has_project ? (size_t)c.nout * c.nterm * Bp : 0;
   z.ap = c.has_ap ? ap_scratch_doubles(p, Bp) : 0;
+  z.rs = c.has_resum ? resum_scratch_doubles(p, Bp) : 0;
   return z;
 }
 
@@ -165,9 +166,9 @@ void eftb_plan_destroy(eftb_plan* p) {
 size_t eftb_workspace_bytes(const eftb_plan* p, int B) {
   if (!p || B < 1) return 0;
   Sizes z = sizes(p, eftb_padded_batch(B));
-  // u | F | D (later reused for the spline coefficients and the AP output) | P22 | Cs | T | Cr | f,DA,H | out | AP operator
+  // u | F | D (later reused for the spline coefficients and the AP output) | P22 | Dg | T | Cr | f,DA,H | out | AP operator
   size_t dreg = z.D > 2 * z.T ? z.D : 2 * z.T;
-  return (z.u + z.F + dreg + z.P22 + z.Cs + z.T + z.Cr + z.scal + z.out + z.ap) * sizeof(double);
+  return (z.u + z.F + dreg + z.P22 + z.Dg + z.T + z.Cr + z.scal + z.out + z.ap + z.rs) * sizeof(double);
 }
 
 int eftb_to_batch_minor(const double* in, int B, int R, double* out, void* stream) {
@@ -192,7 +193,7 @@ int eftb_front(const eftb_plan* p, int B, const double* plin, double* u, double*
   const int Bp = eftb_padded_batch(B);
   int rc = launch_front_prepare(p, B, Bp, plin, u, s);
   if (rc) return rc;
-  return gemm_run(p->Wf, u, F, Bp, 1, 1, 0, 0, 0, s);
+  return gemm_run(p->Wf, u, F, Bp, 1, 1, 0, 0, 0, 0, s);
 }
 
 int eftb_antidiag(const eftb_plan* p, int B, const double* F, double* D, void* stream) {
@@ -206,21 +207,42 @@ int eftb_spectral(const eftb_plan* p, int B, const double* D, double* P22, doubl
   const eftb_config& c = p->cfg;
   const int Bp = eftb_padded_batch(B);
   const size_t dch = (size_t)(c.Nmax + 1) * 2 * Bp;
-  int rc = gemm_run(p->Ak, D, P22, Bp, EFTB_N22, EFTB_N22, dch, 0, (size_t)c.Nk * Bp, s);
+  int rc = gemm_run(p->Ak, D, P22, Bp, EFTB_N22, EFTB_N22, dch, 0, (size_t)c.Nk * Bp, 0, s);
   if (rc) return rc;
-  return gemm_run(p->As, D, Cs, Bp, c.Nl * EFTB_NCH, EFTB_NCH, dch, 0, (size_t)c.Ns * Bp, s);
+  return gemm_run(p->As, D, Cs, Bp, c.Nl * EFTB_NCH, EFTB_NCH, dch, 0, (size_t)c.Ns * Bp, (size_t)EFTB_NCH * c.Ns * Bp, s);
+}
+
+int eftb_spectral_grouped(const eftb_plan* p, int B, const double* D, const double* f, double* Dg, double* P22, double* Cr,
+                          void* stream) {
+  EFTB_NEED(p && D && f && Dg && P22 && Cr && B >= 1, "NULL/invalid argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const eftb_config& c = p->cfg;
+  const int Bp = eftb_padded_batch(B);
+  const size_t dch = (size_t)(c.Nmax + 1) * 2 * Bp, srow = (size_t)c.Ns * Bp;
+  const int ncr = 14 + (c.with_nnlo ? 1 : 0);
+  int rc = launch_regroup(p, Bp, D, f, Dg, s);
+  if (rc) return rc;
+  if ((rc = gemm_run(p->Ak, D, P22, Bp, EFTB_N22, EFTB_N22, dch, 0, (size_t)c.Nk * Bp, 0, s))) return rc;
+  // Cloopl[l][r] = As[l] @ Dg[l][r], written straight into rows 2..13 of Cr[l]
+  return gemm_run(p->As, Dg, Cr + 2 * srow, Bp, c.Nl * 12, 12, dch, 12 * dch, srow, (size_t)ncr * srow, s);
 }
 
 int eftb_group(const eftb_plan* p, int B, const double* F, const double* P22, const double* Cs, const double* f, double* T,
                double* Cr, void* stream) {
-  EFTB_NEED(p && F && P22 && Cs && f && T && Cr && B >= 1, "NULL/invalid argument");
+  EFTB_NEED(p && F && P22 && f && T && Cr && B >= 1, "NULL/invalid argument");
   return launch_group(p, eftb_padded_batch(B), F, P22, Cs, f, T, Cr, (cudaStream_t)stream);
 }
 
-int eftb_resum(const eftb_plan* p, int B, const double* F, const double* Cr, const double* f, double* T, void* stream) {
-  EFTB_NEED(p && F && Cr && f && T && B >= 1, "NULL/invalid argument");
+size_t eftb_resum_scratch_bytes(const eftb_plan* p, int B) {
+  if (!p || B < 1 || !p->cfg.has_resum) return 0;
+  return resum_scratch_doubles(p, eftb_padded_batch(B)) * sizeof(double);
+}
+
+int eftb_resum(const eftb_plan* p, int B, const double* F, const double* Cr, const double* f, double* T, double* scratch,
+               void* stream) {
+  EFTB_NEED(p && F && Cr && f && T && scratch && B >= 1, "NULL/invalid argument");
   if (!p->cfg.has_resum) { eftb_set_error("eftb_resum: plan built without IR resummation"); return EFTB_ERR_NOT_BUILT; }
-  return launch_resum(p, B, eftb_padded_batch(B), F, Cr, f, T, (cudaStream_t)stream);
+  return launch_resum(p, B, eftb_padded_batch(B), F, Cr, f, T, scratch, (cudaStream_t)stream);
 }
 
 size_t eftb_ap_scratch_bytes(const eftb_plan* p, int B) {
@@ -235,7 +257,7 @@ static int ap_stage(const eftb_plan* p, int B, const double* Tin, const double* 
   const int Bp = eftb_padded_batch(B);
   const size_t per_l = (size_t)c.Nk * c.nterm * Bp;
   // B-spline coefficients of every term row: coef[l] = Cinv @ T[l]  (N = nterm*Bp columns)
-  int rc = gemm_run(p->Cinv, Tin, coef, c.nterm * Bp, c.Nl, c.Nl, per_l, 0, per_l, s);
+  int rc = gemm_run(p->Cinv, Tin, coef, c.nterm * Bp, c.Nl, c.Nl, per_l, 0, per_l, 0, s);
   if (rc) return rc;
   if (Bp > B) {  // pad lanes are not processed by the per-cosmology kernels: keep them finite
     EFTB_CUDA_CHECK(cudaMemcpyAsync(Tout, Tin, (size_t)c.Nl * per_l * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -256,7 +278,7 @@ int eftb_project(const eftb_plan* p, int B, const double* T, double* out, void* 
   EFTB_NEED(p && T && out && B >= 1, "NULL/invalid argument");
   if (!p->cfg.has_project) { eftb_set_error("eftb_project: plan built without projection"); return EFTB_ERR_NOT_BUILT; }
   const int Bp = eftb_padded_batch(B);
-  return gemm_run(p->project, T, out, p->cfg.nterm * Bp, 1, 1, 0, 0, 0, (cudaStream_t)stream);
+  return gemm_run(p->project, T, out, p->cfg.nterm * Bp, 1, 1, 0, 0, 0, 0, (cudaStream_t)stream);
 }
 
 int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double* f, const double* DA, const double* H,
@@ -273,7 +295,7 @@ int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double*
   double* F = w;            w += z.F;
   double* D = w;            w += (z.D > 2 * z.T ? z.D : 2 * z.T);
   double* P22 = w;          w += z.P22;
-  double* Cs = w;           w += z.Cs;
+  double* Dg = w;           w += z.Dg;
   double* T = w;            w += z.T;
   double* Cr = w;           w += z.Cr;
   double* scal = w;         w += z.scal;
@@ -286,9 +308,9 @@ int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double*
     if ((rc = launch_to_batch_minor(H, B, Bp, 1, scal + 2 * (size_t)Bp, s))) return rc;
   }
   if ((rc = launch_antidiag(p, Bp, F, D, s))) return rc;
-  if ((rc = eftb_spectral(p, B, D, P22, Cs, stream))) return rc;
-  if ((rc = launch_group(p, Bp, F, P22, Cs, scal, T, Cr, s))) return rc;
-  if (c.has_resum && (rc = launch_resum(p, B, Bp, F, Cr, scal, T, s))) return rc;
+  if ((rc = eftb_spectral_grouped(p, B, D, scal, Dg, P22, Cr, stream))) return rc;
+  if ((rc = launch_group(p, Bp, F, P22, nullptr, scal, T, Cr, s))) return rc;
+  if (c.has_resum && (rc = launch_resum(p, B, Bp, F, Cr, scal, T, out + z.out + z.ap, s))) return rc;
   double* cur = T;
   if (c.has_ap) {
     double* coef = D;
@@ -327,7 +349,7 @@ void eftb_operator_destroy(eftb_operator* op) {
 
 int eftb_operator_apply(const eftb_operator* op, const double* X, double* C, int N, void* stream) {
   if (!op || !X || !C || N < 32 || N % 32) { eftb_set_error("eftb_operator_apply: bad argument (N must be a multiple of 32)"); return EFTB_ERR_ARG; }
-  return gemm_run(op->A, X, C, N, 1, 1, 0, 0, 0, (cudaStream_t)stream);
+  return gemm_run(op->A, X, C, N, 1, 1, 0, 0, 0, 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

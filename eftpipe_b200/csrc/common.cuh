@@ -38,18 +38,18 @@ struct GemmMatrix {       // device copy of a fixed operator, padded for the ker
 };
 int gemm_upload(const double* host, int nbatch, int M, int K, GemmMatrix* out);
 void gemm_free(GemmMatrix* m);
-// z-batch: zb in [0, nz): A matrix index = zb / zdiv (if A has >1 batch), X offset = (zb % zdiv)*xs + (zb / zdiv)*xs2,
-// C offset = zb * cs
+// z-batch: zb in [0, nz), zq = zb / zdiv, zr = zb % zdiv: A matrix index = zq (if A has >1 batch),
+// X offset = zr*xs + zq*xs2, C offset = zr*cs + zq*cs2
 int gemm_run(const GemmMatrix& A, const double* X, double* C, int N, int nz, int zdiv, size_t xs, size_t xs2,
-             size_t cs, cudaStream_t stream);
+             size_t cs, size_t cs2, cudaStream_t stream);
 
 struct AntidiagPack;  // fragment-ordered pair table + warp schedules (antidiag.cu)
 
 // IR-resummation constants in kernel layout (resum.cu resum_pack)
 struct ResumPack {
   double *qpack = nullptr, *Rt = nullptr;  // [qdeg][2][Nl][Nl][NIR][4],  [Na][NsP][Nkr]
-  int NsP = 0;
-  int slot_v[3][4] = {}, slot_kind[3][4] = {}, nslot[3] = {};
+  int NsP = 0, NQ = 0;
+  int nslot[3] = {};  // canonical slots per l': (X, v = l'), (Y, 0), (Y, 1)[, (Y, 2)]
 };
 
 // ---- plan ---------------------------------------------------------------------------------------
@@ -74,9 +74,11 @@ void antidiag_free(eftb_plan* p);
 int launch_front_prepare(const eftb_plan* p, int B, int Bp, const double* plin, double* u, cudaStream_t s);
 int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cudaStream_t s);
 int launch_group(const eftb_plan* p, int Bp, const double* F, const double* P22, const double* Cs,
-                 const double* f, double* T, double* Cr, cudaStream_t s);
+                 const double* f, double* T, double* Cr, cudaStream_t s);  // Cs == NULL: Cloopl rows of Cr already filled
+int launch_regroup(const eftb_plan* p, int Bp, const double* D, const double* f, double* Dg, cudaStream_t s);
 int launch_resum(const eftb_plan* p, int B, int Bp, const double* F, const double* Cr, const double* f,
-                 double* T, cudaStream_t s);
+                 double* T, double* scratch, cudaStream_t s);
+size_t resum_scratch_doubles(const eftb_plan* p, int B);  // expanded Q(f): [B][2 Nl Nl NIR 4]
 int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const double* Tin, const double* DA,
               const double* H, double* scratch, double* Tout, cudaStream_t s);
 size_t ap_scratch_doubles(const eftb_plan* p, int B);  // banded AP operator G + window metadata

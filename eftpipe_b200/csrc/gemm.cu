@@ -24,7 +24,7 @@ struct GemmArgs {
   double* C;
   int M, K, Kp, Mp, N;
   int a_batched, zdiv;
-  size_t xs, xs2, cs;
+  size_t xs, xs2, cs, cs2;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
   const int zq = zb / g.zdiv, zr = zb % g.zdiv;
   const double* A = g.A + (g.a_batched ? (size_t)zq * g.Mp * g.Kp : 0) + (size_t)m0 * g.Kp;
   const double* X = g.X + (size_t)zr * g.xs + (size_t)zq * g.xs2;
-  double* C = g.C + (size_t)zb * g.cs;
+  double* C = g.C + (size_t)zr * g.cs + (size_t)zq * g.cs2;
 
   double acc[MT][4][2];
 #pragma unroll
@@ -179,9 +179,9 @@ void gemm_free(GemmMatrix* m) {
 }
 
 int gemm_run(const GemmMatrix& A, const double* X, double* C, int N, int nz, int zdiv, size_t xs, size_t xs2,
-             size_t cs, cudaStream_t stream) {
+             size_t cs, size_t cs2, cudaStream_t stream) {
   if (!A.d || !X || !C || N % 2) { eftb_set_error("gemm_run: bad arguments"); return EFTB_ERR_ARG; }
-  GemmArgs g{A.d, X, C, A.M, A.K, A.Kp, A.Mp, N, A.nbatch > 1 ? 1 : 0, zdiv, xs, xs2, cs};
+  GemmArgs g{A.d, X, C, A.M, A.K, A.Kp, A.Mp, N, A.nbatch > 1 ? 1 : 0, zdiv, xs, xs2, cs, cs2};
   switch (A.MT) {
     case 10: return launch<10>(g, nz, stream);
     case 9: return launch<9>(g, nz, stream);

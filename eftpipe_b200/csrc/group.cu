@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(128) group_kernel(GroupArgs a) {
       out[0] = a.F[(size_t)(a.row_c11 + l * a.Ns + s) * Bp + b];
       out[rs] = a.F[(size_t)(a.row_cct + l * a.Ns + s) * Bp + b];
       if (a.with_nnlo) out[14 * rs] = a.F[(size_t)(a.row_cctnnlo + l * a.Ns + s) * Bp + b];
+      if (!a.Cs) continue;  // Cloopl rows were produced by the grouped spectral GEMM
       const double* cs = a.Cs + ((size_t)(l * EFTB_NCH) * a.Ns + s) * Bp + b;
       double row[12];
 #pragma unroll
@@ -95,7 +96,50 @@ __global__ void __launch_bounds__(128) group_kernel(GroupArgs a) {
   }
 }
 
+// Dg[l][r][t2][b] = sum over the members (r, p, ch) of reducePsCfl's row r of  f^p * l22|l13[l][ch] * D[ch][t2][b]:
+// the Legendre weighting and f-power grouping of the configuration-space loop terms (pybird.py:805-846) applied
+// BEFORE the linear D -> C(s) transform, so that the transform runs on Nl*12 instead of Nl*38 channels.
+__global__ void __launch_bounds__(128) regroup_kernel(const double* __restrict__ D, const double* __restrict__ f,
+                                                      const double* __restrict__ l22, const double* __restrict__ l13, int Nl,
+                                                      int nt2, int Bp, double* __restrict__ Dg) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x, t2 = blockIdx.y;
+  if (b >= Bp) return;
+  const size_t chs = (size_t)nt2 * Bp;
+  const double f1 = f[b];
+  double fp[5];
+  fp[0] = 1.0;
+#pragma unroll
+  for (int i = 1; i < 5; ++i) fp[i] = fp[i - 1] * f1;
+  double v[EFTB_NCH];
+  const double* src = D + (size_t)t2 * Bp + b;
+#pragma unroll
+  for (int c = 0; c < EFTB_NCH; ++c) v[c] = src[(size_t)c * chs];
+  for (int l = 0; l < Nl; ++l) {
+    double row[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) row[i] = 0.0;
+#define ACC22(r, p, t) row[r] = fma(fp[p] * l22[l * EFTB_N22 + t], v[t], row[r]);
+#define ACC13(r, p, t) row[r] = fma(fp[p] * l13[l * EFTB_N13 + t], v[EFTB_N22 + t], row[r]);
+    EFTB_G22(ACC22)
+    EFTB_G13(ACC13)
+#undef ACC22
+#undef ACC13
+    double* dst = Dg + ((size_t)(l * 12) * nt2 + t2) * Bp + b;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) dst[(size_t)i * chs] = row[i];
+  }
+}
+
 }  // namespace
+
+int launch_regroup(const eftb_plan* p, int Bp, const double* D, const double* f, double* Dg, cudaStream_t s) {
+  const eftb_config& c = p->cfg;
+  const int nt2 = 2 * (c.Nmax + 1);
+  dim3 grid((Bp + 127) / 128, nt2);
+  regroup_kernel<<<grid, 128, 0, s>>>(D, f, p->l22, p->l13, c.Nl, nt2, Bp, Dg);
+  EFTB_LAUNCH_CHECK();
+  return EFTB_OK;
+}
 
 int launch_group(const eftb_plan* p, int Bp, const double* F, const double* P22, const double* Cs, const double* f,
                  double* T, double* Cr, cudaStream_t s) {

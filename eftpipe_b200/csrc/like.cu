@@ -299,7 +299,7 @@ int eftb_like_eval(const eftb_like* L, int B, const double* const* terms, const 
   double* Y = V + (size_t)nd * nc * Bp;
   int rc = fill_vectors(L, Bp, terms, fgrowth, nuis, V, s);
   if (rc) return rc;
-  rc = gemm_run(L->invcov, V, Y, nc * Bp, 1, 1, 0, 0, 0, s);
+  rc = gemm_run(L->invcov, V, Y, nc * Bp, 1, 1, 0, 0, 0, 0, s);
   if (rc) return rc;
   FinArgs a{V, Y, L->sigma_inv, L->sigma_inv_mu, L->mu_sigma_mu, logp, bestfit, status, B, Bp, nd, L->cfg.ngauss, L->cfg.jeffreys};
   const int nG = L->cfg.ngauss;

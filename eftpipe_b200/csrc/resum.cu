@@ -28,9 +28,9 @@ constexpr int RS_SLOTS = 4;  // polynomial slots per l'
 
 struct ResumArgs {
   const double *F, *Cr, *f, *Rt, *qpack, *kr2, *l11, *lct, *lctnnlo;
-  double* T;
-  int B, Bp, Nk, Ns, NsP, nterm, ncr, Nkr, Nklow, qdeg, row_x, row_y;
-  int slot_v[3][RS_SLOTS], slot_kind[3][RS_SLOTS], nslot[3];
+  double *T, *Qf;   // Qf: [B][NQ] expanded Q(f) (scratch)
+  int B, Bp, Nk, Ns, NsP, nterm, ncr, Nkr, Nklow, qdeg, row_x, row_y, NQ;
+  int nslot[3];     // canonical slots of l': 0 = (X, v = l'), 1 + v = (Y, v); nslot = 1 + number of Y orders used
 };
 
 template <int NL, bool NNLO>
@@ -47,10 +47,11 @@ struct Accum {
 };
 
 // Horner sweep of NS polynomial slots for a = 0 and a = 1 over the RS_C points of a chunk, then the weighted
-// slot sum  T_a[c] = sum_slot w[slot][c] P_a[slot][c]
-template <int NIR, int NS>
+// slot sum  T_a[c] = R[l'][c] z[c] P_a[0][c] + Y k^2 [c] sum_v R[v][c] P_a[1+v][c]
+template <int NIR, int NS, int NL>
 __device__ __forceinline__ void horner(const double* __restrict__ q0, const double* __restrict__ q1, const double (&z)[RS_C],
-                                       const double (&w)[RS_SLOTS][RS_C], double (&T0)[RS_C], double (&T1)[RS_C]) {
+                                       const double (&yk)[RS_C], const double (&Rv)[NL][RS_C], int lp, double (&T0)[RS_C],
+                                       double (&T1)[RS_C]) {
   double P0[NS][RS_C], P1[NS][RS_C];
 #pragma unroll
   for (int s = 0; s < NS; ++s)
@@ -73,20 +74,28 @@ __device__ __forceinline__ void horner(const double* __restrict__ q0, const doub
   }
 #pragma unroll
   for (int c = 0; c < RS_C; ++c) {
-    double t0 = 0.0, t1 = 0.0;
+    double y0 = 0.0, y1 = 0.0;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      t0 = fma(w[s][c], P0[s][c], t0);
-      t1 = fma(w[s][c], P1[s][c], t1);
+    for (int v = 0; v < NS - 1; ++v) {
+      y0 = fma(Rv[v][c], P0[1 + v][c], y0);
+      y1 = fma(Rv[v][c], P1[1 + v][c], y1);
     }
-    T0[c] = t0;
-    T1[c] = t1;
+    const double wx = Rv[lp][c] * z[c];
+    T0[c] = fma(wx, P0[0][c], yk[c] * y0);
+    T1[c] = fma(wx, P1[0][c], yk[c] * y1);
   }
 }
 
 template <int NL, int NIR, bool NNLO>
 __device__ __forceinline__ void sweep_chunk(const ResumArgs& a, const double* Qs, const double* Xs, const double* Ys,
                                             const double* Cs, int l, int ik, double k2, int s0, Accum<NL, NNLO>& A) {
+  // R[v,k,s] of this chunk, shared by every l' (Rt is [v][s][k]: lanes = k read contiguously).  Issued first and
+  // consumed only after the first Horner sweep, which hides the L1/L2 latency.
+  double Rv[NL][RS_C];
+#pragma unroll
+  for (int v = 0; v < NL; ++v)
+#pragma unroll
+    for (int c = 0; c < RS_C; ++c) Rv[v][c] = __ldg(a.Rt + ((size_t)v * a.NsP + s0 + c) * a.Nkr + ik);
   double z[RS_C], yk[RS_C];
   {
     const double2 x01 = *reinterpret_cast<const double2*>(Xs + s0), x23 = *reinterpret_cast<const double2*>(Xs + s0 + 2);
@@ -96,21 +105,11 @@ __device__ __forceinline__ void sweep_chunk(const ResumArgs& a, const double* Qs
   }
 #pragma unroll
   for (int lp = 0; lp < NL; ++lp) {
-    // slot weights R[v,k,s] * (z | Y k^2); Rt is [v][s][k] so that the lanes (k) read contiguously
-    double w[RS_SLOTS][RS_C];
-#pragma unroll
-    for (int sl = 0; sl < RS_SLOTS; ++sl) {
-      const bool on = sl < a.nslot[lp];
-      const double* rr = a.Rt + ((size_t)(on ? a.slot_v[lp][sl] : 0) * a.NsP + s0) * a.Nkr + ik;
-      const bool isy = a.slot_kind[lp][sl] != 0;
-#pragma unroll
-      for (int c = 0; c < RS_C; ++c) w[sl][c] = on ? __ldg(rr + (size_t)c * a.Nkr) * (isy ? yk[c] : z[c]) : 0.0;
-    }
     const double* q0 = Qs + (size_t)(((0 * NL + l) * NL + lp) * NIR) * RS_SLOTS;
     const double* q1 = Qs + (size_t)(((1 * NL + l) * NL + lp) * NIR) * RS_SLOTS;
     double T0[RS_C], T1[RS_C];
-    if (a.nslot[lp] > 3) horner<NIR, 4>(q0, q1, z, w, T0, T1);
-    else horner<NIR, 3>(q0, q1, z, w, T0, T1);
+    if (a.nslot[lp] > 3) horner<NIR, 4, NL>(q0, q1, z, yk, Rv, lp, T0, T1);
+    else horner<NIR, 3, NL>(q0, q1, z, yk, Rv, lp, T0, T1);
     const double* crow = Cs + (size_t)lp * a.ncr * a.NsP + s0;
     {
       const double2 c01 = *reinterpret_cast<const double2*>(crow), c23 = *reinterpret_cast<const double2*>(crow + 2);
@@ -142,22 +141,22 @@ __device__ __forceinline__ void write_out(const ResumArgs& a, int b, int l, int 
     double v = 0.0;
 #pragma unroll
     for (int lp = 0; lp < NL; ++lp) v = fma(a.l11[lp * 3 + i], A.lin0[lp], v);
-    out[(size_t)i * Bp] += v;  // pybird.py:1442, :1445
+    atomicAdd(out + (size_t)i * Bp, v);  // pybird.py:1442, :1445 (RED: nobody else touches this element)
   }
   for (int i = 0; i < 6; ++i) {
     double v = 0.0;
 #pragma unroll
     for (int lp = 0; lp < NL; ++lp) v = fma(a.lct[lp * 6 + i], A.lin1[lp], v);
-    out[(size_t)(3 + i) * Bp] += v;  // pybird.py:1443, :1446
+    atomicAdd(out + (size_t)(3 + i) * Bp, v);  // pybird.py:1443, :1446
   }
 #pragma unroll
-  for (int i = 0; i < 12; ++i) out[(size_t)(9 + i) * Bp] += A.loop[i];  // pybird.py:1444, :1462
+  for (int i = 0; i < 12; ++i) atomicAdd(out + (size_t)(9 + i) * Bp, A.loop[i]);  // pybird.py:1444, :1462
   if (NNLO)
     for (int i = 0; i < 3; ++i) {
       double v = 0.0;
 #pragma unroll
       for (int lp = 0; lp < NL; ++lp) v = fma(a.lctnnlo[lp * 3 + i], A.nnlo[lp], v);
-      out[(size_t)(24 + i) * Bp] += v;  // pybird.py:1455-1458
+      atomicAdd(out + (size_t)(24 + i) * Bp, v);  // pybird.py:1455-1458
     }
 }
 
@@ -177,22 +176,21 @@ __global__ void __launch_bounds__(RS_THREADS, 2) resum_kernel(ResumArgs a) {
   double* Cs = Ys + a.NsP;               // [NL][ncr][NsP]
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t Bp = a.Bp;
-  const double f1 = a.f[b];
 
   for (int s = tid; s < a.NsP; s += RS_THREADS) {
     const bool ok = s < a.Ns;
     Xs[s] = ok ? a.F[(size_t)(a.row_x + s) * Bp + b] : 0.0;
     Ys[s] = ok ? a.F[(size_t)(a.row_y + s) * Bp + b] : 0.0;
   }
+#pragma unroll 8
   for (int i = tid; i < NL * a.ncr * a.NsP; i += RS_THREADS) {
     const int s = i % a.NsP, r = i / a.NsP;
     Cs[i] = s < a.Ns ? a.Cr[((size_t)r * a.Ns + s) * Bp + b] : 0.0;
   }
-  // Q^{ll'}(f): polynomials in f (pybird.py:1367-1380 evaluates the reference's lambdas); qpack is [qdeg][NQ]
-  for (int i = tid; i < NQ; i += RS_THREADS) {
-    double v = 0.0;
-    for (int d = a.qdeg - 1; d >= 0; --d) v = fma(v, f1, __ldg(a.qpack + (size_t)d * NQ + i));
-    Qs[i] = v;
+  {  // Q^{ll'}(f) of this cosmology, expanded by resum_q_kernel
+    const double* qf = a.Qf + (size_t)b * NQ;
+#pragma unroll
+    for (int i = tid; i < NQ; i += RS_THREADS) Qs[i] = qf[i];
   }
   __syncthreads();
 
@@ -227,8 +225,27 @@ __global__ void __launch_bounds__(RS_THREADS, 2) resum_kernel(ResumArgs a) {
   }
 }
 
+// Q^{ll'}_u(f) = sum_d q[u][d] f^d for every cosmology (pybird.py:1367-1380 evaluates the reference's lambdas);
+// qpack is [qdeg][NQ] so that consecutive threads read consecutive entries; Qf is [B][NQ]
+__global__ void __launch_bounds__(256) resum_q_kernel(const double* __restrict__ qpack, const double* __restrict__ f, int NQ,
+                                                      int qdeg, int B, double* __restrict__ Qf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= NQ || b >= B) return;
+  const double f1 = f[b];
+  double c[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) c[d] = d < qdeg ? __ldg(qpack + (size_t)d * NQ + i) : 0.0;
+  double v = 0.0;
+#pragma unroll
+  for (int d = 15; d >= 0; --d) v = fma(v, f1, c[d]);
+  Qf[(size_t)b * NQ + i] = v;
+}
+
 template <int NL, int NIR, bool NNLO>
 int run(const ResumArgs& a, cudaStream_t s) {
+  dim3 qgrid((a.NQ + 255) / 256, a.B);
+  resum_q_kernel<<<qgrid, 256, 0, s>>>(a.qpack, a.f, a.NQ, a.qdeg, a.B, a.Qf);
+  EFTB_LAUNCH_CHECK();
   size_t smem = sizeof(double) * ((size_t)2 * NL * NL * NIR * RS_SLOTS + 2 * a.NsP + (size_t)NL * a.ncr * a.NsP);
   static size_t configured = 0;
   if (smem > configured) {
@@ -242,16 +259,20 @@ int run(const ResumArgs& a, cudaStream_t s) {
 
 }  // namespace
 
-// Host-side packing at plan creation: transposed, s-padded operator Rt[v][NsP][Nkr]; per-l' slot list of the
-// non-vanishing polynomials; coefficient table qpack[d][a][l][l'][p][slot].
+// Host-side packing at plan creation: transposed, s-padded operator Rt[v][NsP][Nkr]; the canonical slot
+// structure of Q^{ll'} (slot 0 = (X, v = l'), slot 1 + v = (Y, v)) is verified against the table; coefficient
+// table qpack[d][a][l][l'][p][slot].
 int resum_pack(eftb_plan* p, const double* R, const double* q) {
   const eftb_config& c = p->cfg;
   const int Nl = c.Nl, NIR = c.NIR, Na = c.Na, Nn = 2 * NIR * Na, NsP = eftb_round_up(c.Ns, RS_C);
-  if (Nl > 3) { eftb_set_error("resum: Nl > 3 unsupported"); return EFTB_ERR_ARG; }
+  if (Nl > 3 || Na != Nl || Na + 1 > RS_SLOTS || c.qdeg > 16) {
+    eftb_set_error("resum: unsupported sizes Nl=%d Na=%d qdeg=%d", Nl, Na, c.qdeg);
+    return EFTB_ERR_ARG;
+  }
   auto qat = [&](int a, int l, int lp, int u, int d) { return q[((((size_t)a * Nl + l) * Nl + lp) * Nn + u) * c.qdeg + d]; };
   ResumPack& P = p->rs;
   for (int lp = 0; lp < Nl; ++lp) {
-    int ns = 0;
+    int ymax = -1;
     for (int kind = 0; kind < 2; ++kind)
       for (int v = 0; v < Na; ++v) {
         bool any = false;
@@ -260,13 +281,13 @@ int resum_pack(eftb_plan* p, const double* R, const double* q) {
             for (int pp = 0; pp < NIR && !any; ++pp)
               for (int d = 0; d < c.qdeg && !any; ++d) any = qat(a, l, lp, (kind * NIR + pp) * Na + v, d) != 0.0;
         if (!any) continue;
-        if (ns == RS_SLOTS) { eftb_set_error("resum: more than %d non-zero (kind, v) polynomials for l'=%d", RS_SLOTS, lp); return EFTB_ERR_ARG; }
-        P.slot_v[lp][ns] = v;
-        P.slot_kind[lp][ns] = kind;
-        ++ns;
+        if (kind == 0 && v != lp) {
+          eftb_set_error("resum: Q table couples X^p of l'=%d to Bessel order %d (expected %d only)", lp, v, lp);
+          return EFTB_ERR_ARG;
+        }
+        if (kind == 1) ymax = v;
       }
-    P.nslot[lp] = ns;
-    for (int s = ns; s < RS_SLOTS; ++s) P.slot_v[lp][s] = P.slot_kind[lp][s] = 0;
+    P.nslot[lp] = 2 + ymax < 3 ? 3 : 2 + ymax;  // kernels are instantiated for 3 and 4 slots
   }
   const size_t NQ = (size_t)2 * Nl * Nl * NIR * RS_SLOTS;
   std::vector<double> qp(NQ * c.qdeg, 0.0), rt((size_t)Na * NsP * c.Nkr, 0.0);
@@ -274,15 +295,16 @@ int resum_pack(eftb_plan* p, const double* R, const double* q) {
     for (int l = 0; l < Nl; ++l)
       for (int lp = 0; lp < Nl; ++lp)
         for (int pp = 0; pp < NIR; ++pp)
-          for (int s = 0; s < P.nslot[lp]; ++s) {
+          for (int s = 0; s < 1 + Na; ++s) {
             const size_t e = ((((size_t)a * Nl + l) * Nl + lp) * NIR + pp) * RS_SLOTS + s;
-            const int u = (P.slot_kind[lp][s] * NIR + pp) * Na + P.slot_v[lp][s];
+            const int u = s == 0 ? pp * Na + lp : (NIR + pp) * Na + (s - 1);
             for (int d = 0; d < c.qdeg; ++d) qp[(size_t)d * NQ + e] = qat(a, l, lp, u, d);
           }
   for (int v = 0; v < Na; ++v)
     for (int k = 0; k < c.Nkr; ++k)
       for (int s = 0; s < c.Ns; ++s) rt[((size_t)v * NsP + s) * c.Nkr + k] = R[((size_t)v * c.Nkr + k) * c.Ns + s];
   P.NsP = NsP;
+  P.NQ = (int)NQ;
   EFTB_CUDA_CHECK(cudaMalloc((void**)&P.qpack, qp.size() * sizeof(double)));
   EFTB_CUDA_CHECK(cudaMemcpy(P.qpack, qp.data(), qp.size() * sizeof(double), cudaMemcpyHostToDevice));
   EFTB_CUDA_CHECK(cudaMalloc((void**)&P.Rt, rt.size() * sizeof(double)));
@@ -290,18 +312,17 @@ int resum_pack(eftb_plan* p, const double* R, const double* q) {
   return EFTB_OK;
 }
 
+size_t resum_scratch_doubles(const eftb_plan* p, int B) { return (size_t)p->rs.NQ * B; }
+
 int launch_resum(const eftb_plan* p, int B, int Bp, const double* F, const double* Cr, const double* f, double* T,
-                 cudaStream_t s) {
+                 double* scratch, cudaStream_t s) {
   const eftb_config& c = p->cfg;
   ResumArgs a;
   a.F = F; a.Cr = Cr; a.f = f; a.Rt = p->rs.Rt; a.qpack = p->rs.qpack; a.kr2 = p->kr2; a.l11 = p->l11; a.lct = p->lct;
-  a.lctnnlo = p->lctnnlo; a.T = T; a.B = B; a.Bp = Bp; a.Nk = c.Nk; a.Ns = c.Ns; a.NsP = p->rs.NsP; a.nterm = c.nterm;
-  a.ncr = 14 + (c.with_nnlo ? 1 : 0); a.Nkr = c.Nkr; a.Nklow = c.Nklow; a.qdeg = c.qdeg;
-  a.row_x = c.row_x; a.row_y = c.row_y;
-  for (int lp = 0; lp < 3; ++lp) {
-    a.nslot[lp] = lp < c.Nl ? p->rs.nslot[lp] : 0;
-    for (int sl = 0; sl < RS_SLOTS; ++sl) { a.slot_v[lp][sl] = p->rs.slot_v[lp][sl]; a.slot_kind[lp][sl] = p->rs.slot_kind[lp][sl]; }
-  }
+  a.lctnnlo = p->lctnnlo; a.T = T; a.Qf = scratch; a.B = B; a.Bp = Bp; a.Nk = c.Nk; a.Ns = c.Ns; a.NsP = p->rs.NsP;
+  a.nterm = c.nterm; a.ncr = 14 + (c.with_nnlo ? 1 : 0); a.Nkr = c.Nkr; a.Nklow = c.Nklow; a.qdeg = c.qdeg;
+  a.row_x = c.row_x; a.row_y = c.row_y; a.NQ = p->rs.NQ;
+  for (int lp = 0; lp < 3; ++lp) a.nslot[lp] = lp < c.Nl ? p->rs.nslot[lp] : 0;
   const bool nnlo = c.with_nnlo != 0;
   if (c.Nl == 3 && c.NIR == 16 && c.Na == 3) return nnlo ? run<3, 16, true>(a, s) : run<3, 16, false>(a, s);
   if (c.Nl == 2 && c.NIR == 8 && c.Na == 2) return nnlo ? run<2, 8, true>(a, s) : run<2, 8, false>(a, s);

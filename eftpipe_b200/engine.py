@@ -72,6 +72,7 @@ class DevicePlan:
         self.handle, self.cfg = handle, cfg
         self._ws = None
         self._ap_scratch = None
+        self._rs_scratch = None
         if plan.project is not None:
             self.out_shape = (plan.out_shape[0], g.nterm, plan.out_shape[1])
         else:
@@ -137,17 +138,34 @@ class DevicePlan:
         _lib.check(self.lib.eftb_spectral(self.handle, B, _p(D), _p(P22), _p(Cs), _stream_ptr(self.torch)), "eftb_spectral")
         return P22, Cs
 
-    def group(self, F, P22, Cs, f_bm, B):
+    def spectral_grouped(self, D, f_bm, B):
+        """fused-path variant of `spectral`: returns (P22, Cr) with the Cloopl rows of Cr already filled"""
+        Bp = self.padded(B)
+        c = self.cfg
+        P22 = self._empty(N22, c.Nk, Bp)
+        Dg = self._empty(c.Nl, 12, c.Nmax + 1, 2, Bp)
+        Cr = self._empty(c.Nl, 14 + c.with_nnlo, c.Ns, Bp)
+        _lib.check(self.lib.eftb_spectral_grouped(self.handle, B, _p(D), _p(f_bm), _p(Dg), _p(P22), _p(Cr),
+                                                  _stream_ptr(self.torch)), "eftb_spectral_grouped")
+        return P22, Cr
+
+    def group(self, F, P22, Cs, f_bm, B, Cr=None):
+        """Cs=None with a `Cr` from `spectral_grouped`: only the k-space rows and C11/Cct are assembled"""
         Bp = self.padded(B)
         c = self.cfg
         T = self._empty(c.Nl, c.Nk, c.nterm, Bp)
-        Cr = self._empty(c.Nl, 14 + c.with_nnlo, c.Ns, Bp)
+        if Cr is None:
+            Cr = self._empty(c.Nl, 14 + c.with_nnlo, c.Ns, Bp)
         _lib.check(self.lib.eftb_group(self.handle, B, _p(F), _p(P22), _p(Cs), _p(f_bm), _p(T), _p(Cr),
                                        _stream_ptr(self.torch)), "eftb_group")
         return T, Cr
 
     def resum(self, F, Cr, f_bm, T, B):
-        _lib.check(self.lib.eftb_resum(self.handle, B, _p(F), _p(Cr), _p(f_bm), _p(T), _stream_ptr(self.torch)), "eftb_resum")
+        need = self.lib.eftb_resum_scratch_bytes(self.handle, int(B))
+        if self._rs_scratch is None or self._rs_scratch.numel() * 8 < need:
+            self._rs_scratch = self.torch.empty((need + 7) // 8, dtype=self.torch.float64, device="cuda")
+        _lib.check(self.lib.eftb_resum(self.handle, B, _p(F), _p(Cr), _p(f_bm), _p(T), _p(self._rs_scratch),
+                                       _stream_ptr(self.torch)), "eftb_resum")
         return T
 
     def ap(self, T, DA_bm, H_bm, B):

@@ -252,6 +252,15 @@ def resum_operator(g: GridConfig, NFFT=192):
                 kr2=g.kr**2)
 
 
+def resum_slot_count(rs):
+    """Number of (l', kind, v) polynomials of Q^{ll'} that do not vanish identically - the ones the resum
+    kernel evaluates (csrc/resum.cu resum_pack applies the same rule)."""
+    q, NIR, Na = rs["q"], rs["NIR"], rs["Na"]
+    Nl = q.shape[1]
+    nz = np.any(q.reshape(2, Nl, Nl, 2, NIR, Na, -1) != 0, axis=(0, 1, 4, 6))  # (l', kind, v)
+    return int(nz.sum())
+
+
 # --------------------------------------------------------------------------------------------
 # Alcock-Paczynski
 # --------------------------------------------------------------------------------------------

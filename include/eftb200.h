@@ -118,12 +118,20 @@ int eftb_front(const eftb_plan*, int B, const double* plin, double* u_scratch, d
 /* the quadratic part of makeP22 / makeC22 / makeC13 (pybird.py:1074-1078, :1103-1125) */
 int eftb_antidiag(const eftb_plan*, int B, const double* F, double* D, void* stream);
 int eftb_spectral(const eftb_plan*, int B, const double* D, double* P22, double* Cs, void* stream);
-/* Bird.setPsCfl / reducePsCfl / setPstl / subtractShotNoise (pybird.py:737-866); f: [Bp] */
+/* fused-path variant: the Legendre weighting + f-power grouping of the configuration-space loop terms
+   (reducePsCfl, pybird.py:805-846) is applied to D first (Dg_scratch: [Nl][12][Nmax+1][2][Bp]), so the
+   D -> C(s) transform runs on Nl*12 channels and writes Cloopl straight into rows 2..13 of Cr; f: [Bp] */
+int eftb_spectral_grouped(const eftb_plan*, int B, const double* D, const double* f, double* Dg_scratch,
+                          double* P22, double* Cr, void* stream);
+/* Bird.setPsCfl / reducePsCfl / setPstl / subtractShotNoise (pybird.py:737-866); f: [Bp].
+   Cs == NULL: the Cloopl rows of Cr were already produced by eftb_spectral_grouped */
 int eftb_group(const eftb_plan*, int B, const double* F, const double* P22, const double* Cs,
                const double* f, double* T, double* Cr, void* stream);
-/* Resum.Ps (pybird.py:1413-1464), in place on T */
+/* Resum.Ps (pybird.py:1413-1464), in place on T; scratch: eftb_resum_scratch_bytes(plan, B) bytes
+   (the bulk coefficients Q^{ll'}(f) of every point, pybird.py:1367-1380) */
+size_t eftb_resum_scratch_bytes(const eftb_plan*, int B);
 int eftb_resum(const eftb_plan*, int B, const double* F, const double* Cr, const double* f, double* T,
-               void* stream);
+               double* scratch, void* stream);
 /* APeffect.AP (pybird.py:1598-1621); DA,H: [Bp]; scratch: eftb_ap_scratch_bytes(plan, B) bytes (B-spline
    coefficients [Nl][Nk][nterm][Bp] + the per-cosmology banded resampling operator); Tout may not alias Tin */
 size_t eftb_ap_scratch_bytes(const eftb_plan*, int B);

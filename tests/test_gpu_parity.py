@@ -49,9 +49,14 @@ def stages(gpu, golden2):
     DA_bm, H_bm = dp.to_batch_minor(g["DA"])[0], dp.to_batch_minor(g["H"])[0]
     T_ap = dp.ap(T, DA_bm, H_bm, B)
     out = dp.project(T_ap, B)
+    # the fused pipeline's order: Legendre/f grouping of D before the D -> C(s) transform
+    P22g, Crg = dp.spectral_grouped(D, f_bm, B)
+    Tg, Crg = dp.group(F, P22g, None, f_bm, B, Cr=Crg)
+    dp.resum(F, Crg, f_bm, Tg, B)
+    outg = dp.project(dp.ap(Tg, DA_bm, H_bm, B), B)
     torch.cuda.synchronize()
     return dict(B=B, F=_np(F), D=_np(D), P22=_np(P22), Cs=_np(Cs), T_pre=_np(T_pre), Cr=_np(Cr), T_res=_np(T_res),
-                T_ap=_np(T_ap), out=_np(out))
+                T_ap=_np(T_ap), out=_np(out), Crg=_np(Crg), outg=_np(outg))
 
 
 def test_front(gpu, stages, golden2):
@@ -98,6 +103,9 @@ def test_terms(stages, golden2, stage, prefix):
 def test_cloopl(stages, golden2):
     B = stages["B"]
     assert rowmax_rel(stages["Cr"][:, 2:14, :, :B].transpose(3, 0, 1, 2), golden2["pre_Cloopl"]) <= TOL
+    # grouped variant (what the fused pipeline runs): same rows, and C11/Cct identical
+    assert rowmax_rel(stages["Crg"][:, 2:14, :, :B].transpose(3, 0, 1, 2), golden2["pre_Cloopl"]) <= TOL
+    np.testing.assert_array_equal(stages["Crg"][:, :2, :, :B], stages["Cr"][:, :2, :, :B])
 
 
 def test_projection(gpu, stages, golden2):
@@ -118,7 +126,8 @@ def test_fused_pipeline_equals_stages(gpu, stages, golden2):
     pm, bm = dp.eval_terms(g["plin"], g["f"], g["DA"], g["H"], want_bm=True)
     torch.cuda.synchronize()
     B = stages["B"]
-    np.testing.assert_array_equal(_np(bm)[..., :B], stages["out"][..., :B])
+    np.testing.assert_array_equal(_np(bm)[..., :B], stages["outg"][..., :B])
+    assert rowmax_rel(stages["outg"][..., :B], stages["out"][..., :B]) <= 1e-11
     T = helpers.split_terms(_np(pm))
     for name, arr in T.items():
         assert rowmax_rel(arr, g["bin_" + name]) <= TOL, name
