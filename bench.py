@@ -272,9 +272,10 @@ def run_ours(args):
         return logp, status
 
     # kernels launched per step (counted from the call graph of csrc/api.cu + like.cu):
-    # front: transpose+tails+gemm (3) | f,DA,H transposes (3) | antidiag (1) | spectral gemms (2) | group (1) | resum (1)
-    # | ap: gemm+kernel (2) | project gemm (1) | f, nuisance transposes (2) | like: vectors+gemm+finish (3)
-    launches["n"] = 19
+    # front: transpose+tails+gemm (3) | f,DA,H transposes (3) | antidiag (1) | spectral: regroup + 2 gemms (3) | group (1)
+    # | resum: Q(f) + sweep (2) | ap: gemm + geom + apply (3) | project gemm (1) | f, nuisance transposes (2)
+    # | like: vectors+gemm+finish (3)
+    launches["n"] = 22
 
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")  # > 126 MB L2
     for _ in range(args.warmup):
@@ -332,8 +333,10 @@ def run_ours(args):
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gathered = [torch.empty_like(logp) for _ in range(world)]
-        dist.all_gather(gathered, logp)  # the only cross-GPU traffic of the path: per-point log-likelihoods
+        from eftpipe_b200.shard import gather_points
+
+        all_logp = gather_points(logp, B * world)  # the only cross-GPU traffic of the path: per-point log-likelihoods
+        assert all_logp.shape[0] == B * world
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     total = B * world * args.steps
     value = total / (dev_ms * 1e-3)

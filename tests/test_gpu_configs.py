@@ -1,0 +1,133 @@
+"""GPU parity on the other BASELINE configurations and on edge cases of the AP / resummation kernels, against
+the oracle on seeded inputs (sizes the oracle finishes in seconds):
+
+  config 5   NFFT=512 loop matrices, kmax=0.4 (Nk=84), fine binning
+  NNLO       with_NNLO=True (PctNNLOl rows, CctNNLO resummation)
+  Nl=2 + AP  the 2-multipole instantiations of the resum / AP kernels
+  extreme AP distortions of +-20-30 % (wide B-spline windows, both directions of k'(mu)) and the exact fiducial
+             (k' == k: degenerate window)
+
+Tolerance as in test_gpu_parity.py: 1e-8 of the row maximum."""
+import numpy as np
+import pytest
+
+from conftest import rowmax_rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _oracle_terms(orc, co, nl, rs, batch, i, ap=None, DA=None, H=None):
+    b = orc.Bird(co, batch.kin, batch.plin[i], batch.f[i], DA=None if DA is None else DA[i], H=None if H is None else H[i])
+    nl.PsCf(b)
+    orc.set_PsCfl(b)
+    if rs is not None:
+        rs.Ps(b)
+    if ap is not None:
+        ap.AP(b)
+    parts = [b.P11l, b.Pctl, b.Ploopl, b.Pstl]
+    if co.with_NNLO:
+        parts.append(b.PctNNLOl)
+    return np.concatenate(parts, axis=1)
+
+
+def test_config5_high_resolution():
+    """BASELINE config 5: NFFT=512, kmax=0.4 -> Nk=84, + fine k-binning through the projection operator."""
+    import torch
+
+    import pybird_oracle as orc
+    from eftpipe_b200 import engine, plan, synthetic
+
+    batch = synthetic.make_batch(3, 0.7, seed=512, unique=3)
+    g = plan.GridConfig(Nl=3, kmax=0.4, NFFT=512)
+    kout = np.arange(0.0125, 0.39, 0.005)
+    binm, keff, _, _ = plan.binning_matrix(g.k, kout, decimals=3)
+    proj = plan.compose_projection(g, binning=binm)
+    dp_raw = engine.DevicePlan(plan.build_tracer_plan(Nl=3, kmax=0.4, NFFT=512))
+    dp_bin = engine.DevicePlan(plan.build_tracer_plan(Nl=3, kmax=0.4, NFFT=512, projection=proj))
+    raw, _ = dp_raw.eval_terms(batch.plin, batch.f)
+    binned, _ = dp_bin.eval_terms(batch.plin, batch.f)
+    torch.cuda.synchronize()
+    raw, binned = _np(raw), _np(binned)
+    co = orc.Common(Nl=3, kmax=0.4)
+    assert co.Nk == 84
+    nl, rs = orc.NonLinear(co, NFFT=512), orc.Resum(co)
+    ob = orc.Binning(kout, co, decimals=3)
+    for i in (0, 2):
+        ref = _oracle_terms(orc, co, nl, rs, batch, i)
+        assert rowmax_rel(raw[i], ref) <= TOL, i
+        refb = np.array([[ob.integrate(ref[l, t]) for t in range(ref.shape[1])] for l in range(3)])
+        assert rowmax_rel(binned[i], refb) <= TOL, i
+
+
+def test_nnlo_terms():
+    import torch
+
+    import pybird_oracle as orc
+    from eftpipe_b200 import engine, plan, synthetic
+
+    batch = synthetic.make_batch(4, 0.7, seed=77, unique=4)
+    dp = engine.DevicePlan(plan.build_tracer_plan(Nl=3, with_NNLO=True))
+    got, _ = dp.eval_terms(batch.plin, batch.f)
+    torch.cuda.synchronize()
+    got = _np(got)
+    assert got.shape[2] == 27
+    co = orc.Common(Nl=3, with_NNLO=True)
+    nl, rs = orc.NonLinear(co), orc.Resum(co)
+    for i in (1, 3):
+        assert rowmax_rel(got[i], _oracle_terms(orc, co, nl, rs, batch, i)) <= TOL, i
+
+
+@pytest.mark.parametrize("Nl", [2, 3])
+def test_ap_extreme_and_degenerate_geometry(Nl):
+    """q_perp, q_par far from 1 in both orders (k' increasing / decreasing with mu, windows of ~10-20 B-splines)
+    and the exact fiducial cosmology (k' == k for every mu)."""
+    import torch
+
+    import pybird_oracle as orc
+    from eftpipe_b200 import engine, plan, synthetic
+
+    Om_AP, z_AP = 0.307115, 0.696
+    DA0, H0 = synthetic.angular_distance(Om_AP, z_AP), synthetic.hubble(Om_AP, z_AP)
+    batch = synthetic.make_batch(6, 0.7, seed=11, unique=6)
+    DA = DA0 * np.array([1.0, 1.25, 0.8, 1.1, 0.92, 1.0])
+    H = H0 * np.array([1.0, 0.8, 1.3, 1.1, 1.0, 0.9])
+    for APst in (False, True):
+        dp = engine.DevicePlan(plan.build_tracer_plan(Nl=Nl, ap=dict(DA=DA0, H=H0, APst=APst)))
+        got, _ = dp.eval_terms(batch.plin, batch.f, DA, H)
+        torch.cuda.synchronize()
+        got = _np(got)
+        assert np.isfinite(got).all()
+        co = orc.Common(Nl=Nl)
+        nl, rs = orc.NonLinear(co), orc.Resum(co)
+        ap = orc.APeffect(co, DA=DA0, H=H0, APst=APst)
+        for i in range(6):
+            ref = _oracle_terms(orc, co, nl, rs, batch, i, ap=ap, DA=DA, H=H)
+            assert rowmax_rel(got[i], ref) <= TOL, (Nl, APst, i)
+
+
+def test_large_batch_is_consistent_with_small_batches():
+    """Size-independent property at 4x BASELINE's batch (4096 points, several AP chunks): every point of a
+    large batch equals the same point evaluated in a batch of 32 (no cross-talk between lanes, CTAs, chunks)."""
+    import torch
+
+    from eftpipe_b200 import engine, plan, synthetic
+
+    Om_AP, z_AP = 0.307115, 0.696
+    DA0, H0 = synthetic.angular_distance(Om_AP, z_AP), synthetic.hubble(Om_AP, z_AP)
+    B = 4096
+    batch = synthetic.make_batch(B, 0.7, seed=5, unique=64)
+    dp = engine.DevicePlan(plan.build_tracer_plan(Nl=3, ap=dict(DA=DA0, H=H0, APst=True)))
+    big, _ = dp.eval_terms(batch.plin, batch.f, batch.DA, batch.H)
+    torch.cuda.synchronize()
+    big = _np(big).copy()
+    assert np.isfinite(big).all()
+    for lo in (0, 1504, 4064):
+        sl = slice(lo, lo + 32)
+        small, _ = dp.eval_terms(batch.plin[sl], batch.f[sl], batch.DA[sl], batch.H[sl])
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(_np(small), big[sl])
