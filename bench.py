@@ -238,7 +238,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
+    if world > 1 and rank != 0:
+        dist.barrier()  # rank 0 builds (and caches) the window matrix first; the others load it
     S = host_setup(B, seed=20261018 + 2 + 1000 * rank)  # every rank owns a different shard of the point set
+    if world > 1 and rank == 0:
+        dist.barrier()
     co, win = S["co"], S["win"]
     g = P.GridConfig(Nl=3)
     binm, keff, _, _ = P.binning_matrix(g.k, S["minfo"].kout)

@@ -85,14 +85,18 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
   for (int i = 0; i < 16; ++i) bc[i] = bas[j * 16 + i];
   double knot = knots[j];
 
-  for (int t = 0; t < a.nmu; ++t) {
+  // geometry of one mu node: k' (pybird.py:1608) and mu'^2 (pybird.py:1609); one reciprocal square root serves both
+  auto geom = [&](int t, double& kp, double& mp2) {
     const double m2 = mu2s[t];
     const double root = fma(m2, iF2m1, 1.0);
-    const double rs = rsqrt(root);           // one reciprocal square root serves k' and mu'^2
-    const double kp = kq * (root * rs);      // pybird.py:1608
-    // k' is monotone in mu: j moves (rarely) in one direction inside [jlo, jhi]
-    while (j < jhi && kp >= knots[j + 1]) {
-      double* g = Grow + (j - jlo);     // B-spline j has no support beyond this knot: retire its column
+    const double rs = rsqrt(root);
+    kp = kq * (root * rs);
+    mp2 = m2 * invF2 * (rs * rs);
+  };
+  // move the live window to the interval of k' (rare), then the 4 B-spline values and the even Legendre polynomials
+  auto locate_and_basis = [&](double kp, double mp2, double (&bv)[4], double (&L)[3]) {
+    while (j < jhi && kp >= knots[j + 1]) {  // k' is monotone in mu: j moves in one direction inside [jlo, jhi]
+      double* g = Grow + (j - jlo);          // B-spline j has no support beyond this knot: retire its column
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         atomicAdd(g + q * a.wcap, acc[q][0]);  // fire-and-forget RED: this row belongs to this thread alone
@@ -116,15 +120,20 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
       knot = knots[j];
     }
     const double x = kp - knot;
-    double bv[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) bv[r] = fma(fma(fma(bc[r * 4 + 3], x, bc[r * 4 + 2]), x, bc[r * 4 + 1]), x, bc[r * 4]);
-    // even Legendre polynomials of mu' = mu / F / sqrt(root) (pybird.py:1609) need mu'^2 only
-    const double mp2 = m2 * invF2 * (rs * rs);
-    double L[3];
     L[0] = 1.0;
     L[1] = 0.5 * (3.0 * mp2 - 1.0);
     L[2] = (35.0 * mp2 * mp2 - 30.0 * mp2 + 3.0) * 0.125;
+  };
+  // software pipeline: the square-root chain of node t+1 is issued next to the 45 independent multiply-adds of
+  // node t, so the two overlap inside one warp (there are only ~3 warps per scheduler to hide latency with)
+  double kp, mp2, bv[4], L[3];
+  geom(0, kp, mp2);
+  locate_and_basis(kp, mp2, bv, L);
+  for (int t = 0; t < a.nmu; ++t) {
+    const bool more = t + 1 < a.nmu;
+    if (more) geom(t + 1, kp, mp2);
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       const double w = wls[l * a.nmu + t];
@@ -135,6 +144,7 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
         for (int r = 0; r < 4; ++r) acc[l * NL + lp][r] = fma(wL, bv[r], acc[l * NL + lp][r]);
       }
     }
+    if (more) locate_and_basis(kp, mp2, bv, L);
   }
   double* g = Grow + (j - jlo);
 #pragma unroll
@@ -143,16 +153,22 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
     for (int r = 0; r < 4; ++r) atomicAdd(g + q * a.wcap + r, acc[q][r]);
 }
 
+constexpr int APPLY_CH = 8;  // window columns fetched per step: NL * APPLY_CH independent loads in flight
+
 template <int NL>
 __global__ void __launch_bounds__(APPLY_THREADS) ap_apply_kernel(ApArgs a) {
   constexpr int NQ = NL * NL;
   extern __shared__ __align__(16) double sm[];
-  double* coefs = sm;                                                   // [NL][Nk][nterm]
+  double* coefs = sm;                                                   // [NL][nterm][Nk]
   int2* metas = reinterpret_cast<int2*>(coefs + (size_t)NL * a.Nk * a.nterm);  // [Nk]
   const int bl = blockIdx.x, b = a.b0 + bl, tid = threadIdx.x;
   const size_t Bp = a.Bp;
-  for (int i = tid; i < NL * a.Nk * a.nterm; i += APPLY_THREADS) coefs[i] = a.coef[(size_t)i * Bp + b];
   for (int i = tid; i < a.Nk; i += APPLY_THREADS) metas[i] = a.meta[(size_t)bl * a.Nk + i];
+  {  // B-spline coefficients, point-major [b][l][term][j]: contiguous, coalesced
+    const double* cb = a.coef + (size_t)b * NL * a.Nk * a.nterm;
+#pragma unroll 8
+    for (int i = tid; i < NL * a.Nk * a.nterm; i += APPLY_THREADS) coefs[i] = cb[i];
+  }
   const double qperp = a.DA[b] / a.da_fid, qpar = a.h_fid / a.H[b];
   const double norm = 1.0 / (qperp * qperp * qpar);  // pybird.py:1611
   __syncthreads();
@@ -166,20 +182,21 @@ __global__ void __launch_bounds__(APPLY_THREADS) ap_apply_kernel(ApArgs a) {
     const size_t o = ((size_t)(l * a.Nk + ik) * a.nterm + i) * Bp + b;
     if (!apply) { a.Tout[o] = a.Tin[o]; continue; }
     const int2 mw = metas[ik];
+    // rows (l, l'=0..NL-1) of this node's banded operator; the 24-27 term lanes of a warp read the same words
     const double* Gk = a.G + (((size_t)bl * a.Nk + ik) * NQ + l * NL) * a.wcap;
+    const double* cf = coefs + (size_t)i * a.Nk + mw.x;
     double acc = 0.0;
+    for (int c0 = 0; c0 < mw.y; c0 += APPLY_CH) {
+      double gv[NL][APPLY_CH];
 #pragma unroll
-    for (int lp = 0; lp < NL; ++lp) {
-      const double* cf = coefs + ((size_t)lp * a.Nk + mw.x) * a.nterm + i;
-      const double* gq = Gk + lp * a.wcap;
-      for (int c0 = 0; c0 < mw.y; c0 += 4) {  // 4 independent loads in flight per step
-        double gv[4];
+      for (int lp = 0; lp < NL; ++lp)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) gv[c] = c0 + c < mw.y ? __ldg(gq + c0 + c) : 0.0;
+        for (int c = 0; c < APPLY_CH; ++c) gv[lp][c] = c0 + c < mw.y ? __ldg(Gk + lp * a.wcap + c0 + c) : 0.0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c0 + c < mw.y) acc = fma(gv[c], cf[(size_t)(c0 + c) * a.nterm], acc);
-      }
+      for (int lp = 0; lp < NL; ++lp)
+#pragma unroll
+        for (int c = 0; c < APPLY_CH; ++c)
+          if (c0 + c < mw.y) acc = fma(gv[lp][c], cf[(size_t)lp * a.nterm * a.Nk + c0 + c], acc);
     }
     a.Tout[o] = norm * acc;
   }

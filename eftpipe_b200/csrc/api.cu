@@ -218,13 +218,14 @@ int eftb_spectral_grouped(const eftb_plan* p, int B, const double* D, const doub
   cudaStream_t s = (cudaStream_t)stream;
   const eftb_config& c = p->cfg;
   const int Bp = eftb_padded_batch(B);
-  const size_t dch = (size_t)(c.Nmax + 1) * 2 * Bp, srow = (size_t)c.Ns * Bp;
+  const size_t dch = (size_t)(c.Nmax + 1) * 2 * Bp;
   const int ncr = 14 + (c.with_nnlo ? 1 : 0);
   int rc = launch_regroup(p, Bp, D, f, Dg, s);
   if (rc) return rc;
   if ((rc = gemm_run(p->Ak, D, P22, Bp, EFTB_N22, EFTB_N22, dch, 0, (size_t)c.Nk * Bp, 0, s))) return rc;
-  // Cloopl[l][r] = As[l] @ Dg[l][r], written straight into rows 2..13 of Cr[l]
-  return gemm_run(p->As, Dg, Cr + 2 * srow, Bp, c.Nl * 12, 12, dch, 12 * dch, srow, (size_t)ncr * srow, s);
+  // Cloopl[l][r] = As[l] @ Dg[l][r], written straight into rows 2..13 of the point-major Cr[b][l][ncr][Ns]
+  GemmPointMajor pm{Bp, (size_t)c.Nl * ncr * c.Ns, 0};
+  return gemm_run(p->As, Dg, Cr + 2 * (size_t)c.Ns, Bp, c.Nl * 12, 12, dch, 12 * dch, (size_t)c.Ns, (size_t)ncr * c.Ns, s, &pm);
 }
 
 int eftb_group(const eftb_plan* p, int B, const double* F, const double* P22, const double* Cs, const double* f, double* T,
@@ -256,8 +257,10 @@ static int ap_stage(const eftb_plan* p, int B, const double* Tin, const double* 
   const eftb_config& c = p->cfg;
   const int Bp = eftb_padded_batch(B);
   const size_t per_l = (size_t)c.Nk * c.nterm * Bp;
-  // B-spline coefficients of every term row: coef[l] = Cinv @ T[l]  (N = nterm*Bp columns)
-  int rc = gemm_run(p->Cinv, Tin, coef, c.nterm * Bp, c.Nl, c.Nl, per_l, 0, per_l, 0, s);
+  // B-spline coefficients of every term row: coef[l] = Cinv @ T[l]  (N = nterm*Bp columns), stored point-major
+  // [b][l][term][j] for the one-CTA-per-cosmology apply kernel
+  GemmPointMajor pm{Bp, (size_t)c.Nl * c.nterm * c.Nk, (size_t)c.Nk};
+  int rc = gemm_run(p->Cinv, Tin, coef, c.nterm * Bp, c.Nl, c.Nl, per_l, 0, (size_t)c.nterm * c.Nk, 0, s, &pm);
   if (rc) return rc;
   if (Bp > B) {  // pad lanes are not processed by the per-cosmology kernels: keep them finite
     EFTB_CUDA_CHECK(cudaMemcpyAsync(Tout, Tin, (size_t)c.Nl * per_l * sizeof(double), cudaMemcpyDeviceToDevice, s));

@@ -40,8 +40,11 @@ int gemm_upload(const double* host, int nbatch, int M, int K, GemmMatrix* out);
 void gemm_free(GemmMatrix* m);
 // z-batch: zb in [0, nz), zq = zb / zdiv, zr = zb % zdiv: A matrix index = zq (if A has >1 batch),
 // X offset = zr*xs + zq*xs2, C offset = zr*cs + zq*cs2
+// pm != NULL: point-major output.  Column n = i * bp + b (b = cosmology) goes to C[b * ld + i * is + row] (+ the
+// z offsets zr*cs + zq*cs2): per-cosmology contiguous rows for the one-CTA-per-cosmology consumers.
+struct GemmPointMajor { int bp; size_t ld, is; };
 int gemm_run(const GemmMatrix& A, const double* X, double* C, int N, int nz, int zdiv, size_t xs, size_t xs2,
-             size_t cs, size_t cs2, cudaStream_t stream);
+             size_t cs, size_t cs2, cudaStream_t stream, const GemmPointMajor* pm = nullptr);
 
 struct AntidiagPack;  // fragment-ordered pair table + warp schedules (antidiag.cu)
 

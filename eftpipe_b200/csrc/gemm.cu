@@ -25,6 +25,8 @@ struct GemmArgs {
   int M, K, Kp, Mp, N;
   int a_batched, zdiv;
   size_t xs, xs2, cs, cs2;
+  int pm_bp;         // > 0: point-major epilogue, column n = i * pm_bp + b -> C[b * pm_ld + i * pm_is + row]
+  size_t pm_ld, pm_is;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
@@ -69,7 +71,8 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
     double* as = As + buf * BM * APITCH;
     for (int c = tid; c < BM * 8; c += 128) {
       int r = c >> 3, q = c & 7;
-      cp_async16(as + r * APITCH + q * 2, A + (size_t)r * g.Kp + kt * BK + q * 2, true);
+      const bool ok = m0 + r < g.Mp;  // A is padded to a multiple of 8 rows only: the last slab may be partial
+      cp_async16(as + r * APITCH + q * 2, ok ? A + (size_t)r * g.Kp + kt * BK + q * 2 : g.A, ok);
     }
     double* xs = Xs + buf * BK * XPITCH;
     for (int c = tid; c < BK * (BN / 2); c += 128) {
@@ -108,6 +111,25 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
     }
     __syncthreads();
   }
+  if (g.pm_bp > 0) {
+    // point-major epilogue: the 8 lanes that share a column pair hold 8 consecutive rows -> 64-byte runs per column
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + warp * 32 + j * 8 + (lane & 3) * 2;
+      if (col >= g.N) continue;
+      const int ii = col / g.pm_bp, b = col - ii * g.pm_bp;
+      double* c0 = C + (size_t)b * g.pm_ld + (size_t)ii * g.pm_is;
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const int row = m0 + i * 8 + (lane >> 2);
+        if (row < g.M) {
+          c0[row] = acc[i][j][0];
+          c0[g.pm_ld + row] = acc[i][j][1];
+        }
+      }
+    }
+    return;
+  }
   // epilogue: each lane owns 2 adjacent columns of every tile row -> 16-byte stores
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
@@ -130,22 +152,24 @@ int launch(const GemmArgs& g, int nz, cudaStream_t s) {
     EFTB_CUDA_CHECK(cudaFuncSetAttribute(gemm_f64_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((g.N + BN - 1) / BN, g.Mp / BM, nz);
+  dim3 grid((g.N + BN - 1) / BN, (g.Mp + BM - 1) / BM, nz);
   gemm_f64_kernel<MT><<<grid, 128, smem, s>>>(g);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;
 }
 
-// choose the slab height (in m8 tiles) minimising padding; candidates keep registers < 255
-int pick_mt(int M) {
-  const int cand[] = {10, 9, 8, 7, 6, 5, 4};
+int g_sms = 0;
+
+// slab height (in m8 tiles) for one launch: CTAs are dealt round-robin to the SMs, so the makespan is about
+// ceil(nCTA / SMs) slabs of (8 MT + fixed per-slab overhead) rows; pick the MT that minimises it
+int pick_mt(int M, int ncta_per_slab) {
   int best = 10;
-  double best_waste = 1e9;
-  for (int mt : cand) {
-    int bm = 8 * mt;
-    int mp = eftb_round_up(M, bm);
-    double waste = (double)(mp - M) / M + 0.02 * (10 - mt);  // mild preference for tall slabs
-    if (waste < best_waste) { best_waste = waste; best = mt; }
+  double best_cost = 1e30;
+  for (int mt = 4; mt <= 11; ++mt) {
+    const int bm = 8 * mt, slabs = (M + bm - 1) / bm;
+    const long ncta = (long)slabs * ncta_per_slab;
+    const double cost = (double)((ncta + g_sms - 1) / g_sms) * (bm + 16.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = mt; }
   }
   return best;
 }
@@ -153,8 +177,7 @@ int pick_mt(int M) {
 }  // namespace
 
 int gemm_upload(const double* host, int nbatch, int M, int K, GemmMatrix* out) {
-  int MT = pick_mt(M);
-  int Mp = eftb_round_up(M, 8 * MT), Kp = eftb_round_up(K, BK);
+  int Mp = eftb_round_up(M, 8), Kp = eftb_round_up(K, BK);
   size_t n = (size_t)nbatch * Mp * Kp;
   double* tmp = (double*)calloc(n, sizeof(double));
   if (!tmp) return EFTB_ERR_ARG;
@@ -169,7 +192,7 @@ int gemm_upload(const double* host, int nbatch, int M, int K, GemmMatrix* out) {
     eftb_set_error("gemm_upload: %s", cudaGetErrorString(e));
     return EFTB_ERR_CUDA;
   }
-  out->d = d; out->M = M; out->K = K; out->Mp = Mp; out->Kp = Kp; out->MT = MT; out->nbatch = nbatch;
+  out->d = d; out->M = M; out->K = K; out->Mp = Mp; out->Kp = Kp; out->MT = 0; out->nbatch = nbatch;
   return EFTB_OK;
 }
 
@@ -179,10 +202,17 @@ void gemm_free(GemmMatrix* m) {
 }
 
 int gemm_run(const GemmMatrix& A, const double* X, double* C, int N, int nz, int zdiv, size_t xs, size_t xs2,
-             size_t cs, size_t cs2, cudaStream_t stream) {
-  if (!A.d || !X || !C || N % 2) { eftb_set_error("gemm_run: bad arguments"); return EFTB_ERR_ARG; }
-  GemmArgs g{A.d, X, C, A.M, A.K, A.Kp, A.Mp, N, A.nbatch > 1 ? 1 : 0, zdiv, xs, xs2, cs, cs2};
-  switch (A.MT) {
+             size_t cs, size_t cs2, cudaStream_t stream, const GemmPointMajor* pm) {
+  if (!A.d || !X || !C || N % 2 || (pm && (pm->bp < 2 || pm->bp % 2))) { eftb_set_error("gemm_run: bad arguments"); return EFTB_ERR_ARG; }
+  if (!g_sms) {
+    int dev = 0;
+    EFTB_CUDA_CHECK(cudaGetDevice(&dev));
+    EFTB_CUDA_CHECK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  GemmArgs g{A.d, X, C, A.M, A.K, A.Kp, A.Mp, N, A.nbatch > 1 ? 1 : 0, zdiv, xs, xs2, cs, cs2,
+             pm ? pm->bp : 0, pm ? pm->ld : 0, pm ? pm->is : 0};
+  switch (pick_mt(A.M, ((N + BN - 1) / BN) * nz)) {
+    case 11: return launch<11>(g, nz, stream);
     case 10: return launch<10>(g, nz, stream);
     case 9: return launch<9>(g, nz, stream);
     case 8: return launch<8>(g, nz, stream);

@@ -73,19 +73,22 @@ __global__ void __launch_bounds__(128) group_kernel(GroupArgs a) {
     }
   } else {
     const int s = blockIdx.y - a.Nk;
+    // Cr is point-major [b][l][ncr][Ns]: the one-CTA-per-cosmology resummation kernel reads it contiguously
+    const size_t ld = (size_t)a.Nl * a.ncr * a.Ns;
     for (int l = 0; l < a.Nl; ++l) {
-      double* out = a.Cr + ((size_t)(l * a.ncr) * a.Ns + s) * Bp + b;
-      const size_t rs = (size_t)a.Ns * Bp;
+      double* out = a.Cr + (size_t)b * ld + (size_t)(l * a.ncr) * a.Ns + s;
+      const size_t rs = (size_t)a.Ns;
       out[0] = a.F[(size_t)(a.row_c11 + l * a.Ns + s) * Bp + b];
       out[rs] = a.F[(size_t)(a.row_cct + l * a.Ns + s) * Bp + b];
       if (a.with_nnlo) out[14 * rs] = a.F[(size_t)(a.row_cctnnlo + l * a.Ns + s) * Bp + b];
       if (!a.Cs) continue;  // Cloopl rows were produced by the grouped spectral GEMM
       const double* cs = a.Cs + ((size_t)(l * EFTB_NCH) * a.Ns + s) * Bp + b;
+      const size_t crs = (size_t)a.Ns * Bp;
       double row[12];
 #pragma unroll
       for (int i = 0; i < 12; ++i) row[i] = 0.0;
-#define ACC22(r, p, t) row[r] += fp[p] * a.l22[l * EFTB_N22 + t] * cs[(size_t)(t) * rs];
-#define ACC13(r, p, t) row[r] += fp[p] * a.l13[l * EFTB_N13 + t] * cs[(size_t)(EFTB_N22 + t) * rs];
+#define ACC22(r, p, t) row[r] += fp[p] * a.l22[l * EFTB_N22 + t] * cs[(size_t)(t) * crs];
+#define ACC13(r, p, t) row[r] += fp[p] * a.l13[l * EFTB_N13 + t] * cs[(size_t)(EFTB_N22 + t) * crs];
       EFTB_G22(ACC22)
       EFTB_G13(ACC13)
 #undef ACC22

@@ -129,7 +129,9 @@ struct FinArgs {
   int B, Bp, ndata, ngauss, jeffreys;
 };
 
-// block (32 points, ngauss+1 rows): row g < ngauss accumulates F2[g][0..g] and F1[g]; row ngauss accumulates F0
+// block (32 points, ny entry-rows): every entry of the packed lower triangle of F2, of F1 and F0 is one dot product
+// over the data index, sum_d V[d][ra] * Y[d][rb]; entry-rows are spread over threadIdx.y, loads are coalesced
+// over the 32 points and unrolled 4x (independent partial sums) to keep several loads in flight
 __global__ void like_finish_kernel(FinArgs a) {
   extern __shared__ double sm[];
   const int nG = a.ngauss, nc = nG + 1;
@@ -138,27 +140,39 @@ __global__ void like_finish_kernel(FinArgs a) {
   double* F0 = F1 + (size_t)nG * 32;       // [32]
   const int lx = threadIdx.x, g = threadIdx.y;
   const int b = blockIdx.x * 32 + lx;
-  const size_t Bp = a.Bp;
-  if (g < nG) {
-    double acc[32];
-    double f1 = 0.0;
-    for (int j = 0; j <= g; ++j) acc[j] = 0.0;
-    for (int d = 0; d < a.ndata; ++d) {
-      const double v = a.V[((size_t)d * nc + 1 + g) * Bp + b];
-      const double* y = a.Y + ((size_t)d * nc) * Bp + b;
-      f1 = fma(v, y[0], f1);
-      for (int j = 0; j <= g; ++j) acc[j] = fma(v, y[(size_t)(1 + j) * Bp], acc[j]);
+  const size_t Bp = a.Bp, stride = (size_t)nc * Bp;
+  const int ntri = nG * (nG + 1) / 2, nent = ntri + nG + 1;
+  for (int e = threadIdx.y; e < nent; e += blockDim.y) {
+    int eg = 0, ej = 0, ra = 0, rb = 0;
+    if (e < ntri) {
+      while ((eg + 1) * (eg + 2) / 2 <= e) ++eg;
+      ej = e - eg * (eg + 1) / 2;
+      ra = 1 + eg; rb = 1 + ej;
+    } else if (e < ntri + nG) {
+      eg = e - ntri;
+      ra = 1 + eg;
     }
-    for (int j = 0; j <= g; ++j) {
-      const double v = acc[j] + a.sigma_inv[g * nG + j];  // marginal.py:167-175
-      F2[((size_t)g * nG + j) * 32 + lx] = v;
-      F2[((size_t)j * nG + g) * 32 + lx] = v;
+    const double* pv = a.V + (size_t)ra * Bp + b;
+    const double* py = a.Y + (size_t)rb * Bp + b;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int d = 0;
+    for (; d + 4 <= a.ndata; d += 4) {
+      s0 = fma(pv[(size_t)d * stride], py[(size_t)d * stride], s0);
+      s1 = fma(pv[(size_t)(d + 1) * stride], py[(size_t)(d + 1) * stride], s1);
+      s2 = fma(pv[(size_t)(d + 2) * stride], py[(size_t)(d + 2) * stride], s2);
+      s3 = fma(pv[(size_t)(d + 3) * stride], py[(size_t)(d + 3) * stride], s3);
     }
-    F1[(size_t)g * 32 + lx] = -f1 + a.sigma_inv_mu[g];  // marginal.py:177-185
-  } else {
-    double f0 = 0.0;
-    for (int d = 0; d < a.ndata; ++d) f0 = fma(a.V[((size_t)d * nc) * Bp + b], a.Y[((size_t)d * nc) * Bp + b], f0);
-    F0[lx] = f0 + a.mu_sigma_mu;  // marginal.py:187-196
+    for (; d < a.ndata; ++d) s0 = fma(pv[(size_t)d * stride], py[(size_t)d * stride], s0);
+    const double sum = (s0 + s1) + (s2 + s3);
+    if (e < ntri) {
+      const double v = sum + a.sigma_inv[eg * nG + ej];  // marginal.py:167-175
+      F2[((size_t)eg * nG + ej) * 32 + lx] = v;
+      F2[((size_t)ej * nG + eg) * 32 + lx] = v;
+    } else if (e < ntri + nG) {
+      F1[(size_t)eg * 32 + lx] = -sum + a.sigma_inv_mu[eg];  // marginal.py:177-185
+    } else {
+      F0[lx] = sum + a.mu_sigma_mu;  // marginal.py:187-196
+    }
   }
   __syncthreads();
   if (g != 0 || b >= a.B) return;
@@ -309,7 +323,8 @@ int eftb_like_eval(const eftb_like* L, int B, const double* const* terms, const 
     EFTB_CUDA_CHECK(cudaFuncSetAttribute(like_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  dim3 block(32, nG + 1), grid(Bp / 32);
+  const int nent = nG * (nG + 1) / 2 + nG + 1;
+  dim3 block(32, nent < 30 ? nent : 30), grid(Bp / 32);
   like_finish_kernel<<<grid, block, smem, s>>>(a);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;

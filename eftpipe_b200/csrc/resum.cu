@@ -33,69 +33,73 @@ struct ResumArgs {
   int nslot[3];     // canonical slots of l': 0 = (X, v = l'), 1 + v = (Y, v); nslot = 1 + number of Y orders used
 };
 
-template <int NL, bool NNLO>
+// accumulators of one (l, k) output column: IA = 0 (linear terms, Q_0, contracted with C11) keeps one sum per l';
+// IA = 1 (Q_1) keeps Cct per l', the 12 loop rows and, with NNLO, CctNNLO per l'
+template <int NL, bool NNLO, int IA>
 struct Accum {
-  double lin0[NL], lin1[NL], loop[12], nnlo[NNLO ? NL : 1];
+  double lin[NL], loop[IA ? 12 : 1], nnlo[(IA && NNLO) ? NL : 1];
   __device__ __forceinline__ void zero() {
 #pragma unroll
-    for (int i = 0; i < NL; ++i) lin0[i] = lin1[i] = 0.0;
+    for (int i = 0; i < NL; ++i) lin[i] = 0.0;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) loop[i] = 0.0;
+    for (int i = 0; i < (IA ? 12 : 1); ++i) loop[i] = 0.0;
 #pragma unroll
-    for (int i = 0; i < (NNLO ? NL : 1); ++i) nnlo[i] = 0.0;
+    for (int i = 0; i < ((IA && NNLO) ? NL : 1); ++i) nnlo[i] = 0.0;
   }
 };
 
-// Horner sweep of NS polynomial slots for a = 0 and a = 1 over the RS_C points of a chunk, then the weighted
-// slot sum  T_a[c] = R[l'][c] z[c] P_a[0][c] + Y k^2 [c] sum_v R[v][c] P_a[1+v][c]
+// acc = acc * z + q as a volatile instruction: volatile asm statements keep their program order, which pins the
+// breadth-first schedule of the Horner sweep (NS * RS_C independent chains between two steps of one chain)
+__device__ __forceinline__ void horner_step(double& acc, double z, double q) {
+  asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(acc) : "d"(z), "d"(q));
+}
+
+// Horner sweep of the NS polynomial slots of one (a, l, l') over the RS_C points of a chunk, then the weighted slot
+// sum  T[c] = R[l'][c] z[c] P[0][c] + Y k^2 [c] sum_v R[v][c] P[1+v][c]
 template <int NIR, int NS, int NL>
-__device__ __forceinline__ void horner(const double* __restrict__ q0, const double* __restrict__ q1, const double (&z)[RS_C],
-                                       const double (&yk)[RS_C], const double (&Rv)[NL][RS_C], int lp, double (&T0)[RS_C],
-                                       double (&T1)[RS_C]) {
-  double P0[NS][RS_C], P1[NS][RS_C];
+__device__ __forceinline__ void horner(const double* __restrict__ q, const double (&z)[RS_C], const double (&yk)[RS_C],
+                                       const double (&Rv)[NL][RS_C], int lp, double (&T)[RS_C]) {
+  double P[NS][RS_C];
 #pragma unroll
   for (int s = 0; s < NS; ++s)
 #pragma unroll
-    for (int c = 0; c < RS_C; ++c) P0[s][c] = P1[s][c] = 0.0;
+    for (int c = 0; c < RS_C; ++c) P[s][c] = 0.0;
 #pragma unroll
   for (int p = NIR - 1; p >= 0; --p) {
-    const double2 a01 = *reinterpret_cast<const double2*>(q0 + p * RS_SLOTS);
-    const double2 a23 = *reinterpret_cast<const double2*>(q0 + p * RS_SLOTS + 2);
-    const double2 b01 = *reinterpret_cast<const double2*>(q1 + p * RS_SLOTS);
-    const double2 b23 = *reinterpret_cast<const double2*>(q1 + p * RS_SLOTS + 2);
-    const double qa[4] = {a01.x, a01.y, a23.x, a23.y}, qb[4] = {b01.x, b01.y, b23.x, b23.y};
+    const double2 a01 = *reinterpret_cast<const double2*>(q + p * RS_SLOTS);
+    const double2 a23 = *reinterpret_cast<const double2*>(q + p * RS_SLOTS + 2);
+    const double qa[4] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
     for (int s = 0; s < NS; ++s)
 #pragma unroll
-      for (int c = 0; c < RS_C; ++c) {
-        P0[s][c] = fma(P0[s][c], z[c], qa[s]);
-        P1[s][c] = fma(P1[s][c], z[c], qb[s]);
-      }
+      for (int c = 0; c < RS_C; ++c) horner_step(P[s][c], z[c], qa[s]);
   }
 #pragma unroll
   for (int c = 0; c < RS_C; ++c) {
-    double y0 = 0.0, y1 = 0.0;
+    double y = 0.0;
 #pragma unroll
-    for (int v = 0; v < NS - 1; ++v) {
-      y0 = fma(Rv[v][c], P0[1 + v][c], y0);
-      y1 = fma(Rv[v][c], P1[1 + v][c], y1);
-    }
-    const double wx = Rv[lp][c] * z[c];
-    T0[c] = fma(wx, P0[0][c], yk[c] * y0);
-    T1[c] = fma(wx, P1[0][c], yk[c] * y1);
+    for (int v = 0; v < NS - 1; ++v) y = fma(Rv[v][c], P[1 + v][c], y);
+    T[c] = fma(Rv[lp][c] * z[c], P[0][c], yk[c] * y);
   }
 }
 
-template <int NL, int NIR, bool NNLO>
+__device__ __forceinline__ double dot4(const double (&T)[RS_C], const double* row, double acc) {
+  const double2 c01 = *reinterpret_cast<const double2*>(row), c23 = *reinterpret_cast<const double2*>(row + 2);
+  return fma(T[3], c23.y, fma(T[2], c23.x, fma(T[1], c01.y, fma(T[0], c01.x, acc))));
+}
+
+// Cs holds the rows this IA contracts with: IA = 0: [NL][1][NsP] (C11); IA = 1: [NL][ncr-1][NsP] (Cct, Cloopl x12[, CctNNLO])
+template <int NL, int NIR, bool NNLO, int IA>
 __device__ __forceinline__ void sweep_chunk(const ResumArgs& a, const double* Qs, const double* Xs, const double* Ys,
-                                            const double* Cs, int l, int ik, double k2, int s0, Accum<NL, NNLO>& A) {
+                                            const double* Cs, int l, int ik, double k2, int s0, Accum<NL, NNLO, IA>& A) {
   // R[v,k,s] of this chunk, shared by every l' (Rt is [v][s][k]: lanes = k read contiguously).  Issued first and
   // consumed only after the first Horner sweep, which hides the L1/L2 latency.
   double Rv[NL][RS_C];
+  const double* rbase = a.Rt + (size_t)s0 * a.Nkr + ik;
 #pragma unroll
   for (int v = 0; v < NL; ++v)
 #pragma unroll
-    for (int c = 0; c < RS_C; ++c) Rv[v][c] = __ldg(a.Rt + ((size_t)v * a.NsP + s0 + c) * a.Nkr + ik);
+    for (int c = 0; c < RS_C; ++c) Rv[v][c] = __ldg(rbase + ((size_t)v * a.NsP + c) * a.Nkr);
   double z[RS_C], yk[RS_C];
   {
     const double2 x01 = *reinterpret_cast<const double2*>(Xs + s0), x23 = *reinterpret_cast<const double2*>(Xs + s0 + 2);
@@ -103,61 +107,54 @@ __device__ __forceinline__ void sweep_chunk(const ResumArgs& a, const double* Qs
     z[0] = k2 * x01.x; z[1] = k2 * x01.y; z[2] = k2 * x23.x; z[3] = k2 * x23.y;
     yk[0] = k2 * y01.x; yk[1] = k2 * y01.y; yk[2] = k2 * y23.x; yk[3] = k2 * y23.y;
   }
+  constexpr int NROW = IA ? 0 : 1;  // (unused marker to keep the two layouts visible)
+  (void)NROW;
+  const int nrow = IA ? a.ncr - 1 : 1;
 #pragma unroll
   for (int lp = 0; lp < NL; ++lp) {
-    const double* q0 = Qs + (size_t)(((0 * NL + l) * NL + lp) * NIR) * RS_SLOTS;
-    const double* q1 = Qs + (size_t)(((1 * NL + l) * NL + lp) * NIR) * RS_SLOTS;
-    double T0[RS_C], T1[RS_C];
-    if (a.nslot[lp] > 3) horner<NIR, 4, NL>(q0, q1, z, yk, Rv, lp, T0, T1);
-    else horner<NIR, 3, NL>(q0, q1, z, yk, Rv, lp, T0, T1);
-    const double* crow = Cs + (size_t)lp * a.ncr * a.NsP + s0;
-    {
-      const double2 c01 = *reinterpret_cast<const double2*>(crow), c23 = *reinterpret_cast<const double2*>(crow + 2);
-      A.lin0[lp] = fma(T0[3], c23.y, fma(T0[2], c23.x, fma(T0[1], c01.y, fma(T0[0], c01.x, A.lin0[lp]))));
-    }
-    {
-      const double2 c01 = *reinterpret_cast<const double2*>(crow + a.NsP), c23 = *reinterpret_cast<const double2*>(crow + a.NsP + 2);
-      A.lin1[lp] = fma(T1[3], c23.y, fma(T1[2], c23.x, fma(T1[1], c01.y, fma(T1[0], c01.x, A.lin1[lp]))));
-    }
+    const double* q = Qs + (size_t)((l * NL + lp) * NIR) * RS_SLOTS;
+    double T[RS_C];
+    if (a.nslot[lp] > 3) horner<NIR, 4, NL>(q, z, yk, Rv, lp, T);
+    else horner<NIR, 3, NL>(q, z, yk, Rv, lp, T);
+    const double* crow = Cs + (size_t)lp * nrow * a.NsP + s0;
+    A.lin[lp] = dot4(T, crow, A.lin[lp]);  // IA = 0: C11, IA = 1: Cct
+    if (IA) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      const double* cr = crow + (size_t)(2 + i) * a.NsP;
-      const double2 c01 = *reinterpret_cast<const double2*>(cr), c23 = *reinterpret_cast<const double2*>(cr + 2);
-      A.loop[i] = fma(T1[3], c23.y, fma(T1[2], c23.x, fma(T1[1], c01.y, fma(T1[0], c01.x, A.loop[i]))));
-    }
-    if (NNLO) {
-      const double* cr = crow + (size_t)14 * a.NsP;
-      const double2 c01 = *reinterpret_cast<const double2*>(cr), c23 = *reinterpret_cast<const double2*>(cr + 2);
-      A.nnlo[lp] = fma(T1[3], c23.y, fma(T1[2], c23.x, fma(T1[1], c01.y, fma(T1[0], c01.x, A.nnlo[lp]))));
+      for (int i = 0; i < 12; ++i) A.loop[i] = dot4(T, crow + (size_t)(1 + i) * a.NsP, A.loop[i]);
+      if (NNLO) A.nnlo[lp] = dot4(T, crow + (size_t)13 * a.NsP, A.nnlo[lp]);
     }
   }
 }
 
-template <int NL, bool NNLO>
-__device__ __forceinline__ void write_out(const ResumArgs& a, int b, int l, int ik, const Accum<NL, NNLO>& A) {
+template <int NL, bool NNLO, int IA>
+__device__ __forceinline__ void write_out(const ResumArgs& a, int b, int l, int ik, const Accum<NL, NNLO, IA>& A) {
   double* out = a.T + ((size_t)(l * a.Nk + a.Nklow + ik) * a.nterm) * a.Bp + b;
   const size_t Bp = a.Bp;
-  for (int i = 0; i < 3; ++i) {
-    double v = 0.0;
-#pragma unroll
-    for (int lp = 0; lp < NL; ++lp) v = fma(a.l11[lp * 3 + i], A.lin0[lp], v);
-    atomicAdd(out + (size_t)i * Bp, v);  // pybird.py:1442, :1445 (RED: nobody else touches this element)
-  }
-  for (int i = 0; i < 6; ++i) {
-    double v = 0.0;
-#pragma unroll
-    for (int lp = 0; lp < NL; ++lp) v = fma(a.lct[lp * 6 + i], A.lin1[lp], v);
-    atomicAdd(out + (size_t)(3 + i) * Bp, v);  // pybird.py:1443, :1446
-  }
-#pragma unroll
-  for (int i = 0; i < 12; ++i) atomicAdd(out + (size_t)(9 + i) * Bp, A.loop[i]);  // pybird.py:1444, :1462
-  if (NNLO)
+  // fire-and-forget reductions (RED): no other thread touches these elements
+  if (!IA) {
     for (int i = 0; i < 3; ++i) {
       double v = 0.0;
 #pragma unroll
-      for (int lp = 0; lp < NL; ++lp) v = fma(a.lctnnlo[lp * 3 + i], A.nnlo[lp], v);
-      atomicAdd(out + (size_t)(24 + i) * Bp, v);  // pybird.py:1455-1458
+      for (int lp = 0; lp < NL; ++lp) v = fma(a.l11[lp * 3 + i], A.lin[lp], v);
+      atomicAdd(out + (size_t)i * Bp, v);  // pybird.py:1442, :1445
     }
+  } else {
+    for (int i = 0; i < 6; ++i) {
+      double v = 0.0;
+#pragma unroll
+      for (int lp = 0; lp < NL; ++lp) v = fma(a.lct[lp * 6 + i], A.lin[lp], v);
+      atomicAdd(out + (size_t)(3 + i) * Bp, v);  // pybird.py:1443, :1446
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) atomicAdd(out + (size_t)(9 + i) * Bp, A.loop[i]);  // pybird.py:1444, :1462
+    if (NNLO)
+      for (int i = 0; i < 3; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int lp = 0; lp < NL; ++lp) v = fma(a.lctnnlo[lp * 3 + i], A.nnlo[lp], v);
+        atomicAdd(out + (size_t)(24 + i) * Bp, v);  // pybird.py:1455-1458
+      }
+  }
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -166,31 +163,37 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-template <int NL, int NIR, bool NNLO>
-__global__ void __launch_bounds__(RS_THREADS, 2) resum_kernel(ResumArgs a) {
+// one CTA = one cosmology and one a in {0, 1}; 3 CTAs per SM (a single warp cannot issue DFMAs at the full pipe
+// rate, it takes 3-4 warps per scheduler)
+template <int NL, int NIR, bool NNLO, int IA>
+__global__ void __launch_bounds__(RS_THREADS, 3) resum_kernel(ResumArgs a) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int NQ = 2 * NL * NL * NIR * RS_SLOTS;
-  double* Qs = sm;                       // [2][NL][NL][NIR][4]
-  double* Xs = Qs + NQ;                  // [NsP]
+  constexpr int NQH = NL * NL * NIR * RS_SLOTS;  // this a's half of the expanded Q table
+  double* Qs = sm;                       // [NL][NL][NIR][4]
+  double* Xs = Qs + NQH;                 // [NsP]
   double* Ys = Xs + a.NsP;               // [NsP]
-  double* Cs = Ys + a.NsP;               // [NL][ncr][NsP]
+  double* Cs = Ys + a.NsP;               // [NL][nrow][NsP]
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t Bp = a.Bp;
+  const int nrow = IA ? a.ncr - 1 : 1, row0 = IA ? 1 : 0;
 
   for (int s = tid; s < a.NsP; s += RS_THREADS) {
     const bool ok = s < a.Ns;
     Xs[s] = ok ? a.F[(size_t)(a.row_x + s) * Bp + b] : 0.0;
     Ys[s] = ok ? a.F[(size_t)(a.row_y + s) * Bp + b] : 0.0;
   }
+  {  // Cr is point-major [b][l][ncr][Ns]: contiguous, coalesced
+    const double* crb = a.Cr + (size_t)b * NL * a.ncr * a.Ns;
 #pragma unroll 8
-  for (int i = tid; i < NL * a.ncr * a.NsP; i += RS_THREADS) {
-    const int s = i % a.NsP, r = i / a.NsP;
-    Cs[i] = s < a.Ns ? a.Cr[((size_t)r * a.Ns + s) * Bp + b] : 0.0;
+    for (int i = tid; i < NL * nrow * a.NsP; i += RS_THREADS) {
+      const int s = i % a.NsP, r = (i / a.NsP) % nrow, l = i / (a.NsP * nrow);
+      Cs[i] = s < a.Ns ? crb[((size_t)l * a.ncr + row0 + r) * a.Ns + s] : 0.0;
+    }
   }
   {  // Q^{ll'}(f) of this cosmology, expanded by resum_q_kernel
-    const double* qf = a.Qf + (size_t)b * NQ;
+    const double* qf = a.Qf + (size_t)b * (2 * NQH) + (size_t)IA * NQH;
 #pragma unroll
-    for (int i = tid; i < NQ; i += RS_THREADS) Qs[i] = qf[i];
+    for (int i = tid; i < NQH; i += RS_THREADS) Qs[i] = qf[i];
   }
   __syncthreads();
 
@@ -198,13 +201,13 @@ __global__ void __launch_bounds__(RS_THREADS, 2) resum_kernel(ResumArgs a) {
   const int rem = ntask % RS_THREADS;
   const bool coop = rem > 0 && rem <= RS_THREADS / 32;
   const int nmain = coop ? ntask - rem : ntask;
-  Accum<NL, NNLO> A;
+  Accum<NL, NNLO, IA> A;
   for (int task = tid; task < nmain; task += RS_THREADS) {
     const int l = task / a.Nkr, ik = task - l * a.Nkr;
     const double k2 = a.kr2[ik];
     A.zero();
-    for (int ch = 0; ch < nchunk; ++ch) sweep_chunk<NL, NIR, NNLO>(a, Qs, Xs, Ys, Cs, l, ik, k2, ch * RS_C, A);
-    write_out<NL, NNLO>(a, b, l, ik, A);
+    for (int ch = 0; ch < nchunk; ++ch) sweep_chunk<NL, NIR, NNLO, IA>(a, Qs, Xs, Ys, Cs, l, ik, k2, ch * RS_C, A);
+    write_out<NL, NNLO, IA>(a, b, l, ik, A);
   }
   const int warp = tid >> 5, lane = tid & 31;
   if (coop && warp < rem) {
@@ -212,16 +215,18 @@ __global__ void __launch_bounds__(RS_THREADS, 2) resum_kernel(ResumArgs a) {
     const int l = task / a.Nkr, ik = task - l * a.Nkr;
     const double k2 = a.kr2[ik];
     A.zero();
-    for (int ch = lane; ch < nchunk; ch += 32) sweep_chunk<NL, NIR, NNLO>(a, Qs, Xs, Ys, Cs, l, ik, k2, ch * RS_C, A);
+    for (int ch = lane; ch < nchunk; ch += 32) sweep_chunk<NL, NIR, NNLO, IA>(a, Qs, Xs, Ys, Cs, l, ik, k2, ch * RS_C, A);
 #pragma unroll
-    for (int i = 0; i < NL; ++i) { A.lin0[i] = warp_sum(A.lin0[i]); A.lin1[i] = warp_sum(A.lin1[i]); }
+    for (int i = 0; i < NL; ++i) A.lin[i] = warp_sum(A.lin[i]);
+    if (IA) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) A.loop[i] = warp_sum(A.loop[i]);
-    if (NNLO) {
+      for (int i = 0; i < 12; ++i) A.loop[i] = warp_sum(A.loop[i]);
+      if (NNLO) {
 #pragma unroll
-      for (int i = 0; i < NL; ++i) A.nnlo[i] = warp_sum(A.nnlo[i]);
+        for (int i = 0; i < NL; ++i) A.nnlo[i] = warp_sum(A.nnlo[i]);
+      }
     }
-    if (lane == 0) write_out<NL, NNLO>(a, b, l, ik, A);
+    if (lane == 0) write_out<NL, NNLO, IA>(a, b, l, ik, A);
   }
 }
 
@@ -241,20 +246,29 @@ __global__ void __launch_bounds__(256) resum_q_kernel(const double* __restrict__
   Qf[(size_t)b * NQ + i] = v;
 }
 
+template <int NL, int NIR, bool NNLO, int IA>
+int run_half(const ResumArgs& a, cudaStream_t s) {
+  const int nrow = IA ? a.ncr - 1 : 1;
+  size_t smem = sizeof(double) * ((size_t)NL * NL * NIR * RS_SLOTS + 2 * a.NsP + (size_t)NL * nrow * a.NsP);
+  static size_t configured = 0;
+  if (smem > configured) {
+    EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NNLO, IA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  resum_kernel<NL, NIR, NNLO, IA><<<a.B, RS_THREADS, smem, s>>>(a);
+  EFTB_LAUNCH_CHECK();
+  return EFTB_OK;
+}
+
 template <int NL, int NIR, bool NNLO>
 int run(const ResumArgs& a, cudaStream_t s) {
   dim3 qgrid((a.NQ + 255) / 256, a.B);
   resum_q_kernel<<<qgrid, 256, 0, s>>>(a.qpack, a.f, a.NQ, a.qdeg, a.B, a.Qf);
   EFTB_LAUNCH_CHECK();
-  size_t smem = sizeof(double) * ((size_t)2 * NL * NL * NIR * RS_SLOTS + 2 * a.NsP + (size_t)NL * a.ncr * a.NsP);
-  static size_t configured = 0;
-  if (smem > configured) {
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NNLO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  resum_kernel<NL, NIR, NNLO><<<a.B, RS_THREADS, smem, s>>>(a);
-  EFTB_LAUNCH_CHECK();
-  return EFTB_OK;
+  // the heavier half first; the light (a = 0) CTAs fill its tail
+  int rc = run_half<NL, NIR, NNLO, 1>(a, s);
+  if (rc) return rc;
+  return run_half<NL, NIR, NNLO, 0>(a, s);
 }
 
 }  // namespace

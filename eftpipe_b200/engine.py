@@ -144,7 +144,7 @@ class DevicePlan:
         c = self.cfg
         P22 = self._empty(N22, c.Nk, Bp)
         Dg = self._empty(c.Nl, 12, c.Nmax + 1, 2, Bp)
-        Cr = self._empty(c.Nl, 14 + c.with_nnlo, c.Ns, Bp)
+        Cr = self._empty(Bp, c.Nl, 14 + c.with_nnlo, c.Ns)  # point-major
         _lib.check(self.lib.eftb_spectral_grouped(self.handle, B, _p(D), _p(f_bm), _p(Dg), _p(P22), _p(Cr),
                                                   _stream_ptr(self.torch)), "eftb_spectral_grouped")
         return P22, Cr
@@ -155,7 +155,7 @@ class DevicePlan:
         c = self.cfg
         T = self._empty(c.Nl, c.Nk, c.nterm, Bp)
         if Cr is None:
-            Cr = self._empty(c.Nl, 14 + c.with_nnlo, c.Ns, Bp)
+            Cr = self._empty(Bp, c.Nl, 14 + c.with_nnlo, c.Ns)  # point-major
         _lib.check(self.lib.eftb_group(self.handle, B, _p(F), _p(P22), _p(Cs), _p(f_bm), _p(T), _p(Cr),
                                        _stream_ptr(self.torch)), "eftb_group")
         return T, Cr

@@ -228,7 +228,7 @@ class Bird(_TermsView):
 
     @property
     def Cloopl(self):
-        return self._out(self._Cr[:, 2:14, :, : self.B].permute(3, 0, 1, 2))
+        return self._out(self._Cr[: self.B, :, 2:14, :])
 
     # ---- reference methods ----
     def setPsCfl(self):

@@ -152,10 +152,19 @@ class Window:
         return Wal
 
     def _save_Wal(self):
-        np.save(self.window_fourier_file, self.Wal)
+        # the reference saves on the MPI root only (window.py:361-369); here several ranks may build the same
+        # window concurrently, so every file is written under a private name and renamed into place atomically
+        import os
+
+        final = self.window_fourier_file
+        tmp = final.with_name(f".{final.stem}.{os.getpid()}.tmp.npy")
+        np.save(tmp, self.Wal)
+        os.replace(tmp, final)
         if self._create_meta:
-            with self.window_fourier_file.with_suffix(".json").open("w") as fh:
+            mtmp = final.with_name(f".{final.stem}.{os.getpid()}.tmp.json")
+            with mtmp.open("w") as fh:
                 json.dump(self.meta, fh, indent=2)
+            os.replace(mtmp, final.with_suffix(".json"))
 
     # ---- operators ----
     @property

@@ -110,7 +110,7 @@ int eftb_to_point_major(const double* in, int B, int R, const int32_t* perm, dou
  * P22  [28][Nk][Bp]               bird.P22          (pybird.py:1074-1078)
  * Cs   [Nl][38][Ns][Bp]           bird.C22 (ch<28), bird.C13 (ch>=28), before Legendre weights
  * T    [Nl][Nk][nterm][Bp]        term index: 0-2 P11l, 3-8 Pctl, 9-20 Ploopl, 21-23 Pstl, 24-26 PctNNLOl
- * Cr   [Nl][ncr][Ns][Bp]          rows: C11, Cct, Cloopl x12 [, CctNNLO]; ncr = 14 + with_nnlo
+ * Cr   [Bp][Nl][ncr][Ns]          POINT-major; rows: C11, Cct, Cloopl x12 [, CctNNLO]; ncr = 14 + with_nnlo
  */
 /* Bird.__init__ interpolation + FFTLog.Coef + IRFilters + makeP13/C11/Cct (pybird.py:694-695,
    :1127-1141, :1080-1101, :1316-1353; fftlog.py:84-166).  plin: point-major [B][nin]. */
