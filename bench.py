@@ -236,6 +236,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
     if world > 1 and rank != 0:
@@ -285,6 +286,19 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(d_plin, d_f, d_DA, d_H, d_cols)
     torch.cuda.synchronize()
+    # one CUDA graph per step: the 22 launches are replayed with a single launch call
+    graph = None
+    if not args.no_graph:
+        from eftpipe_b200.engine import capture_graph
+
+        try:
+            graph, (g_logp, g_status) = capture_graph(lambda: step(d_plin, d_f, d_DA, d_H, d_cols))
+            for _ in range(args.warmup):
+                graph.replay()
+            torch.cuda.synchronize()
+        except Exception as exc:  # report and fall back to eager launches
+            print(f"bench: CUDA graph capture failed ({exc}); timing eager launches", file=sys.stderr)
+            graph = None
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local)
@@ -296,7 +310,11 @@ def run_ours(args):
     for i in range(args.steps):
         flush.zero_()  # evict L2 between timed iterations (not timed)
         ev[i][0].record()
-        logp, status = step(d_plin, d_f, d_DA, d_H, d_cols)
+        if graph is not None:
+            graph.replay()
+            logp, status = g_logp, g_status
+        else:
+            logp, status = step(d_plin, d_f, d_DA, d_H, d_cols)
         ev[i][1].record()
     torch.cuda.synchronize()
     w1 = time.time()
@@ -312,13 +330,29 @@ def run_ours(args):
     h_png = torch.empty((B, 3 * nk), dtype=torch.float64).pin_memory()
     g_in = [torch.empty_like(x, device="cuda") for x in (h_plin, h_f, h_DA, h_H, h_cols)]
 
+    def e2e_device():
+        lp, _ = step(*g_in)
+        vec = like.vectors(B, [terms_bm], [dp.to_batch_minor(g_in[1])[0]], dp.to_batch_minor(g_in[4]))
+        return lp, vec[:, :, 0].contiguous()
+
+    e2e_graph = None
+    if graph is not None:
+        try:
+            e2e_graph, (e_logp, e_png) = capture_graph(e2e_device)
+        except Exception as exc:
+            print(f"bench: e2e graph capture failed ({exc})", file=sys.stderr)
+            e2e_graph = None
+
     def e2e_step():
         for dst, src in zip(g_in, (h_plin, h_f, h_DA, h_H, h_cols)):
             dst.copy_(src, non_blocking=True)
-        logp, _ = step(*g_in)
-        vec = like.vectors(B, [terms_bm], [dp.to_batch_minor(g_in[1])[0]], dp.to_batch_minor(g_in[4]))
-        h_logp.copy_(logp, non_blocking=True)
-        h_png.copy_(vec[:, :, 0], non_blocking=True)
+        if e2e_graph is not None:
+            e2e_graph.replay()
+            lp, png = e_logp, e_png
+        else:
+            lp, png = e2e_device()
+        h_logp.copy_(lp, non_blocking=True)
+        h_png.copy_(png, non_blocking=True)
 
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()
@@ -358,7 +392,8 @@ def run_ours(args):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-shard x{world}",
-                   "l2": "256 MiB buffer written between timed iterations; per-step working set ~%d MB" % (dp.lib.eftb_workspace_bytes(dp.handle, B) // 2**20)},
+                   "l2": "256 MiB buffer written between timed iterations; per-step working set ~%d MB" % (dp.lib.eftb_workspace_bytes(dp.handle, B) // 2**20),
+                   "launch": "one CUDA graph replay per step" if graph is not None else "eager launches"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches["n"] * args.steps,
@@ -376,6 +411,120 @@ def run_ours(args):
                                           f"({os.cpu_count()}); oracle/pybird_oracle.py restatement of the reference path"}
         line["logp_check"]["max_rel_err_vs_oracle"] = float(np.max(np.abs(got - ref_logp) / np.abs(ref_logp)))
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ config 3 (informational)
+def run_multitracer(args):
+    """BASELINE configs[2]/[3]: the DR16 NGC LRG x ELG x cross likelihood (3 tracer pipelines, 142 data points, 14
+    analytically marginalised parameters) through the reference-facing API (theory.EFTLSS + likelihood.EFTLike).
+    Not the driver's bench line (that is config 2); run with --workload config3 to get the north-star figure."""
+    import torch
+    import torch.distributed as dist
+
+    from eftpipe_b200 import likelihood, synthetic, theory
+    from eftpipe_b200.engine import capture_graph
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fx = load_fixture()
+    B = args.batch
+    ap = dict(Om_AP=0.307115, rdrag_AP=147.66, h_AP=0.6777, APst=True)
+    tracers = {
+        "LRG_NGC": dict(prefix="LRG_NGC_", z=0.696, nd=4.5e-5, window=dict(window_configspace_array=fx["win_LRG"])),
+        "ELG_NGC": dict(prefix="ELG_NGC_", z=0.849, nd=2.3e-4, window=dict(window_configspace_array=fx["win_ELG"])),
+        "X_NGC": dict(prefix="X_NGC_", z=0.763, cross=["LRG_NGC", "ELG_NGC"], window=dict(window_configspace_array=fx["win_X"])),
+        "default": dict(km=0.7, kr=0.25, with_IRresum=True, with_APeffect=True, with_window=True, APeffect=ap,
+                        window=dict(accboost=4, windowk=0.1)),
+    }
+    west = {n: {"scale": None} for n in ("b3", "cct", "cr1", "cr2", "ce0", "cequad")}
+    marg = {"LRG_NGC_": west, "ELG_NGC_": dict(west), "X_NGC_ce0": {"scale": None}, "X_NGC_cequad": {"scale": None}}
+    if world > 1 and rank != 0:
+        dist.barrier()
+    t0 = time.time()
+    like = likelihood.EFTLike(
+        tracers=["LRG_NGC", "ELG_NGC", "X_NGC"], chained=[False, True, False],
+        data={"LRG_NGC": dict(table=fx["NGC_LRG_P"], ls=[0, 2, 4], kmin=0.02, kmax=0.20),
+              "ELG_NGC": dict(table=fx["NGC_ELG_Q"], ls=[0, 2], kmin=0.03, kmax=0.20, symbol="Q"),
+              "X_NGC": dict(table=fx["NGC_X_P"], ls=[0, 2, 4], kmin=0.02, kmax=0.20)},
+        cov=dict(matrix=fx["cov_NGC_L024E02X024_PQP"], Nreal=1000), with_binning=True, jeffreys=True, marg=marg)
+    th = theory.EFTLSS(tracers).must_provide(like.get_requirements()).initialize()
+    like.initialize_with_provider(th)
+    t_setup = time.time() - t0
+    if world > 1 and rank == 0:
+        dist.barrier()
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda")
+    cosmo = {}
+    for name, z in (("LRG_NGC", 0.696), ("ELG_NGC", 0.849), ("X_NGC", 0.763)):
+        b = synthetic.make_batch(B, z, seed=20261018 + 3 + 1000 * rank, unique=min(B, 32))
+        cosmo[name] = dict(pkh=dev(b.plin), f=dev(b.f), DA=dev(b.DA), H=dev(b.H))
+    rng = np.random.default_rng(11 + rank)
+    params = {}
+    for pre, b1 in (("LRG_NGC_", 2.1), ("ELG_NGC_", 1.4)):
+        params[pre + "b1"] = dev(b1 + 0.05 * rng.standard_normal(B))
+        c2 = 0.7 + 0.1 * rng.standard_normal(B)
+        params[pre + "b2"], params[pre + "b4"] = dev(c2 / np.sqrt(2)), dev(c2 / np.sqrt(2))
+
+    def step():
+        th.calculate(cosmo)
+        res = like.calculate(params)
+        return res["logp"], res["status"]
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    graph = None
+    if not args.no_graph:
+        try:
+            graph, (g_logp, g_status) = capture_graph(step)
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as exc:
+            print(f"bench: CUDA graph capture failed ({exc}); timing eager launches", file=sys.stderr)
+            graph = None
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    w0 = time.time()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        if graph is not None:
+            graph.replay()
+            logp, status = g_logp, g_status
+        else:
+            logp, status = step()
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    w1 = time.time()
+    clocks = sampler.stop(w0, w1)
+    t = torch.tensor([sum(a.elapsed_time(b_) for a, b_ in ev)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t[0])
+    if rank == 0:
+        line = {"metric": METRIC, "value": B * world * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "config3: DR16 NGC LRG x ELG x cross, 3 tracer pipelines (IRresum + AP + window + binning, ELG chained),"
+                                       " 142 data points, 14 marginalised parameters (Jeffreys), through theory.EFTLSS + likelihood.EFTLike",
+                           "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-shard x{world}",
+                           "launch": "one CUDA graph replay per step" if graph is not None else "eager launches"},
+                "clocks": clocks, "setup_s": round(t_setup, 1),
+                "logp_check": {"finite": bool(torch.isfinite(logp).all()), "status_nonzero": int((status != 0).sum())}}
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -482,11 +631,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="points per GPU per step")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
+                    help="config2 = the bench line (single tracer); config3 = informational multi-tracer likelihood")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "config3":
+        return run_multitracer(args)
     return run_ours(args)
 
 

@@ -38,21 +38,24 @@ __global__ void to_point_major_kernel(const double* __restrict__ in, int B, int 
 }
 
 // power-law tails beyond the last input sample (fftlog.py:146-151) for the loop FFTLog and for the
-// 32-point IR-filter FFTLog of P exp(-k^2/Lambda^2)/k^2 (pybird.py:1321-1325).  One lane per point.
+// 32-point IR-filter FFTLog of P exp(-k^2/Lambda^2)/k^2 (pybird.py:1321-1325).  One thread per (tail node, point).
 __global__ void front_tails_kernel(const double* __restrict__ plin, int B, int Bp, int nin, int ntail, int ntailx,
                                    const double* __restrict__ lr, const double* __restrict__ lrx, double inv_dlog,
                                    double wx_last, double wx_prev, double* __restrict__ u) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
   if (b >= Bp) return;
-  int src = min(b, B - 1);
+  const int src = min(b, B - 1);
   double last = plin[(size_t)src * nin + nin - 1], prev = plin[(size_t)src * nin + nin - 2];
-  double slope = (log(last) - log(prev)) * inv_dlog;
-  double* ut = u + (size_t)nin * Bp + b;
-  for (int i = 0; i < ntail; ++i) ut[(size_t)i * Bp] = last * exp(slope * lr[i]);
-  double fl = last * wx_last, fp = prev * wx_prev;
-  double slx = (log(fl) - log(fp)) * inv_dlog;
-  ut += (size_t)ntail * Bp;
-  for (int i = 0; i < ntailx; ++i) ut[(size_t)i * Bp] = fl * exp(slx * lrx[i]);
+  double x;
+  if (i < ntail) {
+    x = lr[i];
+  } else {
+    last *= wx_last;
+    prev *= wx_prev;
+    x = lrx[i - ntail];
+  }
+  const double slope = (log(last) - log(prev)) * inv_dlog;
+  u[(size_t)(nin + i) * Bp + b] = last * exp(slope * x);
 }
 
 }  // namespace
@@ -75,7 +78,7 @@ int launch_front_prepare(const eftb_plan* p, int B, int Bp, const double* plin, 
   const eftb_config& c = p->cfg;
   int rc = launch_to_batch_minor(plin, B, Bp, c.nin, u, s);
   if (rc) return rc;
-  front_tails_kernel<<<(Bp + 127) / 128, 128, 0, s>>>(plin, B, Bp, c.nin, c.ntail, c.ntailx, p->lr, p->lrx, c.inv_dlog,
+  front_tails_kernel<<<dim3((Bp + 127) / 128, c.ntail + c.ntailx), 128, 0, s>>>(plin, B, Bp, c.nin, c.ntail, c.ntailx, p->lr, p->lrx, c.inv_dlog,
                                                      c.wx_last, c.wx_prev, u);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;

@@ -166,7 +166,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // one CTA = one cosmology and one a in {0, 1}; 3 CTAs per SM (a single warp cannot issue DFMAs at the full pipe
 // rate, it takes 3-4 warps per scheduler)
 template <int NL, int NIR, bool NNLO, int IA>
-__global__ void __launch_bounds__(RS_THREADS, 3) resum_kernel(ResumArgs a) {
+__device__ __forceinline__ void resum_body(const ResumArgs& a) {
   extern __shared__ __align__(16) double sm[];
   constexpr int NQH = NL * NL * NIR * RS_SLOTS;  // this a's half of the expanded Q table
   double* Qs = sm;                       // [NL][NL][NIR][4]
@@ -230,6 +230,13 @@ __global__ void __launch_bounds__(RS_THREADS, 3) resum_kernel(ResumArgs a) {
   }
 }
 
+// grid (B, 2): blockIdx.y = 0 runs the heavier a = 1 half (issued first), blockIdx.y = 1 the a = 0 half that fills the tail
+template <int NL, int NIR, bool NNLO>
+__global__ void __launch_bounds__(RS_THREADS, 3) resum_kernel(ResumArgs a) {
+  if (blockIdx.y == 0) resum_body<NL, NIR, NNLO, 1>(a);
+  else resum_body<NL, NIR, NNLO, 0>(a);
+}
+
 // Q^{ll'}_u(f) = sum_d q[u][d] f^d for every cosmology (pybird.py:1367-1380 evaluates the reference's lambdas);
 // qpack is [qdeg][NQ] so that consecutive threads read consecutive entries; Qf is [B][NQ]
 __global__ void __launch_bounds__(256) resum_q_kernel(const double* __restrict__ qpack, const double* __restrict__ f, int NQ,
@@ -246,29 +253,20 @@ __global__ void __launch_bounds__(256) resum_q_kernel(const double* __restrict__
   Qf[(size_t)b * NQ + i] = v;
 }
 
-template <int NL, int NIR, bool NNLO, int IA>
-int run_half(const ResumArgs& a, cudaStream_t s) {
-  const int nrow = IA ? a.ncr - 1 : 1;
-  size_t smem = sizeof(double) * ((size_t)NL * NL * NIR * RS_SLOTS + 2 * a.NsP + (size_t)NL * nrow * a.NsP);
-  static size_t configured = 0;
-  if (smem > configured) {
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NNLO, IA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  resum_kernel<NL, NIR, NNLO, IA><<<a.B, RS_THREADS, smem, s>>>(a);
-  EFTB_LAUNCH_CHECK();
-  return EFTB_OK;
-}
-
 template <int NL, int NIR, bool NNLO>
 int run(const ResumArgs& a, cudaStream_t s) {
   dim3 qgrid((a.NQ + 255) / 256, a.B);
   resum_q_kernel<<<qgrid, 256, 0, s>>>(a.qpack, a.f, a.NQ, a.qdeg, a.B, a.Qf);
   EFTB_LAUNCH_CHECK();
-  // the heavier half first; the light (a = 0) CTAs fill its tail
-  int rc = run_half<NL, NIR, NNLO, 1>(a, s);
-  if (rc) return rc;
-  return run_half<NL, NIR, NNLO, 0>(a, s);
+  size_t smem = sizeof(double) * ((size_t)NL * NL * NIR * RS_SLOTS + 2 * a.NsP + (size_t)NL * (a.ncr - 1) * a.NsP);
+  static size_t configured = 0;
+  if (smem > configured) {
+    EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NNLO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  resum_kernel<NL, NIR, NNLO><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
+  EFTB_LAUNCH_CHECK();
+  return EFTB_OK;
 }
 
 }  // namespace

@@ -22,6 +22,25 @@ def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def capture_graph(fn, warmup=2):
+    """Capture `fn()` (a fixed sequence of library calls on static device tensors) into a CUDA graph.  Returns
+    (graph, outputs): `graph.replay()` re-runs the ~20 kernel launches of a pipeline step with one launch call,
+    `outputs` are the static tensors `fn` returned.  The library's launchers are capture-safe after their first
+    call (function attributes and the anti-diagonal schedule are set up once, no synchronisation, no allocation)."""
+    torch = _lib.require_cuda()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warmup):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = fn()
+    return graph, out
+
+
 class DevicePlan:
     """One tracer's pipeline on the current CUDA device."""
 
