@@ -28,18 +28,17 @@ struct ApArgs {
   double da_fid, h_fid;
 };
 
-// Branch-free 1/sqrt(x) for x ~ O(1): single-precision seed (one MUFU) and two Newton steps with FMA residuals
-// (relative error 1e-7 -> 1e-14 -> ~1 ulp).  CUDA's rsqrt(double) carries a special-case branch + call, which splits
-// the loop body into basic blocks and stops the scheduler from overlapping this chain with the accumulation.
+// Branch-free 1/sqrt(x): single-precision seed (one MUFU) and ONE Newton step with an FMA residual -> relative
+// error ~1e-14.  That is six orders below the 1e-8 parity bar for everything it feeds (k', mu'^2: smooth functions),
+// and it halves the dependent FP64 chain of a mu node, which is what bounds this kernel (a DFMA has ~40 cycles of
+// latency on this part and there are only ~3 warps per scheduler to hide it).  CUDA's rsqrt(double) also carries a
+// special-case branch + call that splits the loop body into basic blocks.
 __device__ __forceinline__ double rsqrt_newton(double x) {
   float yf;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)x));
-  double y = (double)yf;
-  double e = fma(-(x * y), y, 1.0);
-  y = fma(0.5 * y, e, y);
-  e = fma(-(x * y), y, 1.0);
-  y = fma(0.5 * y, e, y);
-  return y;
+  const double y = (double)yf;
+  const double e = fma(-(x * y), y, 1.0);
+  return fma(0.5 * y, e, y);
 }
 
 constexpr int GEOM_THREADS = 128;
@@ -167,14 +166,25 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
     for (int r = 0; r < 4; ++r) atomicAdd(g + q * a.wcap + r, acc[q][r]);
 }
 
-constexpr int APPLY_CH = 8;  // window columns fetched per step: NL * APPLY_CH independent loads in flight
+constexpr int APPLY_WS = 16;  // window columns of a node staged in shared memory (wider windows: rest from global)
 
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+
+// One CTA per cosmology.  Thread = (k group, l, term row): the B-spline coefficients of the cosmology live in shared
+// memory ([l'][term][j], point-major from the Cinv GEMM), and the banded-operator rows of the NEXT k node of each
+// group are copied global -> shared with cp.async while the current node is contracted (double buffer), so every
+// operator word is fetched once per CTA and its DRAM/L2 latency is hidden behind the previous node.
 template <int NL>
 __global__ void __launch_bounds__(APPLY_THREADS) ap_apply_kernel(ApArgs a) {
   constexpr int NQ = NL * NL;
   extern __shared__ __align__(16) double sm[];
+  const int nslot = NL * a.nterm, ngrp = APPLY_THREADS / nslot;
   double* coefs = sm;                                                   // [NL][nterm][Nk]
-  int2* metas = reinterpret_cast<int2*>(coefs + (size_t)NL * a.Nk * a.nterm);  // [Nk]
+  double* Gs = coefs + (size_t)NL * a.Nk * a.nterm;                     // [2][ngrp][NQ][APPLY_WS]
+  int2* metas = reinterpret_cast<int2*>(Gs + (size_t)2 * ngrp * NQ * APPLY_WS);  // [Nk]
   const int bl = blockIdx.x, b = a.b0 + bl, tid = threadIdx.x;
   const size_t Bp = a.Bp;
   for (int i = tid; i < a.Nk; i += APPLY_THREADS) metas[i] = a.meta[(size_t)bl * a.Nk + i];
@@ -187,32 +197,54 @@ __global__ void __launch_bounds__(APPLY_THREADS) ap_apply_kernel(ApArgs a) {
   const double norm = 1.0 / (qperp * qperp * qpar);  // pybird.py:1611
   __syncthreads();
 
-  const int nslot = NL * a.nterm, ngrp = APPLY_THREADS / nslot;
   const int grp = tid / nslot, slot = tid - grp * nslot;
-  if (grp >= ngrp) return;
-  const int l = slot / a.nterm, i = slot - l * a.nterm;
+  const bool active = grp < ngrp;
+  const int l = active ? slot / a.nterm : 0, i = active ? slot - l * a.nterm : 0;
   const bool apply = a.ap_st || i < 21 || i >= 24;  // Pstl only with APst (pybird.py:1618-1619)
-  for (int ik = grp; ik < a.Nk; ik += ngrp) {
-    const size_t o = ((size_t)(l * a.Nk + ik) * a.nterm + i) * Bp + b;
-    if (!apply) { a.Tout[o] = a.Tin[o]; continue; }
-    const int2 mw = metas[ik];
-    // rows (l, l'=0..NL-1) of this node's banded operator; the 24-27 term lanes of a warp read the same words
-    const double* Gk = a.G + (((size_t)bl * a.Nk + ik) * NQ + l * NL) * a.wcap;
-    const double* cf = coefs + (size_t)i * a.Nk + mw.x;
-    double acc = 0.0;
-    for (int c0 = 0; c0 < mw.y; c0 += APPLY_CH) {
-      double gv[NL][APPLY_CH];
-#pragma unroll
-      for (int lp = 0; lp < NL; ++lp)
-#pragma unroll
-        for (int c = 0; c < APPLY_CH; ++c) gv[lp][c] = c0 + c < mw.y ? __ldg(Gk + lp * a.wcap + c0 + c) : 0.0;
-#pragma unroll
-      for (int lp = 0; lp < NL; ++lp)
-#pragma unroll
-        for (int c = 0; c < APPLY_CH; ++c)
-          if (c0 + c < mw.y) acc = fma(gv[lp][c], cf[(size_t)lp * a.nterm * a.Nk + c0 + c], acc);
+  const double* Gb = a.G + (size_t)bl * a.Nk * NQ * a.wcap;
+  auto prefetch = [&](int ik, int buf) {
+    if (active && ik < a.Nk) {
+      const int wn = min(metas[ik].y, APPLY_WS);
+      const double* Gk = Gb + (size_t)ik * NQ * a.wcap;
+      double* dst = Gs + (size_t)((buf * ngrp + grp) * NQ) * APPLY_WS;
+      for (int e = slot; e < NQ * APPLY_WS; e += nslot) {
+        const int q = e / APPLY_WS, c = e - q * APPLY_WS;
+        if (c < wn) cp_async8(dst + e, Gk + (size_t)q * a.wcap + c);
+      }
     }
-    a.Tout[o] = norm * acc;
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  prefetch(grp, 0);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+  const int niter = (a.Nk + ngrp - 1) / ngrp;
+  for (int it = 0; it < niter; ++it) {
+    const int buf = it & 1, ik = grp + it * ngrp;
+    prefetch(ik + ngrp, buf ^ 1);
+    if (active && ik < a.Nk) {
+      const size_t o = ((size_t)(l * a.Nk + ik) * a.nterm + i) * Bp + b;
+      if (!apply) {
+        a.Tout[o] = a.Tin[o];
+      } else {
+        const int2 mw = metas[ik];
+        const double* gq = Gs + (size_t)((buf * ngrp + grp) * NQ + l * NL) * APPLY_WS;
+        const double* cf = coefs + (size_t)i * a.Nk + mw.x;
+        const int wn = min(mw.y, APPLY_WS);
+        double acc = 0.0;
+#pragma unroll
+        for (int lp = 0; lp < NL; ++lp)
+          for (int c = 0; c < wn; ++c) acc = fma(gq[lp * APPLY_WS + c], cf[(size_t)lp * a.nterm * a.Nk + c], acc);
+        if (mw.y > APPLY_WS) {  // strong AP distortion: the columns beyond the staged window straight from global
+          const double* Gk = Gb + ((size_t)ik * NQ + l * NL) * a.wcap;
+          for (int c = APPLY_WS; c < mw.y; ++c)
+#pragma unroll
+            for (int lp = 0; lp < NL; ++lp) acc = fma(__ldg(Gk + lp * a.wcap + c), cf[(size_t)lp * a.nterm * a.Nk + c], acc);
+        }
+        a.Tout[o] = norm * acc;
+      }
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
   }
 }
 
@@ -227,7 +259,8 @@ int ap_chunk(const eftb_config& c, int B) {
 template <int NL>
 int run(ApArgs a, int B, cudaStream_t s) {
   const size_t smem_g = sizeof(double) * ((size_t)(1 + NL) * a.nmu + a.nint + (size_t)a.nint * 16);
-  const size_t smem_a = sizeof(double) * ((size_t)NL * a.Nk * a.nterm) + sizeof(int2) * a.Nk;
+  const size_t smem_a = sizeof(double) * ((size_t)NL * a.Nk * a.nterm + (size_t)2 * (APPLY_THREADS / (NL * a.nterm)) * NL * NL * APPLY_WS) +
+                        sizeof(int2) * a.Nk;
   if (NL * a.nterm > APPLY_THREADS || smem_g > 200 * 1024 || smem_a > 200 * 1024) {
     eftb_set_error("ap: unsupported sizes nmu=%d nterm=%d Nk=%d", a.nmu, a.nterm, a.Nk);
     return EFTB_ERR_ARG;

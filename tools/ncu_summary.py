@@ -48,7 +48,7 @@ RAW = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"
        "sm__inst_executed_pipe_tensor_op_dmma.avg.pct_of_peak_sustained_active"]
 
 
-def full(src, dst, max_ids=8):
+def full(src, dst, max_ids=6):
     det = subprocess.run(["ncu", "-i", src, "--page", "details", "--csv"], capture_output=True, text=True).stdout
     raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(det.splitlines()))
