@@ -38,7 +38,7 @@ class EftbConstants(C.Structure):
         ("lrx", c_double_p), ("pair_table", c_double_p), ("pair_offsets", c_int32_p),
         ("Ak", c_double_p), ("As", c_double_p), ("R", c_double_p), ("q", c_double_p),
         ("kr2", c_double_p), ("Cinv", c_double_p), ("knot_lo", c_double_p), ("basis", c_double_p),
-        ("mu", c_double_p), ("wl", c_double_p), ("project", c_double_p),
+        ("mu", c_double_p), ("wl", c_double_p), ("project", c_double_p), ("project_st", c_double_p),
     ]
 
 

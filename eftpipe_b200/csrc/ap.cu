@@ -82,10 +82,11 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
   const int jlo = min(jfirst, jlast), jhi = max(jfirst, jlast);
   const int wn = jhi - jlo + 4;
   double* Grow = a.G + ((size_t)bl * a.Nk + ik) * NQ * a.wcap;
-  for (int q = 0; q < NQ; ++q)
-    for (int c = 0; c < wn; ++c) Grow[q * a.wcap + c] = 0.0;
   a.meta[(size_t)bl * a.Nk + ik] = make_int2(jlo, wn);
-  __threadfence();  // the zeroes must reach L2 before this thread's reductions (RED) on the same words
+  // k'(mu) is monotone, so the live window is only ever moved in the direction jfirst -> jlast (a k' that dips back
+  // across a knot by rounding keeps its current interval: the spline is C2, the value agrees to ~1e-14).  Every
+  // column of the window is therefore retired exactly once, with a plain store: no zero-fill, no atomics.
+  const bool up = jlast > jfirst, down = jlast < jfirst;
 
   double acc[NQ][4];
 #pragma unroll
@@ -108,11 +109,11 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
   };
   // move the live window to the interval of k' (rare), then the 4 B-spline values and the even Legendre polynomials
   auto locate_and_basis = [&](double kp, double mp2, double (&bv)[4], double (&L)[3]) {
-    while (j < jhi && kp >= knots[j + 1]) {  // k' is monotone in mu: j moves in one direction inside [jlo, jhi]
+    while (up && j < jhi && kp >= knots[j + 1]) {
       double* g = Grow + (j - jlo);          // B-spline j has no support beyond this knot: retire its column
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        atomicAdd(g + q * a.wcap, acc[q][0]);  // fire-and-forget RED: this row belongs to this thread alone
+        g[q * a.wcap] = acc[q][0];
         acc[q][0] = acc[q][1]; acc[q][1] = acc[q][2]; acc[q][2] = acc[q][3]; acc[q][3] = 0.0;
       }
       ++j;
@@ -120,11 +121,11 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
       for (int i = 0; i < 16; ++i) bc[i] = bas[j * 16 + i];
       knot = knots[j];
     }
-    while (j > jlo && kp < knot) {
+    while (down && j > jlo && kp < knot) {
       double* g = Grow + (j + 3 - jlo);
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        atomicAdd(g + q * a.wcap, acc[q][3]);
+        g[q * a.wcap] = acc[q][3];
         acc[q][3] = acc[q][2]; acc[q][2] = acc[q][1]; acc[q][1] = acc[q][0]; acc[q][0] = 0.0;
       }
       --j;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) atomicAdd(g + q * a.wcap + r, acc[q][r]);
+    for (int r = 0; r < 4; ++r) g[q * a.wcap + r] = acc[q][r];
 }
 
 constexpr int APPLY_WS = 16;  // window columns of a node staged in shared memory (wider windows: rest from global)

@@ -135,6 +135,7 @@ int eftb_plan_create(const eftb_config* cfg, const eftb_constants* h, eftb_plan*
   int nl_out = c.Nl, nk_out = c.Nk;
   if (c.has_project) {
     rc |= gemm_upload(h->project, 1, c.nout, c.Nl * c.Nk, &p->project);
+    if (h->project_st) rc |= gemm_upload(h->project_st, 1, c.nout, c.Nl * c.Nk, &p->project_st);
     nl_out = c.nl_out;
     nk_out = c.nl_out > 0 ? c.nout / c.nl_out : 0;
     if (nl_out < 1 || nl_out * nk_out != c.nout) { eftb_set_error("eftb_plan_create: nout != nl_out*nk_out"); rc = EFTB_ERR_ARG; }
@@ -159,7 +160,7 @@ void eftb_plan_destroy(eftb_plan* p) {
                   p->rs.Rt, p->rs.qpack, p->kr2, p->knot_lo, p->basis, p->mu, p->wl, p->perm_out};
   for (void* q : ptrs) if (q) cudaFree(q);
   antidiag_free(p);
-  gemm_free(&p->Wf); gemm_free(&p->Ak); gemm_free(&p->As); gemm_free(&p->Cinv); gemm_free(&p->project);
+  gemm_free(&p->Wf); gemm_free(&p->Ak); gemm_free(&p->As); gemm_free(&p->Cinv); gemm_free(&p->project); gemm_free(&p->project_st);
   delete p;
 }
 
@@ -281,7 +282,12 @@ int eftb_project(const eftb_plan* p, int B, const double* T, double* out, void* 
   EFTB_NEED(p && T && out && B >= 1, "NULL/invalid argument");
   if (!p->cfg.has_project) { eftb_set_error("eftb_project: plan built without projection"); return EFTB_ERR_NOT_BUILT; }
   const int Bp = eftb_padded_batch(B);
-  return gemm_run(p->project, T, out, p->cfg.nterm * Bp, 1, 1, 0, 0, 0, 0, (cudaStream_t)stream);
+  const size_t ld = (size_t)p->cfg.nterm * Bp;
+  int rc = gemm_run(p->project, T, out, p->cfg.nterm * Bp, 1, 1, 0, 0, 0, 0, (cudaStream_t)stream);
+  if (rc || !p->project_st.d) return rc;
+  // the stochastic rows (terms 21..23) see their own operator (window_st = False, fiberst = False): a column window
+  return gemm_run(p->project_st, T + (size_t)21 * Bp, out + (size_t)21 * Bp, 3 * Bp, 1, 1, 0, 0, 0, 0, (cudaStream_t)stream, nullptr,
+                  ld, ld);
 }
 
 int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double* f, const double* DA, const double* H,

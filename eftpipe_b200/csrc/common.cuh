@@ -44,7 +44,8 @@ void gemm_free(GemmMatrix* m);
 // z offsets zr*cs + zq*cs2): per-cosmology contiguous rows for the one-CTA-per-cosmology consumers.
 struct GemmPointMajor { int bp; size_t ld, is; };
 int gemm_run(const GemmMatrix& A, const double* X, double* C, int N, int nz, int zdiv, size_t xs, size_t xs2,
-             size_t cs, size_t cs2, cudaStream_t stream, const GemmPointMajor* pm = nullptr);
+             size_t cs, size_t cs2, cudaStream_t stream, const GemmPointMajor* pm = nullptr, size_t ldx = 0,
+             size_t ldc = 0);  // ldx / ldc: row pitch of X / C when the N columns are a window of a wider array (0 = N)
 
 struct AntidiagPack;  // fragment-ordered pair table + warp schedules (antidiag.cu)
 
@@ -61,7 +62,7 @@ struct eftb_plan {
   int K;  // nin + ntail + ntailx
   double *k = nullptr, *l11 = nullptr, *lct = nullptr, *lctnnlo = nullptr, *l22 = nullptr, *l13 = nullptr;
   double *lr = nullptr, *lrx = nullptr;
-  GemmMatrix Wf, Ak, As, Cinv, project;
+  GemmMatrix Wf, Ak, As, Cinv, project, project_st;  // project_st: operator of the stochastic rows when it differs
   AntidiagPack* ad = nullptr;
   double* kr2 = nullptr;
   ResumPack rs;

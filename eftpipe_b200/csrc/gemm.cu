@@ -27,6 +27,7 @@ struct GemmArgs {
   size_t xs, xs2, cs, cs2;
   int pm_bp;         // > 0: point-major epilogue, column n = i * pm_bp + b -> C[b * pm_ld + i * pm_is + row]
   size_t pm_ld, pm_is;
+  size_t ldx, ldc;   // row pitch of X and of the batch-minor C (>= N: a column window of a wider array)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
       int r = c / (BN / 2), q = c % (BN / 2);
       int kk = kt * BK + r, col = n0 + q * 2;
       bool ok = (kk < g.K) && (col < g.N);
-      const double* src = ok ? X + (size_t)kk * g.N + col : X;
+      const double* src = ok ? X + (size_t)kk * g.ldx + col : X;
       cp_async16(xs + r * XPITCH + q * 2, src, ok);
     }
     cp_async_commit();
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int col = n0 + warp * 32 + j * 8 + (lane & 3) * 2;
-      if (col < g.N) *reinterpret_cast<double2*>(C + (size_t)row * g.N + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+      if (col < g.N) *reinterpret_cast<double2*>(C + (size_t)row * g.ldc + col) = make_double2(acc[i][j][0], acc[i][j][1]);
     }
   }
 }
@@ -202,15 +203,15 @@ void gemm_free(GemmMatrix* m) {
 }
 
 int gemm_run(const GemmMatrix& A, const double* X, double* C, int N, int nz, int zdiv, size_t xs, size_t xs2,
-             size_t cs, size_t cs2, cudaStream_t stream, const GemmPointMajor* pm) {
-  if (!A.d || !X || !C || N % 2 || (pm && (pm->bp < 2 || pm->bp % 2))) { eftb_set_error("gemm_run: bad arguments"); return EFTB_ERR_ARG; }
+             size_t cs, size_t cs2, cudaStream_t stream, const GemmPointMajor* pm, size_t ldx, size_t ldc) {
+  if (!A.d || !X || !C || N % 2 || ldx % 2 || ldc % 2 || (pm && (pm->bp < 2 || pm->bp % 2))) { eftb_set_error("gemm_run: bad arguments"); return EFTB_ERR_ARG; }
   if (!g_sms) {
     int dev = 0;
     EFTB_CUDA_CHECK(cudaGetDevice(&dev));
     EFTB_CUDA_CHECK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   GemmArgs g{A.d, X, C, A.M, A.K, A.Kp, A.Mp, N, A.nbatch > 1 ? 1 : 0, zdiv, xs, xs2, cs, cs2,
-             pm ? pm->bp : 0, pm ? pm->ld : 0, pm ? pm->is : 0};
+             pm ? pm->bp : 0, pm ? pm->ld : 0, pm ? pm->is : 0, ldx ? ldx : (size_t)N, ldc ? ldc : (size_t)N};
   switch (pick_mt(A.M, ((N + BN - 1) / BN) * nz)) {
     case 11: return launch<11>(g, nz, stream);
     case 10: return launch<10>(g, nz, stream);

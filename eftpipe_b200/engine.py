@@ -86,6 +86,8 @@ class DevicePlan:
         if plan.project is not None:
             cfg.has_project, cfg.nout, cfg.nl_out = 1, plan.project.shape[0], plan.out_shape[0]
             cst.project = ptr(plan.project)
+            if plan.project_stoch is not None:
+                cst.project_st = ptr(plan.project_stoch)
         handle = C.c_void_p()
         _lib.check(self.lib.eftb_plan_create(C.byref(cfg), C.byref(cst), C.byref(handle)), "eftb_plan_create")
         self.handle, self.cfg = handle, cfg

@@ -353,6 +353,47 @@ def binning_matrix(k, kout, accboost=1, decimals=2, kedges=None):
     return mat, keff, bmin, bmax
 
 
+def fiber_matrix(k, Nl, fs, Dfc, ktrust=0.25):
+    """(Nl, Nk, Nl, Nk) operator F of `FiberCollision.dPcorr` (pybird.py:1703-1756), so that the corrected spectrum
+    is P + F.P: linear interpolation of P_l'(k) onto 1024 log-spaced q in [k_0, ktrust] (pybird.py:1714-1721),
+    then -fs Dfc^2/2 * sum_q q dq P_l'(q) f_ll'(k, q) with the IR kernel for q < k, l' <= l and the UV kernel for
+    k < q < ktrust, l' >= l (pybird.py:44-85, :1728-1755)."""
+    from scipy.special import j1
+
+    k = np.asarray(k, float)
+    q = np.geomspace(k.min(), ktrust, num=1024)
+    dq = np.concatenate([[0.0], q[1:] - q[:-1]])
+    # linear interpolation matrix S[q, n] of scipy interp1d(kind="linear", fill_value="extrapolate")
+    idx = np.clip(np.searchsorted(k, q, side="right") - 1, 0, k.size - 2)
+    w = (q - k[idx]) / (k[idx + 1] - k[idx])
+    S = np.zeros((q.size, k.size))
+    S[np.arange(q.size), idx] = 1.0 - w
+    S[np.arange(q.size), idx + 1] += w
+    W2D = 2.0 * j1(q * Dfc) / (q * Dfc)
+
+    def H(l, lp, x):  # pybird.py:49-65
+        table = {(2, 0): x**2 - 1.0, (4, 0): 1.75 * x**4 - 2.5 * x**2 + 0.75, (4, 2): x**4 - x**2}
+        return table.get((l, lp), 0.0 * x)
+
+    F = np.zeros((Nl, k.size, Nl, k.size))
+    for i, kv in enumerate(k):
+        ir, uv = q < kv, (q > kv) & (q < ktrust)
+        for l in range(Nl):
+            for lp in range(Nl):
+                L, Lp = 2 * l, 2 * lp
+                wq = np.zeros_like(q)
+                if lp <= l:
+                    x = q[ir] / kv
+                    f = x * W2D[ir] * (x**L if L == Lp else (2.0 * L + 1.0) / 2.0 * H(max(L, Lp), min(L, Lp), x))
+                    wq[ir] += q[ir] * dq[ir] * f
+                if lp >= l:
+                    x = kv / q[uv]
+                    f = W2D[uv] * (x**L if L == Lp else (2.0 * L + 1.0) / 2.0 * H(max(L, Lp), min(L, Lp), x))
+                    wq[uv] += q[uv] * dq[uv] * f
+                F[l, i, lp, :] = -0.5 * fs * Dfc**2 * (wq @ S)
+    return F
+
+
 def chained_matrix(Nl):
     """Q_l = P_l - A_l P_{l+2} (chained.py:13-54)."""
     from scipy.special import eval_legendre
@@ -386,6 +427,7 @@ class TracerPlan:
     ap_fid: tuple | None = None  # (DA_fid, H_fid)
     ap_st: bool = False
     project: np.ndarray | None = None  # (Nout, Nl*Nk)
+    project_stoch: np.ndarray | None = None  # (Nout, Nl*Nk): operator of the stochastic terms when it differs
     project_st: bool = True  # apply the projection to the stochastic terms
     picc_out: np.ndarray | None = None  # (Nout,)
     out_shape: tuple | None = None  # (Nl_out, nk_out)
@@ -421,34 +463,60 @@ def build_tracer_plan(Nl=3, kmax=0.3, NFFT=256, with_NNLO=False, kin=None, windo
         plan.out_shape = tuple(projection["shape"])
         plan.kout = projection.get("kout")
         plan.project_st = bool(projection.get("st", True))
+        if projection.get("matrix_st") is not None:
+            plan.project_stoch = np.ascontiguousarray(projection["matrix_st"], dtype=float)
     return plan
 
 
-def compose_projection(g: GridConfig, window=None, icc=None, binning=None, chained=False, window_st=True):
-    """Compose window (+ICC), binning and chained mixing into one matrix on the Nl*Nk nodes.
+def compose_projection(g: GridConfig, window=None, icc=None, binning=None, chained=False, window_st=True, fiber=None,
+                       fiber_st=False):
+    """Compose window (+ICC), fibre collisions, binning and chained mixing into one matrix on the Nl*Nk nodes, in the
+    reference's order (theory.py:582-604).
 
     window : None or (Na, Nk, Nl, Nk) effective matrix (`window_effective_matrix`)
     icc    : None or dict(matrix=(Na,Nk,Nl,Nk), PSN_times_Pshot=(Na,Nk))    (window.py:393-405)
+    fiber  : None or (Nl, Nk, Nl, Nk) matrix F of `fiber_matrix`: P <- P + F.P  (pybird.py:1760-1806; not Picc)
     binning: None or (nbin, Nk) matrix (`binning_matrix`)
-    Returns dict(matrix=(Nout, Nl*Nk), picc=(Nout,), shape=(Nl_out, nk_out), st=window_st).
-    The stochastic terms see the same operator when `window_st` (reference default); the case
-    window_st=False with a window is handled by the caller building a second plan."""
+    Returns dict(matrix=(Nout, Nl*Nk), picc=(Nout,), shape=(Nl_out, nk_out), st=True, matrix_st=None or (Nout, Nl*Nk)).
+    `matrix_st` is the operator of the stochastic terms when it differs from `matrix`: the window leaves them alone
+    with window_st=False (window.py:401-403), the fibre correction unless fiberst (pybird.py:1798-1806)."""
     Nl, Nk = g.Nl, g.Nk
-    op = np.eye(Nl * Nk).reshape(Nl, Nk, Nl, Nk)
+    eye = np.eye(Nl * Nk).reshape(Nl, Nk, Nl, Nk)
+    op, op_st = eye, eye
     picc = np.zeros((Nl, Nk))
     if window is not None:
         op = np.array(window, dtype=float)
         if icc is not None:
             op = op - icc["matrix"]
             picc = picc - icc["PSN_times_Pshot"]
+        if window_st:
+            op_st = op
+        elif op.shape != eye.shape:
+            raise ValueError("window_st=False needs a window that preserves the node grid")
+    if fiber is not None:
+        if op.shape[0] != Nl:
+            raise ValueError("fibre-collision correction needs Na == Nl window output")
+        add = eye + np.asarray(fiber, float)
+        op = np.einsum("akbm,bmln->akln", add, op)
+        if fiber_st:
+            op_st = np.einsum("akbm,bmln->akln", add, op_st)
+    differs = op_st is not op and not np.array_equal(op_st, op)
     Na = op.shape[0]
+
+    def finish(o):
+        if binning is not None:
+            o = np.einsum("bk,akln->abln", binning, o)
+        if chained:
+            o = np.einsum("ca,akln->ckln", chained_matrix(Na), o)
+        return o
+
+    op = finish(op)
     if binning is not None:
-        op = np.einsum("bk,akln->abln", binning, op)
         picc = picc @ binning.T
     if chained:
-        cm = chained_matrix(Na)
-        op = np.einsum("ca,akln->ckln", cm, op)
-        picc = cm @ picc
+        picc = chained_matrix(Na) @ picc
     shape = op.shape[:2]
-    return dict(matrix=op.reshape(shape[0] * shape[1], Nl * Nk), picc=picc.reshape(-1), shape=shape,
-                st=window_st)
+    out = dict(matrix=op.reshape(shape[0] * shape[1], Nl * Nk), picc=picc.reshape(-1), shape=shape, st=True, matrix_st=None)
+    if differs:
+        out["matrix_st"] = finish(op_st).reshape(shape[0] * shape[1], Nl * Nk)
+    return out

@@ -349,6 +349,31 @@ class APeffect:
 
 
 # --------------------------------------------------------------------------------------------------
+class FiberCollision:
+    """pybird.py:1631-1809 - effective-window fibre-collision correction, same keywords.  `fibcolWindow(bird)` adds
+    the correlated correction dPcorr to P11l, Pctl, Ploopl[, PctNNLOl] and, with `fiberst`, to Pstl (not to Picc);
+    dPcorr is linear in the spectrum, so it is one fixed operator (plan.fiber_matrix) applied on the DMMA GEMM."""
+
+    def __init__(self, fs, Dfc, ktrust=0.25, fiberst=False, co=None, name="pybird.fiber", snapshot=False):
+        self.co = common if co is None else co
+        self.fs, self.Dfc, self.ktrust, self.fiberst = fs, Dfc, ktrust, fiberst
+        self.name, self.snapshot = name, snapshot
+        self._matrix = None
+
+    def matrix(self):
+        """(Nl, Nk, Nl, Nk) operator F with dPcorr = F.P"""
+        if self._matrix is None:
+            self._matrix = P.fiber_matrix(self.co.k, self.co.Nl, self.fs, self.Dfc, self.ktrust)
+        return self._matrix
+
+    def fibcolWindow(self, bird):
+        n = self.co.Nl * self.co.Nk
+        op = np.eye(n) + self.matrix().reshape(n, n)
+        apply_node_operator(bird, op, self.co.Nl, stochastic=self.fiberst, cache_owner=self)
+        if self.snapshot:
+            bird.create_snapshot("fiber")
+
+
 class NodeOperator:
     """A fixed matrix on the (multipole, k-node) axis applied to every term row of a batch
     (`eftb_operator_*`): window, integral constraint, binning, chained mixing."""

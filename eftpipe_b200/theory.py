@@ -17,11 +17,11 @@ from .engine import DevicePlan
 from .icc import IntegralConstraint
 from .marginal import LoggedError
 from .parambasis import find_param_basis
-from .pybird import APeffect, Common, DAfunc, Hubble
+from .pybird import APeffect, Common, DAfunc, FiberCollision, Hubble
 from .window import Window
 
 _KNOWN = {"prefix", "z", "nd", "km", "kr", "cross", "provider", "use_cb", "with_IRresum", "with_APeffect",
-          "with_window", "with_fiber", "with_NNLO", "with_RSD", "kmax", "IRresum", "APeffect", "window", "icc",
+          "with_window", "with_fiber", "with_NNLO", "with_RSD", "kmax", "IRresum", "APeffect", "window", "icc", "fiber",
           "binning", "basis", "chained", "ls", "Nl"}
 
 
@@ -44,8 +44,6 @@ class EFTLSS:
             unknown = set(cfg) - _KNOWN
             if unknown:
                 raise LoggedError(f"tracer {name}: unknown configuration keys {sorted(unknown)}")
-            if cfg.get("with_fiber"):
-                raise NotImplementedError("fibre-collision correction is not part of this build (SURVEY 8f #1)")
         self.cache_dir_path = cache_dir_path
         self.requirements = {}
         self.bases, self.commons, self.plans, self.info = {}, {}, {}, {}
@@ -112,6 +110,9 @@ class EFTLSS:
                 if cfg.get("icc"):
                     icc = IntegralConstraint(co=co, **cfg["icc"])
                 window = Window(co=co, icc=icc, **wc)
+            fiber = None
+            if cfg.get("with_fiber"):  # theory.py:378-385, :482-485
+                fiber = FiberCollision(co=co, **dict(cfg.get("fiber") or {}))
             binm = None
             keff = co.k
             if req["binned"]:
@@ -119,11 +120,12 @@ class EFTLSS:
                 binm, keff = bo.matrix, bo.keff
             g = P.GridConfig(Nl=Nl, kmax=cfg.get("kmax", 0.3), with_NNLO=co.with_NNLO)
             proj = None
-            if window is not None or binm is not None or req["chained"]:
+            if window is not None or binm is not None or req["chained"] or fiber is not None:
                 proj = P.compose_projection(
                     g, window=None if window is None else window_matrix(window),
                     icc=None if icc is None else dict(matrix=icc.effective_matrix(), PSN_times_Pshot=icc.PSN),
-                    binning=binm, chained=req["chained"], window_st=True if window is None else window.window_st)
+                    binning=binm, chained=req["chained"], window_st=True if window is None else window.window_st,
+                    fiber=None if fiber is None else fiber.matrix(), fiber_st=False if fiber is None else fiber.fiberst)
                 proj["kout"] = keff
             rs = cfg.get("IRresum") or {}
             host = P.build_tracer_plan(Nl=Nl, kmax=cfg.get("kmax", 0.3), with_NNLO=co.with_NNLO,

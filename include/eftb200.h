@@ -82,6 +82,8 @@ typedef struct {
   const double* mu;         /* [nmu] */
   const double* wl;         /* [Nl][nmu]  2*trapz weight*(2l+1)/2*L_l(mu) */
   const double* project;    /* [nout][Nl*Nk] */
+  const double* project_st; /* [nout][Nl*Nk] or NULL: operator of the stochastic terms (21..23) when it differs from
+                               `project` (window_st=False window.py:401-403, fiberst=False pybird.py:1798-1806) */
 } eftb_constants;
 
 /* ---- library ----------------------------------------------------------------------------------- */

@@ -442,6 +442,58 @@ class APeffect:
 
 
 # --------------------------------------------------------------------------------------
+# fibre collisions (pybird.py:44-85, :1631-1809), effective-window method
+# --------------------------------------------------------------------------------------
+def _w2d(x):
+    from scipy.special import j1
+
+    return 2.0 * j1(x) / x  # pybird.py:44-46
+
+
+def _hllp(l, lp, x):
+    """pybird.py:49-65"""
+    if (l, lp) == (2, 0):
+        return x**2 - 1.0
+    if (l, lp) == (4, 0):
+        return 1.75 * x**4 - 2.5 * x**2 + 0.75
+    if (l, lp) == (4, 2):
+        return x**4 - x**2
+    return x * 0.0
+
+
+def fiber_dPcorr(co: Common, PS, fs, Dfc, ktrust=0.25):
+    """FiberCollision.dPcorr(co.k, co.k, PS) (pybird.py:1703-1756); PS: (Nl, nrow, Nk)."""
+    k = co.k
+    q = np.geomspace(k.min(), ktrust, num=1024)
+    dq = np.concatenate([[0.0], q[1:] - q[:-1]])
+    PSq = interp1d(k, PS, axis=-1, bounds_error=False, fill_value="extrapolate")(q)
+    out = np.zeros(PS.shape)
+    for l in range(co.Nl):
+        for lp in range(co.Nl):
+            L, Lp = 2 * l, 2 * lp
+            for i, kv in enumerate(k):
+                if lp <= l:  # IR: q < k  (pybird.py:68-75)
+                    m = q < kv
+                    x = q[m] / kv
+                    f = x * _w2d(q[m] * Dfc) * (x**L if L == Lp else (2.0 * L + 1.0) / 2.0 * _hllp(max(L, Lp), min(L, Lp), x))
+                    out[l, :, i] += -0.5 * fs * Dfc**2 * (PSq[lp][:, m] @ (q[m] * dq[m] * f))
+                if lp >= l:  # UV: k < q < ktrust  (pybird.py:78-85)
+                    m = (q > kv) & (q < ktrust)
+                    x = kv / q[m]
+                    f = _w2d(q[m] * Dfc) * (x**L if L == Lp else (2.0 * L + 1.0) / 2.0 * _hllp(max(L, Lp), min(L, Lp), x))
+                    out[l, :, i] += -0.5 * fs * Dfc**2 * (PSq[lp][:, m] @ (q[m] * dq[m] * f))
+    return out
+
+
+def fibcol_window(bird: Bird, fs, Dfc, ktrust=0.25, fiberst=False):
+    """FiberCollision.fibcolWindow (pybird.py:1760-1806)"""
+    names = ["P11l", "Pctl", "Ploopl"] + (["PctNNLOl"] if bird.co.with_NNLO else []) + (["Pstl"] if fiberst else [])
+    for name in names:
+        P = getattr(bird, name)
+        setattr(bird, name, P + fiber_dPcorr(bird.co, P, fs, Dfc, ktrust))
+
+
+# --------------------------------------------------------------------------------------
 # window / integral constraint apply step, binning, chained
 # --------------------------------------------------------------------------------------
 def window_pgrid(kmax=0.3, accboost=1):

@@ -38,3 +38,8 @@ def golden_nl2():
 @pytest.fixture(scope="session")
 def fftlog_kat():
     return dict(np.load(os.path.join(GOLDEN, "fftlog_kat.npz")))
+
+
+@pytest.fixture(scope="session")
+def fiber_kat():
+    return dict(np.load(os.path.join(GOLDEN, "fiber_kat.npz")))

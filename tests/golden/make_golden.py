@@ -314,6 +314,19 @@ def main():
         g2[key] = np.array(vals)
     np.savez_compressed(os.path.join(HERE, "nl2_resum.npz"), **g2)
 
+    # ---- fibre collisions: reference FiberCollision.dPcorr / fibcolWindow on random term arrays (eastcoast mock yaml
+    # values tests/yamls/mock_eBOSS_LRG_ELG_NGC_all_like.yaml:30-39)
+    fkw = dict(fs=0.6, Dfc=0.43 / 0.6777, ktrust=0.25)
+    co_r3, co_o3 = pb.Common(Nl=3), orc.Common(Nl=3)
+    fc = pb.FiberCollision(co=co_r3, **fkw)
+    rng = np.random.default_rng(20261018)
+    PS = rng.normal(size=(3, 4, co_r3.Nk)) * np.array([1e4, 1e3, 1e2])[:, None, None]
+    d_ref = fc.dPcorr(co_r3.k, co_r3.k, PS, **fkw)
+    d_orc = orc.fiber_dPcorr(co_o3, PS, **fkw)
+    worst = max(worst, relerr(d_orc, d_ref))
+    print("fibre dPcorr: oracle vs reference %.2e" % relerr(d_orc, d_ref))
+    np.savez_compressed(os.path.join(HERE, "fiber_kat.npz"), meta=meta(), fiber=json.dumps(fkw), PS=PS, dPcorr=d_ref)
+
     print("worst oracle-vs-reference error: %.3e   (%.0fs)" % (worst, time.time() - t0))
     assert worst < 1e-9, "oracle does not reproduce the reference"
 
