@@ -22,6 +22,7 @@ namespace {
 struct ApArgs {
   const double *coef, *Tin, *DA, *H, *k, *knot_lo, *basis, *mu, *wl;
   double *Tout, *G;
+  double* mutab;    // [nb][nmu][AP_TAB]: sqrt(root) and w_l(mu) L_l'(mu') of every (cosmology, mu) node
   int2* meta;       // per (b, k): first B-spline index of the window, window length
   int b0, nb;       // this launch handles cosmologies [b0, b0 + nb)
   int Bp, Nk, nterm, nmu, nint, ap_st, wcap;
@@ -44,17 +45,44 @@ __device__ __forceinline__ double rsqrt_newton(double x) {
 constexpr int GEOM_THREADS = 128;
 constexpr int APPLY_THREADS = 256;
 
+// Everything of the resampling geometry that depends on (cosmology, mu) only - NOT on the k node:
+//   k'(k, mu) = (k / q_perp) * sqrt(root),  root = 1 + mu^2 (F^-2 - 1)                 (pybird.py:1608)
+//   mu'^2 = mu^2 F^-2 / root  ->  even Legendre L_l'(mu'), times the quadrature weight w_l(mu)   (pybird.py:1609, :1595)
+// one thread per (cosmology, mu node); AP_TAB doubles per node: sqrt(root), then w_l L_l' for (l, l').
+constexpr int AP_TAB = 10;
+
 template <int NL>
-__global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
+__global__ void __launch_bounds__(128) ap_mu_kernel(ApArgs a) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= a.nb * a.nmu) return;
+  const int bl = gid / a.nmu, t = gid - bl * a.nmu, b = a.b0 + bl;
+  const double qperp = a.DA[b] / a.da_fid, qpar = a.h_fid / a.H[b];  // pybird.py:1560-1561
+  const double Fap = qpar / qperp;
+  const double invF2 = 1.0 / (Fap * Fap);
+  const double m = a.mu[t], m2 = m * m;
+  const double root = fma(m2, invF2 - 1.0, 1.0);
+  const double rs = rsqrt_newton(root);
+  const double mp2 = m2 * invF2 * (rs * rs);
+  double L[3];
+  L[0] = 1.0;
+  L[1] = 0.5 * (3.0 * mp2 - 1.0);
+  L[2] = (35.0 * mp2 * mp2 - 30.0 * mp2 + 3.0) * 0.125;
+  double* out = a.mutab + (size_t)gid * AP_TAB;
+  out[0] = root * rs;
+#pragma unroll
+  for (int l = 0; l < NL; ++l)
+#pragma unroll
+    for (int lp = 0; lp < NL; ++lp) out[1 + l * NL + lp] = a.wl[l * a.nmu + t] * L[lp];
+}
+
+template <int NL>
+__global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
   constexpr int NQ = NL * NL;
+  static_assert(1 + NL * NL <= AP_TAB, "mu table too narrow");
   extern __shared__ __align__(16) double sm[];
-  double* mu2s = sm;                       // [nmu]  mu^2
-  double* wls = mu2s + a.nmu;              // [NL][nmu]
-  double* knots = wls + (size_t)NL * a.nmu;  // [nint]
+  double* knots = sm;                      // [nint]
   double* bas = knots + a.nint;            // [nint][4][4]
   const int tid = threadIdx.x;
-  for (int i = tid; i < a.nmu; i += GEOM_THREADS) { const double m = a.mu[i]; mu2s[i] = m * m; }
-  for (int i = tid; i < NL * a.nmu; i += GEOM_THREADS) wls[i] = a.wl[i];
   for (int i = tid; i < a.nint; i += GEOM_THREADS) knots[i] = a.knot_lo[i];
   for (int i = tid; i < a.nint * 16; i += GEOM_THREADS) bas[i] = a.basis[i];
   __syncthreads();
@@ -62,11 +90,10 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
   if (gid >= a.nb * a.Nk) return;
   const int bl = gid / a.Nk, ik = gid - bl * a.Nk, b = a.b0 + bl;
 
-  const double qperp = a.DA[b] / a.da_fid, qpar = a.h_fid / a.H[b];  // pybird.py:1560-1561
-  const double Fap = qpar / qperp;
-  const double invF2 = 1.0 / (Fap * Fap);
-  const double iF2m1 = invF2 - 1.0;
+  const double qperp = a.DA[b] / a.da_fid;  // pybird.py:1560
   const double kq = a.k[ik] / qperp;
+  // this cosmology's mu table; the lanes of a warp are consecutive k of (mostly) one cosmology: broadcast loads
+  const double* tab = a.mutab + (size_t)bl * a.nmu * AP_TAB;
 
   auto locate = [&](double x) {  // largest j with knots[j] <= x, clamped (end polynomials extrapolate)
     int lo = 0, hi = a.nint - 1;
@@ -76,9 +103,8 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
     }
     return lo;
   };
-  auto kprime = [&](int t) { const double root = fma(mu2s[t], iF2m1, 1.0); return kq * (root * rsqrt_newton(root)); };
-  const int jfirst = locate(kprime(0));
-  const int jlast = locate(kprime(a.nmu - 1));
+  const int jfirst = locate(kq * tab[0]);
+  const int jlast = locate(kq * tab[(size_t)(a.nmu - 1) * AP_TAB]);
   const int jlo = min(jfirst, jlast), jhi = max(jfirst, jlast);
   const int wn = jhi - jlo + 4;
   double* Grow = a.G + ((size_t)bl * a.Nk + ik) * NQ * a.wcap;
@@ -99,16 +125,17 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
   for (int i = 0; i < 16; ++i) bc[i] = bas[j * 16 + i];
   double knot = knots[j];
 
-  // geometry of one mu node: k' (pybird.py:1608) and mu'^2 (pybird.py:1609); one reciprocal square root serves both
-  auto geom = [&](int t, double& kp, double& mp2) {
-    const double m2 = mu2s[t];
-    const double root = fma(m2, iF2m1, 1.0);
-    const double rs = rsqrt_newton(root);
-    kp = kq * (root * rs);
-    mp2 = m2 * invF2 * (rs * rs);
-  };
-  // move the live window to the interval of k' (rare), then the 4 B-spline values and the even Legendre polynomials
-  auto locate_and_basis = [&](double kp, double mp2, double (&bv)[4], double (&L)[3]) {
+  for (int t = 0; t < a.nmu; ++t) {
+    // 80 bytes per node, 16-byte aligned: sqrt(root) | w_l L_l'
+    const double2* row = reinterpret_cast<const double2*>(tab + (size_t)t * AP_TAB);
+    double wL[AP_TAB];
+#pragma unroll
+    for (int i = 0; i < AP_TAB / 2; ++i) {
+      const double2 v = __ldg(row + i);
+      wL[2 * i] = v.x;
+      wL[2 * i + 1] = v.y;
+    }
+    const double kp = kq * wL[0];
     while (up && j < jhi && kp >= knots[j + 1]) {
       double* g = Grow + (j - jlo);          // B-spline j has no support beyond this knot: retire its column
 #pragma unroll
@@ -134,31 +161,13 @@ __global__ void __launch_bounds__(GEOM_THREADS) ap_geom_kernel(ApArgs a) {
       knot = knots[j];
     }
     const double x = kp - knot;
+    double bv[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) bv[r] = fma(fma(fma(bc[r * 4 + 3], x, bc[r * 4 + 2]), x, bc[r * 4 + 1]), x, bc[r * 4]);
-    L[0] = 1.0;
-    L[1] = 0.5 * (3.0 * mp2 - 1.0);
-    L[2] = (35.0 * mp2 * mp2 - 30.0 * mp2 + 3.0) * 0.125;
-  };
-  // software pipeline: the square-root chain of node t+1 is issued next to the 45 independent multiply-adds of
-  // node t, so the two overlap inside one warp (there are only ~3 warps per scheduler to hide latency with)
-  double kp, mp2, bv[4], L[3];
-  geom(0, kp, mp2);
-  locate_and_basis(kp, mp2, bv, L);
-  for (int t = 0; t < a.nmu; ++t) {
-    const bool more = t + 1 < a.nmu;
-    if (more) geom(t + 1, kp, mp2);
 #pragma unroll
-    for (int l = 0; l < NL; ++l) {
-      const double w = wls[l * a.nmu + t];
+    for (int q = 0; q < NQ; ++q)
 #pragma unroll
-      for (int lp = 0; lp < NL; ++lp) {
-        const double wL = w * L[lp];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) acc[l * NL + lp][r] = fma(wL, bv[r], acc[l * NL + lp][r]);
-      }
-    }
-    if (more) locate_and_basis(kp, mp2, bv, L);
+      for (int r = 0; r < 4; ++r) acc[q][r] = fma(wL[1 + q], bv[r], acc[q][r]);
   }
   double* g = Grow + (j - jlo);
 #pragma unroll
@@ -259,7 +268,7 @@ int ap_chunk(const eftb_config& c, int B) {
 
 template <int NL>
 int run(ApArgs a, int B, cudaStream_t s) {
-  const size_t smem_g = sizeof(double) * ((size_t)(1 + NL) * a.nmu + a.nint + (size_t)a.nint * 16);
+  const size_t smem_g = sizeof(double) * (a.nint + (size_t)a.nint * 16);
   const size_t smem_a = sizeof(double) * ((size_t)NL * a.Nk * a.nterm + (size_t)2 * (APPLY_THREADS / (NL * a.nterm)) * NL * NL * APPLY_WS) +
                         sizeof(int2) * a.Nk;
   if (NL * a.nterm > APPLY_THREADS || smem_g > 200 * 1024 || smem_a > 200 * 1024) {
@@ -280,6 +289,8 @@ int run(ApArgs a, int B, cudaStream_t s) {
     a.b0 = b0;
     a.nb = B - b0 < chunk ? B - b0 : chunk;
     const int nthreads = a.nb * a.Nk;
+    ap_mu_kernel<NL><<<(a.nb * a.nmu + 127) / 128, 128, 0, s>>>(a);
+    EFTB_LAUNCH_CHECK();
     ap_geom_kernel<NL><<<(nthreads + GEOM_THREADS - 1) / GEOM_THREADS, GEOM_THREADS, smem_g, s>>>(a);
     EFTB_LAUNCH_CHECK();
     ap_apply_kernel<NL><<<a.nb, APPLY_THREADS, smem_a, s>>>(a);
@@ -293,7 +304,7 @@ int run(ApArgs a, int B, cudaStream_t s) {
 size_t ap_scratch_doubles(const eftb_plan* p, int B) {
   const eftb_config& c = p->cfg;
   const size_t chunk = ap_chunk(c, B);
-  return chunk * c.Nk * c.Nl * c.Nl * c.Nk + chunk * c.Nk;  // G | meta (int2 = 8 bytes each)
+  return chunk * c.Nk * c.Nl * c.Nl * c.Nk + chunk * c.Nk + 1 + chunk * c.nmu * AP_TAB;  // G | meta (int2 = 8 bytes) | pad | mu table
 }
 
 int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const double* Tin, const double* DA, const double* H,
@@ -307,6 +318,10 @@ int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const doubl
   a.b0 = 0;
   a.G = scratch;
   a.meta = reinterpret_cast<int2*>(scratch + (size_t)a.nb * c.Nk * c.Nl * c.Nl * c.Nk);
+  {
+    size_t off = (size_t)a.nb * c.Nk * c.Nl * c.Nl * c.Nk + (size_t)a.nb * c.Nk;
+    a.mutab = scratch + off + (off & 1);  // 16-byte aligned rows (scratch itself is 16-byte aligned)
+  }
   if (c.Nl == 3) return run<3>(a, B, s);
   if (c.Nl == 2) return run<2>(a, B, s);
   eftb_set_error("ap: unsupported Nl=%d", c.Nl);
