@@ -28,6 +28,7 @@ class EftbConfig(C.Structure):
         + [(n, C.c_int32) for n in ("has_ap", "nmu", "nint", "ap_st")]
         + [(n, C.c_double) for n in ("da_fid", "h_fid")]
         + [(n, C.c_int32) for n in ("has_project", "nout", "nl_out")]
+        + [(n, C.c_int32) for n in ("row_cre_cf", "row_cim_cf")]
     )
 
 
@@ -70,8 +71,10 @@ SIGNATURES = {
     "eftb_to_point_major": (C.c_int, [_VP, _I, _I, _VP, _VP, _VP]),
     "eftb_front": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP]),
     "eftb_antidiag": (C.c_int, [_VP, _I, _VP, _VP, _VP]),
-    "eftb_spectral": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP]),
-    "eftb_spectral_grouped": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "eftb_antidiag_cf": (C.c_int, [_VP, _I, _VP, _VP, _VP]),
+    "eftb_has_cf_set": (C.c_int, [_VP]),
+    "eftb_spectral": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP]),
+    "eftb_spectral_grouped": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "eftb_group": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "eftb_resum": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "eftb_resum_scratch_bytes": (C.c_size_t, [_VP, _I]),

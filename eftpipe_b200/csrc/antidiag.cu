@@ -274,7 +274,7 @@ static int get_schedule(AntidiagPack* P, int Nmax, int nbins, AdSchedule* out) {
   return EFTB_OK;
 }
 
-int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cudaStream_t s) {
+int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cudaStream_t s, bool cf_set) {
   const eftb_config& c = p->cfg;
   AntidiagPack* P = p->ad;
   if (!P) { eftb_set_error("antidiag: plan has no pair table"); return EFTB_ERR_ARG; }
@@ -301,8 +301,9 @@ int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cuda
   int rc = get_schedule(P, c.Nmax, ctas_per_group * AD_WARPS, &sc);
   if (rc) return rc;
   AdArgs a;
-  a.cre = F + (size_t)c.row_cre * Bp;
-  a.cim = F + (size_t)c.row_cim * Bp;
+  const bool second = cf_set && c.row_cre_cf >= 0;  // pybird.py:1151-1160: coef_cf differs from coef_pk
+  a.cre = F + (size_t)(second ? c.row_cre_cf : c.row_cre) * Bp;
+  a.cim = F + (size_t)(second ? c.row_cim_cf : c.row_cim) * Bp;
   a.tab = P->tab; a.descs = sc.descs; a.bin_off = sc.bin_off; a.D = D; a.Nmax = c.Nmax; a.Bp = Bp;
   dim3 grid(ngroups, ctas_per_group);
   antidiag_kernel<<<grid, AD_WARPS * 32, smem, s>>>(a);

@@ -25,7 +25,7 @@ int upload(T** dst, const T* src, size_t n) {
 }
 
 struct Sizes {
-  size_t u, F, D, P22, Dg, T, Cr, scal, out, ap, rs;
+  size_t u, F, D, P22, Dg, T, Cr, scal, out, ap, rs, Dcf;
 };
 
 Sizes sizes(const eftb_plan* p, int Bp) {
@@ -42,6 +42,7 @@ Sizes sizes(const eftb_plan* p, int Bp) {
   z.out = c.has_project ? (size_t)c.nout * c.nterm * Bp : 0;
   z.ap = c.has_ap ? ap_scratch_doubles(p, Bp) : 0;
   z.rs = c.has_resum ? resum_scratch_doubles(p, Bp) : 0;
+  z.Dcf = c.row_cre_cf >= 0 ? z.D : 0;
   return z;
 }
 
@@ -103,6 +104,10 @@ int eftb_plan_create(const eftb_config* cfg, const eftb_constants* h, eftb_plan*
     return EFTB_ERR_ARG;
   }
   if (c.nterm != 24 + (c.with_nnlo ? 3 : 0)) { eftb_set_error("eftb_plan_create: nterm inconsistent with with_nnlo"); return EFTB_ERR_ARG; }
+  if ((c.row_cre_cf >= 0) != (c.row_cim_cf >= 0) || c.row_cre_cf + c.Nmax / 2 + 1 > c.front_rows || c.row_cim_cf + c.Nmax / 2 + 1 > c.front_rows) {
+    eftb_set_error("eftb_plan_create: inconsistent rows of the second coefficient set");
+    return EFTB_ERR_ARG;
+  }
   eftb_plan* p = new eftb_plan();
   p->cfg = c;
   p->K = c.nin + c.ntail + c.ntailx;
@@ -169,7 +174,7 @@ size_t eftb_workspace_bytes(const eftb_plan* p, int B) {
   Sizes z = sizes(p, eftb_padded_batch(B));
   // u | F | D (later reused for the spline coefficients and the AP output) | P22 | Dg | T | Cr | f,DA,H | out | AP operator
   size_t dreg = z.D > 2 * z.T ? z.D : 2 * z.T;
-  return (z.u + z.F + dreg + z.P22 + z.Dg + z.T + z.Cr + z.scal + z.out + z.ap + z.rs) * sizeof(double);
+  return (z.u + z.F + dreg + z.P22 + z.Dg + z.T + z.Cr + z.scal + z.out + z.ap + z.rs + z.Dcf) * sizeof(double);
 }
 
 int eftb_to_batch_minor(const double* in, int B, int R, double* out, void* stream) {
@@ -202,26 +207,35 @@ int eftb_antidiag(const eftb_plan* p, int B, const double* F, double* D, void* s
   return launch_antidiag(p, eftb_padded_batch(B), F, D, (cudaStream_t)stream);
 }
 
-int eftb_spectral(const eftb_plan* p, int B, const double* D, double* P22, double* Cs, void* stream) {
+int eftb_antidiag_cf(const eftb_plan* p, int B, const double* F, double* D, void* stream) {
+  EFTB_NEED(p && F && D && B >= 1, "NULL/invalid argument");
+  return launch_antidiag(p, eftb_padded_batch(B), F, D, (cudaStream_t)stream, true);
+}
+
+int eftb_has_cf_set(const eftb_plan* p) { return p && p->cfg.row_cre_cf >= 0; }
+
+int eftb_spectral(const eftb_plan* p, int B, const double* D, const double* Dcf, double* P22, double* Cs, void* stream) {
   EFTB_NEED(p && D && P22 && Cs && B >= 1, "NULL/invalid argument");
+  if (!Dcf) Dcf = D;
   cudaStream_t s = (cudaStream_t)stream;
   const eftb_config& c = p->cfg;
   const int Bp = eftb_padded_batch(B);
   const size_t dch = (size_t)(c.Nmax + 1) * 2 * Bp;
   int rc = gemm_run(p->Ak, D, P22, Bp, EFTB_N22, EFTB_N22, dch, 0, (size_t)c.Nk * Bp, 0, s);
   if (rc) return rc;
-  return gemm_run(p->As, D, Cs, Bp, c.Nl * EFTB_NCH, EFTB_NCH, dch, 0, (size_t)c.Ns * Bp, (size_t)EFTB_NCH * c.Ns * Bp, s);
+  return gemm_run(p->As, Dcf, Cs, Bp, c.Nl * EFTB_NCH, EFTB_NCH, dch, 0, (size_t)c.Ns * Bp, (size_t)EFTB_NCH * c.Ns * Bp, s);
 }
 
-int eftb_spectral_grouped(const eftb_plan* p, int B, const double* D, const double* f, double* Dg, double* P22, double* Cr,
-                          void* stream) {
+int eftb_spectral_grouped(const eftb_plan* p, int B, const double* D, const double* Dcf, const double* f, double* Dg, double* P22,
+                          double* Cr, void* stream) {
   EFTB_NEED(p && D && f && Dg && P22 && Cr && B >= 1, "NULL/invalid argument");
+  if (!Dcf) Dcf = D;
   cudaStream_t s = (cudaStream_t)stream;
   const eftb_config& c = p->cfg;
   const int Bp = eftb_padded_batch(B);
   const size_t dch = (size_t)(c.Nmax + 1) * 2 * Bp;
   const int ncr = 14 + (c.with_nnlo ? 1 : 0);
-  int rc = launch_regroup(p, Bp, D, f, Dg, s);
+  int rc = launch_regroup(p, Bp, Dcf, f, Dg, s);
   if (rc) return rc;
   if ((rc = gemm_run(p->Ak, D, P22, Bp, EFTB_N22, EFTB_N22, dch, 0, (size_t)c.Nk * Bp, 0, s))) return rc;
   // Cloopl[l][r] = As[l] @ Dg[l][r], written straight into rows 2..13 of the point-major Cr[b][l][ncr][Ns]
@@ -309,6 +323,7 @@ int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double*
   double* Cr = w;           w += z.Cr;
   double* scal = w;         w += z.scal;
   double* out = w;
+  double* Dcf = z.Dcf ? out + z.out + z.ap + z.rs : nullptr;
   int rc;
   if ((rc = eftb_front(p, B, plin, u, F, stream))) return rc;
   if ((rc = launch_to_batch_minor(f, B, Bp, 1, scal, s))) return rc;
@@ -317,7 +332,8 @@ int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double*
     if ((rc = launch_to_batch_minor(H, B, Bp, 1, scal + 2 * (size_t)Bp, s))) return rc;
   }
   if ((rc = launch_antidiag(p, Bp, F, D, s))) return rc;
-  if ((rc = eftb_spectral_grouped(p, B, D, scal, Dg, P22, Cr, stream))) return rc;
+  if (Dcf && (rc = launch_antidiag(p, Bp, F, Dcf, s, true))) return rc;
+  if ((rc = eftb_spectral_grouped(p, B, D, Dcf, scal, Dg, P22, Cr, stream))) return rc;
   if ((rc = launch_group(p, Bp, F, P22, nullptr, scal, T, Cr, s))) return rc;
   if (c.has_resum && (rc = launch_resum(p, B, Bp, F, Cr, scal, T, out + z.out + z.ap, s))) return rc;
   double* cur = T;

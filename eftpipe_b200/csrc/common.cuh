@@ -76,7 +76,7 @@ int resum_pack(eftb_plan* p, const double* R, const double* q);
 int antidiag_pack(eftb_plan* p, const double* pair_table, const int32_t* offsets);
 void antidiag_free(eftb_plan* p);
 int launch_front_prepare(const eftb_plan* p, int B, int Bp, const double* plin, double* u, cudaStream_t s);
-int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cudaStream_t s);
+int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cudaStream_t s, bool cf_set = false);
 int launch_group(const eftb_plan* p, int Bp, const double* F, const double* P22, const double* Cs,
                  const double* f, double* T, double* Cr, cudaStream_t s);  // Cs == NULL: Cloopl rows of Cr already filled
 int launch_regroup(const eftb_plan* p, int Bp, const double* D, const double* f, double* Dg, cudaStream_t s);

@@ -57,6 +57,7 @@ class DevicePlan:
         cfg.row_c11, cfg.row_cct = rows["C11"][0], rows["Cct"][0]
         cfg.row_cctnnlo = rows["CctNNLO"][0] if g.with_NNLO else -1
         cfg.row_x, cfg.row_y = rows["X"][0], rows["Y"][0]
+        cfg.row_cre_cf, cfg.row_cim_cf = (rows["cre_cf"][0], rows["cim_cf"][0]) if "cre_cf" in rows else (-1, -1)
         aux = plan.front_aux
         cfg.inv_dlog, cfg.wx_last, cfg.wx_prev = aux["inv_dlog"], aux["wX_last"], aux["wX_prev"]
         cfg.npair = plan.pair_table.shape[0]
@@ -147,26 +148,32 @@ class DevicePlan:
         _lib.check(self.lib.eftb_front(self.handle, B, _p(plin), _p(u), _p(F), _stream_ptr(self.torch)), "eftb_front")
         return F
 
-    def antidiag(self, F, B):
+    @property
+    def has_cf_set(self):
+        """IRcutoff "loop" / "resum": the configuration-space terms use their own FFTLog coefficients"""
+        return self.cfg.row_cre_cf >= 0
+
+    def antidiag(self, F, B, cf_set=False):
         D = self._empty(NCH, self.cfg.Nmax + 1, 2, self.padded(B))
-        _lib.check(self.lib.eftb_antidiag(self.handle, B, _p(F), _p(D), _stream_ptr(self.torch)), "eftb_antidiag")
+        fn = self.lib.eftb_antidiag_cf if cf_set else self.lib.eftb_antidiag
+        _lib.check(fn(self.handle, B, _p(F), _p(D), _stream_ptr(self.torch)), "eftb_antidiag")
         return D
 
-    def spectral(self, D, B):
+    def spectral(self, D, B, Dcf=None):
         Bp = self.padded(B)
         P22 = self._empty(N22, self.cfg.Nk, Bp)
         Cs = self._empty(self.cfg.Nl, NCH, self.cfg.Ns, Bp)
-        _lib.check(self.lib.eftb_spectral(self.handle, B, _p(D), _p(P22), _p(Cs), _stream_ptr(self.torch)), "eftb_spectral")
+        _lib.check(self.lib.eftb_spectral(self.handle, B, _p(D), _p(Dcf), _p(P22), _p(Cs), _stream_ptr(self.torch)), "eftb_spectral")
         return P22, Cs
 
-    def spectral_grouped(self, D, f_bm, B):
+    def spectral_grouped(self, D, f_bm, B, Dcf=None):
         """fused-path variant of `spectral`: returns (P22, Cr) with the Cloopl rows of Cr already filled"""
         Bp = self.padded(B)
         c = self.cfg
         P22 = self._empty(N22, c.Nk, Bp)
         Dg = self._empty(c.Nl, 12, c.Nmax + 1, 2, Bp)
         Cr = self._empty(Bp, c.Nl, 14 + c.with_nnlo, c.Ns)  # point-major
-        _lib.check(self.lib.eftb_spectral_grouped(self.handle, B, _p(D), _p(f_bm), _p(Dg), _p(P22), _p(Cr),
+        _lib.check(self.lib.eftb_spectral_grouped(self.handle, B, _p(D), _p(Dcf), _p(f_bm), _p(Dg), _p(P22), _p(Cr),
                                                   _stream_ptr(self.torch)), "eftb_spectral_grouped")
         return P22, Cr
 

@@ -53,13 +53,34 @@ class GridConfig:
     kmax: float = 0.3
     NFFT: int = 256
     with_NNLO: bool = False
+    optiresum: bool = False
     k: np.ndarray = field(init=False)
     s: np.ndarray = field(init=False)
 
     def __post_init__(self):
         self.k = tables.kbird(self.kmax)
-        self.s = tables.sbird()
-        self.Nk, self.Ns = self.k.size, self.s.size
+        # `s`: the grid the reference evaluates correlation functions on (co.s); `sr`: the grid the resummation
+        # integrates over; `E` (len(sr), len(s)): the linear map C(s) -> resummation input.  Full resummation: sr = s,
+        # E = identity (None).  optiresum (pybird.py:553-554, :1235-1244, :1382-1400): s = arange(70, 200, 2.5),
+        # sr = the BAO range (70, 190], E = restriction minus the broadband that interpolates s^2 C linearly between
+        # the points outside that range.  The device only ever holds E.C, so its `Ns` is len(sr).
+        if self.optiresum:
+            self.s = np.arange(70.0, 200.0, 2.5)
+            idlow, idhigh = np.where(self.s > 70.0)[0][0], np.where(self.s > 190.0)[0][0]
+            self.sr = self.s[idlow:idhigh]
+            out = np.concatenate([np.arange(idlow), np.arange(idhigh, self.s.size)])
+            snobao = self.s[out]
+            from scipy.interpolate import interp1d
+
+            broadband = interp1d(snobao, np.eye(snobao.size), kind="linear", axis=0)(self.sr)  # (Nsr, Nout)
+            E = np.zeros((self.sr.size, self.s.size))
+            E[np.arange(self.sr.size), idlow + np.arange(self.sr.size)] = 1.0
+            E[:, out] -= broadband * snobao[None, :] ** 2 * self.sr[:, None] ** -2
+            self.E = E
+        else:
+            self.s = tables.sbird()
+            self.sr, self.E = self.s, None
+        self.Nk, self.Ns, self.Ns_full = self.k.size, self.sr.size, self.s.size
         self.kr = self.k[0.02 <= self.k]
         self.Nkr = self.kr.size
         self.Nklow = self.Nk - self.Nkr
@@ -69,6 +90,10 @@ class GridConfig:
         self.l22 = tables.legendre_weights(self.Nl, tables.MU22)
         self.l13 = tables.legendre_weights(self.Nl, tables.MU13)
         self.nterm = N11 + NCT + NLOOP + NST + (NNNLO if self.with_NNLO else 0)
+
+    def to_sr(self, mat):
+        """apply E along axis -2 of an operator whose rows are indexed by s: (..., Ns_full, K) -> (..., Ns, K)"""
+        return mat if self.E is None else np.einsum("rs,...sk->...rk", self.E, mat)
 
 
 # --------------------------------------------------------------------------------------------
@@ -127,12 +152,12 @@ def spectral_matrices(fft: FFTLog, g: GridConfig):
     Ak[:, 1::2] = (-herm[:, None] * Ek.imag).T.astype(float)
     Ml = tables.bessel_power(2 * np.arange(g.Nl)[:, None], (-0.5 * eta2 - 1.5)[None, :])
     Es = _phase_ld(-eta2 - 6.0, np.log(g.s.astype(np.longdouble)))
-    As = np.empty((g.Nl, g.Ns, 2 * (Nmax + 1)))
+    As = np.empty((g.Nl, g.Ns_full, 2 * (Nmax + 1)))
     for l in range(g.Nl):
         G = Ml[l].astype(np.clongdouble)[:, None] * Es
         As[l][:, 0::2] = (herm[:, None] * G.real).T.astype(float)
         As[l][:, 1::2] = (-herm[:, None] * G.imag).T.astype(float)
-    return Ak, As
+    return Ak, np.ascontiguousarray(g.to_sr(As))
 
 
 # --------------------------------------------------------------------------------------------
@@ -154,26 +179,50 @@ class FrontLayout:
         return max(a + b for a, b in self.rows.values())
 
 
-def front_operator(kin, g: GridConfig, fft: FFTLog, M13, window=0.2):
+def _coef_operator(fft: FFTLog, kin, window, cut_index=0):
+    """(Nmax+1, nin) complex matrix of `FFTLog.Coef` on the samples kin[cut_index:] with a zero-padded low side
+    (NonLinear.Coef with IRcut, pybird.py:1137-1141); cut_index = 0 is the default two-sided "extrap" call, whose
+    low tail never triggers because kin[0] lies below the FFTLog grid (checked)."""
+    if cut_index == 0:
+        if fft.has_low_tail(kin):
+            raise NotImplementedError("input k-grid must start below the FFTLog xmin (reference default)")
+        return fft.operator(kin, window=window)
+    L = np.zeros((fft.Nmax + 1, kin.size), dtype=complex)
+    L[:, cut_index:] = fft.operator(kin[cut_index:], window=window)
+    return L
+
+
+def front_operator(kin, g: GridConfig, fft: FFTLog, M13, window=0.2, lambda_ir=LAMBDA_IR, ircutoff=False, kIR=None):
     """Real matrix Wf (M, K) and layout.  Input vector u = [P_lin(kin) | tail | tailX] with
       tail_i  = P_last exp(n lr_i),  n  from the last two samples of P_lin           (fftlog.py:146-151)
       tailX_i = fX_last exp(nX lrx_i), fX = P_lin exp(-k^2/Lambda^2)/k^2            (pybird.py:1321-1325)
     Output rows: Re c_n, Im c_n (n = 0..Nmax/2), P11(k), Re sum_n c_n k^{eta_n} M13[b,n], C11, Cct
-    [, CctNNLO], X(s), Y(s)."""
+    [, CctNNLO], X(s), Y(s).
+
+    ircutoff in {False, "all", "loop", "resum"} (pybird.py:1151-1160, :1320-1334): the k-space loops, the
+    configuration-space terms and the IR filters each use either the full P_lin or the samples at k >= kIR with a
+    zero-padded low side.  When the two coefficient sets differ, the configuration-space one is emitted as extra
+    rows "cre_cf"/"cim_cf" and the anti-diagonal stage runs once per set."""
     kin = np.asarray(kin, float)
-    if fft.has_low_tail(kin):
-        raise NotImplementedError("input k-grid must start below the FFTLog xmin (reference default)")
+    if ircutoff is True:
+        ircutoff = "all"
+    if ircutoff not in (False, "all", "loop", "resum"):
+        raise ValueError(f"unexpected IRcutoff option: {ircutoff}")
+    if ircutoff and kIR is None:
+        raise ValueError("kIR must be specified when doing IRcutoff")
+    icut = int(np.searchsorted(kin, kIR)) if ircutoff else 0
+    cut_pk = icut if ircutoff in ("all", "loop") else 0
+    cut_cf = icut if ircutoff in ("all", "resum") else 0
+    cut_x = icut if ircutoff in ("all", "resum") else 0
     Nmax, Nh = fft.Nmax, fft.Nmax // 2
-    L = fft.operator(kin, window=window)  # (N, nin)
     Lt, lr = fft.tail_operator(kin, window=window)
-    Lc = np.concatenate([L, Lt], axis=1)  # c = Lc @ [P | tail]
+    Lc = np.concatenate([_coef_operator(fft, kin, window, cut_pk), Lt], axis=1)  # c = Lc @ [P | tail]
+    Lc_cf = Lc if cut_cf == cut_pk else np.concatenate([_coef_operator(fft, kin, window, cut_cf), Lt], axis=1)
     nin, ntail = kin.size, lr.size
 
     xf = FFTLog(Nmax=32, xmin=1.5e-5, xmax=10.0, bias=-2.6)  # pybird.py:1293
-    if xf.has_low_tail(kin):
-        raise NotImplementedError
-    wX = np.exp(-(kin**2) / LAMBDA_IR**2) / kin**2
-    LX = xf.operator(kin, window=None) * wX[None, :]
+    wX = np.exp(-(kin**2) / lambda_ir**2) / kin**2
+    LX = _coef_operator(xf, kin, None, cut_x) * wX[None, :]
     LXt, lrx = xf.tail_operator(kin, window=None)
     ntailx = lrx.size
     K = nin + ntail + ntailx
@@ -198,6 +247,7 @@ def front_operator(kin, g: GridConfig, fft: FFTLog, M13, window=0.2):
         cursor += mat.shape[0]
 
     Cfull = embed(Lc)
+    Cfull_cf = Cfull if Lc_cf is Lc else embed(Lc_cf)
     add("cre", Cfull[: Nh + 1].real)
     add("cim", Cfull[: Nh + 1].imag)
     add("P11", embed(np.concatenate([cubic_matrix(kin, g.k), np.zeros((g.Nk, ntail))], axis=1)).real)
@@ -209,23 +259,26 @@ def front_operator(kin, g: GridConfig, fft: FFTLog, M13, window=0.2):
     G13 = (M13[:, None, :] * kPow.T[None, :, :]).reshape(N13 * g.Nk, -1)
     add("P13raw", (G13 @ Cfull).real)
     Mcf11 = tables.bessel_power(ell[:, None], nu[None, :])  # pybird.py:1029
-    add("C11", ((Mcf11[:, None, :] * sPow.T[None]).reshape(g.Nl * g.Ns, -1) @ Cfull).real)
+    # configuration-space rows live on the resummation grid: E applied to the reference's C(s) (identity unless optiresum)
+    on_sr = lambda G: g.to_sr((G.reshape(g.Nl * g.Ns_full, -1) @ Cfull_cf).real.reshape(g.Nl, g.Ns_full, -1))
+    add("C11", on_sr(Mcf11[:, None, :] * sPow.T[None]))
     Mcfct = tables.bessel_power(ell[:, None], nu[None, :] - 1.0)  # pybird.py:1052
-    Gct = (Mcfct[:, None, :] * sPow.T[None]) * (g.s**-2)[None, :, None]  # pybird.py:1092-1096
-    add("Cct", (Gct.reshape(g.Nl * g.Ns, -1) @ Cfull).real)
+    add("Cct", on_sr((Mcfct[:, None, :] * sPow.T[None]) * (g.s**-2)[None, :, None]))  # pybird.py:1092-1096
     if g.with_NNLO:
         Mn = tables.bessel_power(ell[:, None], nu[None, :] - 2.0)  # pybird.py:1056
-        Gn = (Mn[:, None, :] * sPow.T[None]) * (g.s**-4)[None, :, None]
-        add("CctNNLO", (Gn.reshape(g.Nl * g.Ns, -1) @ Cfull).real)
-    # IR filters (pybird.py:1316-1353): X = 2/3 (X0off - X0 - X2), Y = 2 X2
+        add("CctNNLO", on_sr((Mn[:, None, :] * sPow.T[None]) * (g.s**-4)[None, :, None]))
+    # IR filters (pybird.py:1316-1353) on the resummation grid: X = 2/3 (X0off - X0 - X2), Y = 2 X2
     CX = embed(mat_x=np.concatenate([LX, LXt], axis=1))
     XM = np.array([tables.bessel_power(2 * l, -0.5 * xf.Pow) for l in range(2)])
-    XsPow = np.exp(np.outer(-xf.Pow - 3.0, np.log(g.s)))
+    XsPow = np.exp(np.outer(-xf.Pow - 3.0, np.log(g.sr)))
     X02 = (XM[:, None, :] * XsPow.T[None]) @ CX  # (2, Ns, K) complex
     off = (XM[0] @ CX)[None, :]
     X0 = off - X02[0]
     add("X", (2.0 / 3.0 * (X0 - X02[1])).real)
     add("Y", (2.0 * X02[1]).real)
+    if Cfull_cf is not Cfull:
+        add("cre_cf", Cfull_cf[: Nh + 1].real)
+        add("cim_cf", Cfull_cf[: Nh + 1].imag)
     Wf = np.concatenate(blocks, axis=0)
     layout = FrontLayout(nin=nin, ntail=ntail, ntailx=ntailx, rows=rows)
     aux = dict(lr=lr, lrx=lrx, wX_last=wX[-1], wX_prev=wX[-2],
@@ -244,7 +297,7 @@ def resum_operator(g: GridConfig, NFFT=192):
     NIR = 16 if Nl == 3 else 8  # pybird.py:1247-1258
     Na = 3 if NIR == 16 else 2
     fft = FFTLog(Nmax=NFFT, xmin=0.1, xmax=10000.0, bias=-0.6)
-    L = fft.operator(g.s, window=None)  # (N, Ns)
+    L = fft.operator(g.sr, window=None)  # (N, Ns)
     M = np.array([8.0 * np.pi**3 * tables.bessel_power(2 * l, -0.5 * fft.Pow) for l in range(Na)])
     kPow = np.exp(np.outer(-fft.Pow - 3.0, np.log(g.kr)))
     R = np.real(np.einsum("vn,nk,ns->vks", M, kPow, L))
@@ -439,14 +492,16 @@ class TracerPlan:
 
 
 def build_tracer_plan(Nl=3, kmax=0.3, NFFT=256, with_NNLO=False, kin=None, window=0.2,
-                      with_resum=True, resum_NFFT=192, ap=None, projection=None, loop_cache=None):
+                      with_resum=True, resum_NFFT=192, ap=None, projection=None, loop_cache=None,
+                      optiresum=False, lambda_ir=LAMBDA_IR, ircutoff=False, kIR=None):
     """ap: None or dict(DA=, H=, nbinsmu=200, accboost=1, APst=False);
-    projection: None or dict(matrix=(Nout, Nl*Nk), picc=(Nout,), shape=(Nl_out, nk_out), kout=, st=True)."""
-    g = GridConfig(Nl=Nl, kmax=kmax, NFFT=NFFT, with_NNLO=with_NNLO)
+    projection: None or dict(matrix=(Nout, Nl*Nk), picc=(Nout,), shape=(Nl_out, nk_out), kout=, st=True);
+    optiresum / lambda_ir / ircutoff / kIR: `Common(optiresum=, IRcutoff=, kIR=)`, `Resum(LambdaIR=)`."""
+    g = GridConfig(Nl=Nl, kmax=kmax, NFFT=NFFT, with_NNLO=with_NNLO, optiresum=optiresum)
     kin = np.logspace(-5, 0, 200) if kin is None else np.asarray(kin, float)
     fft = FFTLog(Nmax=NFFT, xmin=1.5e-5, xmax=1000.0, bias=-1.6)  # pybird.py:919
     M22, M13 = loop_cache if loop_cache is not None else loop_matrices(fft)
-    Wf, layout, aux = front_operator(kin, g, fft, M13, window=window)
+    Wf, layout, aux = front_operator(kin, g, fft, M13, window=window, lambda_ir=lambda_ir, ircutoff=ircutoff, kIR=kIR)
     table, offsets = antidiagonal_table(M22, M13)
     Ak, As = spectral_matrices(fft, g)
     plan = TracerPlan(grid=g, kin=kin, Wf=Wf, front=layout, front_aux=aux, pair_table=table,

@@ -9,7 +9,10 @@ names, stage order and error behaviour, so that `theory.py:557-609`-style driver
 
 Differences, all additive: a leading batch axis (B cosmologies per call), arrays are torch float64 CUDA
 tensors, and the arithmetic runs in libeftb200's sm_100a kernels through the C ABI - there is no CPU
-path.  Unsupported reference options raise NotImplementedError at construction (optiresum, IRcutoff).
+path.  `optiresum`, `IRcutoff`/`kIR` and `LambdaIR` are plan constants: they change the fixed operators the
+plan builder composes (eftpipe_b200/plan.py), not the kernels.  With `optiresum` the configuration-space
+arrays (`C11`, `Cct`, `C22`, `C13`, `Cloopl`) hold the extracted BAO peak on `co.sr` (what `Resum.extractBAO`,
+pybird.py:1382-1400, feeds the resummation) instead of the raw correlation function on `co.s`.
 """
 from __future__ import annotations
 
@@ -41,13 +44,13 @@ class Common:
 
     def __init__(self, Nl=None, No=None, kmax=0.3, optiresum=False, kmA=0.7, krA=0.25, ndA=3e-4, kmB=None, krB=None,
                  ndB=None, counterform="westcoast", with_NNLO=False, kIR=None, IRcutoff=False):
-        if optiresum:
-            raise NotImplementedError("optiresum=True is outside the B200 hot path (default full resummation only)")
         if IRcutoff and kIR is None:
             raise ValueError("kIR must be specified when doing IRcutoff")
-        if IRcutoff:
-            raise NotImplementedError("IRcutoff is outside the B200 hot path")
-        self.optiresum, self.IRcutoff, self.kIR = optiresum, IRcutoff, kIR
+        if IRcutoff is True:  # pybird.py:530-531
+            IRcutoff = "all"
+        if IRcutoff not in (False, "all", "loop", "resum"):
+            raise ValueError(f"unexpected IRcutoff option: {IRcutoff}")  # pybird.py:1160 raises at the first PsCf
+        self.optiresum, self.IRcutoff, self.kIR = bool(optiresum), IRcutoff, kIR
         self.kmA, self.krA, self.ndA = kmA, krA, ndA
         self.kmB = kmA if kmB is None else kmB
         self.krB = krA if krB is None else krB
@@ -63,9 +66,10 @@ class Common:
             raise ValueError("No should always be smaller than Nl")
         self.N11, self.Nct, self.NctNNLO, self.N22, self.N13, self.Nloop = 3, 6, 3, 28, 10, 12
         self.kmax = kmax
-        g = P.GridConfig(Nl=self.Nl, kmax=kmax, with_NNLO=with_NNLO)
-        self.k, self.s, self.kr = g.k, g.s, g.kr
-        self.Nk, self.Ns, self.Nkr, self.Nklow = g.Nk, g.Ns, g.Nkr, g.Nklow
+        g = P.GridConfig(Nl=self.Nl, kmax=kmax, with_NNLO=with_NNLO, optiresum=self.optiresum)
+        self.k, self.s, self.sr, self.kr = g.k, g.s, g.sr, g.kr  # sr: the resummation grid (= s unless optiresum)
+        self.Nk, self.Ns, self.Nkr, self.Nklow = g.Nk, g.Ns_full, g.Nkr, g.Nklow
+        self.Nsr = g.Ns
         self.l11, self.lct, self.lctNNLO, self.l22, self.l13 = g.l11, g.lct, g.lctNNLO, g.l22, g.l13
         self.nterm = g.nterm
         # stage registry -> one device plan per Common (built lazily, rebuilt when a stage is added)
@@ -89,7 +93,8 @@ class Common:
                 Nl=self.Nl, kmax=self.kmax, NFFT=nl.NFFT, with_NNLO=self.with_NNLO, kin=nl.kin, window=nl.window,
                 with_resum=rs is not None, resum_NFFT=rs.NFFT if rs is not None else 192,
                 ap=None if ap is None else dict(DA=ap.DA, H=ap.H, nbinsmu=ap._nbinsmu, accboost=ap._accboost, APst=ap.APst),
-                loop_cache=nl._loop_cache)
+                loop_cache=nl._loop_cache, optiresum=self.optiresum, ircutoff=self.IRcutoff, kIR=self.kIR,
+                lambda_ir=rs.LambdaIR if rs is not None else P.LAMBDA_IR)
             self._device = (self._version, DevicePlan(host))
         return self._device[1]
 
@@ -212,11 +217,11 @@ class Bird(_TermsView):
 
     @property
     def C11(self):
-        return self._out(self._rows("C11").reshape(self.co.Nl, self.co.Ns, self.B).permute(2, 0, 1))
+        return self._out(self._rows("C11").reshape(self.co.Nl, self.co.Nsr, self.B).permute(2, 0, 1))
 
     @property
     def Cct(self):
-        return self._out(self._rows("Cct").reshape(self.co.Nl, self.co.Ns, self.B).permute(2, 0, 1))
+        return self._out(self._rows("Cct").reshape(self.co.Nl, self.co.Nsr, self.B).permute(2, 0, 1))
 
     @property
     def C22(self):
@@ -283,16 +288,17 @@ class NonLinear:
         dp = bird.co.device_plan()
         F = bird._front()
         bird._D = dp.antidiag(F, bird.B)
-        bird._P22, bird._Cs = dp.spectral(bird._D, bird.B)
+        # IRcutoff "loop"/"resum": coef_cf differs from coef_pk (pybird.py:1151-1160) -> a second anti-diagonal pass
+        bird._Dcf = dp.antidiag(F, bird.B, cf_set=True) if dp.has_cf_set else None
+        bird._P22, bird._Cs = dp.spectral(bird._D, bird.B, bird._Dcf)
 
 
 class Resum:
-    """pybird.py:1174-1464 (full resummation)."""
+    """pybird.py:1174-1464: full resummation, or the BAO-peak-only "optiresum" variant when `co.optiresum`."""
 
     def __init__(self, LambdaIR=0.2, NFFT=192, co=common, name="pybird.IRresum", snapshot=False):
-        if LambdaIR != P.LAMBDA_IR:
-            raise NotImplementedError("LambdaIR is fixed to the reference default 0.2 in this build")
-        self.co, self.LambdaIR, self.NFFT, self.snapshot = co, LambdaIR, NFFT, snapshot
+        self.co, self.LambdaIR, self.NFFT, self.snapshot = co, float(LambdaIR), NFFT, snapshot
+        self.sr = co.sr
         self.NIR = 16 if co.Nl == 3 else 8
         self.Na = 3 if self.NIR == 16 else 2
         self.Nn = 2 * self.NIR * self.Na

@@ -22,7 +22,7 @@ from .window import Window
 
 _KNOWN = {"prefix", "z", "nd", "km", "kr", "cross", "provider", "use_cb", "with_IRresum", "with_APeffect",
           "with_window", "with_fiber", "with_NNLO", "with_RSD", "kmax", "IRresum", "APeffect", "window", "icc", "fiber",
-          "binning", "basis", "chained", "ls", "Nl"}
+          "binning", "basis", "chained", "ls", "Nl", "optiresum", "IRcutoff", "kIR"}
 
 
 def _merge(default, cfg):
@@ -96,7 +96,9 @@ class EFTLSS:
             cross_prefix = [self.tracers[t]["prefix"] for t in cross] if isinstance(cross, (list, tuple)) else []
             basis = basis_cls(prefix=cfg.get("prefix", ""), cross_prefix=cross_prefix)
             co = Common(Nl=Nl, No=No, kmax=cfg.get("kmax", 0.3), kmA=kmA, krA=krA, ndA=ndA, kmB=kmB, krB=krB, ndB=ndB,
-                        counterform=basis.counterform(), with_NNLO=bool(cfg.get("with_NNLO", False)))
+                        counterform=basis.counterform(), with_NNLO=bool(cfg.get("with_NNLO", False)),
+                        optiresum=bool(cfg.get("optiresum", False)), IRcutoff=cfg.get("IRcutoff", False),
+                        kIR=cfg.get("kIR"))  # theory.py:421-437
             ap = None
             if cfg.get("with_APeffect"):
                 apc = dict(cfg.get("APeffect") or {})
@@ -118,7 +120,7 @@ class EFTLSS:
             if req["binned"]:
                 bo = Binning(co=co, **(req["binning"] or cfg.get("binning") or {}))
                 binm, keff = bo.matrix, bo.keff
-            g = P.GridConfig(Nl=Nl, kmax=cfg.get("kmax", 0.3), with_NNLO=co.with_NNLO)
+            g = P.GridConfig(Nl=Nl, kmax=cfg.get("kmax", 0.3), with_NNLO=co.with_NNLO, optiresum=co.optiresum)
             proj = None
             if window is not None or binm is not None or req["chained"] or fiber is not None:
                 proj = P.compose_projection(
@@ -130,7 +132,8 @@ class EFTLSS:
             rs = cfg.get("IRresum") or {}
             host = P.build_tracer_plan(Nl=Nl, kmax=cfg.get("kmax", 0.3), with_NNLO=co.with_NNLO,
                                        with_resum=bool(cfg.get("with_IRresum", True)), resum_NFFT=rs.get("NFFT", 192),
-                                       ap=ap, projection=proj)
+                                       ap=ap, projection=proj, optiresum=co.optiresum, ircutoff=co.IRcutoff, kIR=co.kIR,
+                                       lambda_ir=rs.get("LambdaIR", P.LAMBDA_IR))
             self.bases[name], self.commons[name] = basis, co
             self.plans[name] = DevicePlan(host)
             nl_out, nk = host.out_shape if proj is not None else (Nl, g.Nk)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EFTB_ABI_VERSION 1
+#define EFTB_ABI_VERSION 2
 
 typedef enum {
   EFTB_OK = 0,
@@ -57,6 +57,9 @@ typedef struct {
   /* window (+ICC) / binning / chained projection (window.py:371-415, icc.py:471-484,
      binning.py:131-162, chained.py:32-68) */
   int32_t has_project, nout, nl_out; /* nout = nl_out * nk_out */
+  /* IRcutoff "loop" / "resum" (pybird.py:1151-1160): the configuration-space terms use a second set of FFTLog
+     coefficients, emitted by the front operator at these rows; row_cre_cf < 0: one set serves both */
+  int32_t row_cre_cf, row_cim_cf;
 } eftb_config;
 
 typedef struct {
@@ -110,21 +113,28 @@ int eftb_to_point_major(const double* in, int B, int R, const int32_t* perm, dou
  * F    [front_rows][Bp]           front-end products: c_n (Hermitian half), P11, 13-loop, C11, Cct, X, Y
  * D    [38][Nmax+1][2][Bp]        anti-diagonal sums of c_n c_m M_ch[n,m]
  * P22  [28][Nk][Bp]               bird.P22          (pybird.py:1074-1078)
- * Cs   [Nl][38][Ns][Bp]           bird.C22 (ch<28), bird.C13 (ch>=28), before Legendre weights
+ * Cs   [Nl][38][Ns][Bp]           bird.C22 (ch<28), bird.C13 (ch>=28), before Legendre weights.  Ns counts the points
+ *                                 of the resummation grid: with optiresum every configuration-space array is the
+ *                                 extracted BAO peak (Resum.extractBAO, pybird.py:1382-1400) of the reference's
  * T    [Nl][Nk][nterm][Bp]        term index: 0-2 P11l, 3-8 Pctl, 9-20 Ploopl, 21-23 Pstl, 24-26 PctNNLOl
  * Cr   [Bp][Nl][ncr][Ns]          POINT-major; rows: C11, Cct, Cloopl x12 [, CctNNLO]; ncr = 14 + with_nnlo
  */
 /* Bird.__init__ interpolation + FFTLog.Coef + IRFilters + makeP13/C11/Cct (pybird.py:694-695,
    :1127-1141, :1080-1101, :1316-1353; fftlog.py:84-166).  plin: point-major [B][nin]. */
 int eftb_front(const eftb_plan*, int B, const double* plin, double* u_scratch, double* F, void* stream);
-/* the quadratic part of makeP22 / makeC22 / makeC13 (pybird.py:1074-1078, :1103-1125) */
+/* the quadratic part of makeP22 / makeC22 / makeC13 (pybird.py:1074-1078, :1103-1125).  eftb_antidiag uses the
+   k-space coefficient set (coef_pk, pybird.py:1162), eftb_antidiag_cf the configuration-space one (coef_cf, :1163);
+   they coincide unless the plan was built with IRcutoff "loop" or "resum" (eftb_has_cf_set) */
 int eftb_antidiag(const eftb_plan*, int B, const double* F, double* D, void* stream);
-int eftb_spectral(const eftb_plan*, int B, const double* D, double* P22, double* Cs, void* stream);
+int eftb_antidiag_cf(const eftb_plan*, int B, const double* F, double* D, void* stream);
+int eftb_has_cf_set(const eftb_plan*);
+/* D -> P22(k), Dcf -> C22/C13(s); Dcf == NULL: D serves both */
+int eftb_spectral(const eftb_plan*, int B, const double* D, const double* Dcf, double* P22, double* Cs, void* stream);
 /* fused-path variant: the Legendre weighting + f-power grouping of the configuration-space loop terms
    (reducePsCfl, pybird.py:805-846) is applied to D first (Dg_scratch: [Nl][12][Nmax+1][2][Bp]), so the
    D -> C(s) transform runs on Nl*12 channels and writes Cloopl straight into rows 2..13 of Cr; f: [Bp] */
-int eftb_spectral_grouped(const eftb_plan*, int B, const double* D, const double* f, double* Dg_scratch,
-                          double* P22, double* Cr, void* stream);
+int eftb_spectral_grouped(const eftb_plan*, int B, const double* D, const double* Dcf, const double* f,
+                          double* Dg_scratch, double* P22, double* Cr, void* stream);
 /* Bird.setPsCfl / reducePsCfl / setPstl / subtractShotNoise (pybird.py:737-866); f: [Bp].
    Cs == NULL: the Cloopl rows of Cr were already produced by eftb_spectral_grouped */
 int eftb_group(const eftb_plan*, int B, const double* F, const double* P22, const double* Cs,

@@ -206,8 +206,14 @@ class Common:
     ndB: float | None = None
     counterform: str = "westcoast"
     with_NNLO: bool = False
+    kIR: float | None = None
+    IRcutoff: bool | str = False
 
     def __post_init__(self):
+        if self.IRcutoff and self.kIR is None:  # :528-529
+            raise ValueError("kIR must be specified when doing IRcutoff")
+        if self.IRcutoff is True:  # :530-531
+            self.IRcutoff = "all"
         self.No = self.Nl if self.No is None else self.No
         if self.No > self.Nl:
             raise ValueError("No should always be smaller than Nl")
@@ -268,16 +274,30 @@ class NonLinear:
         self.kPow = np.exp(np.outer(self.grid.Pow, np.log(co.k)))  # :1060
         self.sPow = np.exp(np.outer(-self.grid.Pow - 3.0, np.log(co.s)))  # :1064
 
-    def coef(self, bird: Bird, window=0.2):
-        return fftlog_coef(self.grid, bird.kin, bird.Pin, extrap="extrap", window=window)  # :1127-1141
+    def coef(self, bird: Bird, window=0.2, IRcut=False):
+        """pybird.py:1127-1141: with IRcut the samples below kIR are dropped and the low side is zero padded"""
+        k, Pin, extrap = bird.kin, bird.Pin, ("extrap", "extrap")
+        if IRcut:
+            idx = np.searchsorted(k, self.co.kIR)
+            k, Pin, extrap = k[idx:], Pin[idx:], ("padding", "extrap")
+        return fftlog_coef(self.grid, k, Pin, extrap=extrap, window=window)
 
     def PsCf(self, bird: Bird, window=0.2):
-        """pybird.py:1143-1171 (no IR cutoff)."""
+        """pybird.py:1143-1171"""
         co = self.co
-        c = self.coef(bird, window)
-        bird.coef = c
-        v = c[:, None] * self.kPow  # (N, Nk)
-        u = c[:, None] * self.sPow  # (N, Ns)
+        mode = co.IRcutoff
+        if mode == "all" or mode is False:  # :1151-1160
+            c_cf = c_pk = self.coef(bird, window, IRcut=bool(mode))
+        elif mode == "loop":
+            c_pk, c_cf = self.coef(bird, window, IRcut=True), self.coef(bird, window, IRcut=False)
+        elif mode == "resum":
+            c_pk, c_cf = self.coef(bird, window, IRcut=False), self.coef(bird, window, IRcut=True)
+        else:
+            raise ValueError(f"unexpected IRcutoff option: {mode}")
+        bird.coef, bird.coef_cf = c_pk, c_cf
+        v = c_pk[:, None] * self.kPow  # (N, Nk)
+        u = c_cf[:, None] * self.sPow  # (N, Ns)
+        c = c_pk
         # P22[b,k] = k^3 Re sum_nm v_nk v_mk M22[b,n,m]   (:1074-1078); contraction order of the reference's
         # einsum path: matrix times panel first (one zgemm), then the dot with the second panel
         N = c.size
@@ -327,14 +347,20 @@ def set_PsCfl(bird: Bird):
 
 
 # --------------------------------------------------------------------------------------
-# IR resummation (pybird.py:1174-1464), fullresum only
+# IR resummation (pybird.py:1174-1464): full resummation and the "optiresum" BAO-peak variant
 # --------------------------------------------------------------------------------------
 class Resum:
     def __init__(self, co: Common, LambdaIR=0.2, NFFT=192):
-        if co.optiresum:
-            raise NotImplementedError("oracle restates the default full resummation only")
         self.co = co
         self.LambdaIR = LambdaIR
+        if co.optiresum:  # :1235-1244
+            self.idlow = np.where(co.s > 70.0)[0][0]
+            self.idhigh = np.where(co.s > 190.0)[0][0]
+            self.sbao = co.s[self.idlow : self.idhigh]
+            self.snobao = np.concatenate([co.s[: self.idlow], co.s[self.idhigh :]])
+            self.sr = self.sbao
+        else:
+            self.sr = co.s
         self.NIR = 16 if co.Nl == 3 else 8  # :1247-1250
         self.Na = 3 if self.NIR == 16 else 2
         self.Nn = 2 * self.NIR * self.Na
@@ -345,15 +371,18 @@ class Resum:
         self.kPow = np.exp(np.outer(-self.grid.Pow - 3.0, np.log(co.kr)))  # :1308
         self.xgrid = LogGrid(Nmax=32, xmin=1.5e-5, xmax=10.0, bias=-2.6)  # :1293
         self.XM = np.array([mpc(2 * l, -0.5 * self.xgrid.Pow) for l in range(2)])  # :1310-1314
-        self.XsPow = np.exp(np.outer(-self.xgrid.Pow - 3.0, np.log(co.s)))  # :1304
+        self.XsPow = np.exp(np.outer(-self.xgrid.Pow - 3.0, np.log(self.sr)))  # :1304
         qt = tables()["q_nl3" if self.NIR == 16 else "q_nl2"]
         self.qcoef = qt  # [N-j, l, lp, u, degree]
 
     def filters(self, bird: Bird):
         """IR filters X(s), Y(s) (pybird.py:1316-1353)."""
-        kin = bird.kin
-        c = fftlog_coef(self.xgrid, kin, bird.Pin * np.exp(-(kin**2) / self.LambdaIR**2) / kin**2,
-                        extrap="extrap", window=None)
+        kin, Pin, extrap = bird.kin, bird.Pin, "extrap"
+        if self.co.IRcutoff in ("all", "resum"):  # :1320-1334
+            idx = np.searchsorted(kin, self.co.kIR)
+            kin, Pin, extrap = kin[idx:], Pin[idx:], ("padding", "extrap")
+        c = fftlog_coef(self.xgrid, kin, Pin * np.exp(-(kin**2) / self.LambdaIR**2) / kin**2,
+                        extrap=extrap, window=None)
         X02 = np.real(self.XM @ (c[:, None] * self.XsPow))
         off = np.real(np.sum(c * 1.0 ** (-self.xgrid.Pow - 3.0) * self.XM[0]))
         X02[0] = off - X02[0]
@@ -364,13 +393,23 @@ class Resum:
         fp = f ** np.arange(self.qcoef.shape[-1])
         return (self.qcoef @ fp)[::-1]
 
+    def extract_bao(self, cf):
+        """pybird.py:1382-1400: with optiresum, the BAO peak = cf minus a broadband that interpolates s^2 cf
+        linearly between the points outside (70, 190]"""
+        if not self.co.optiresum:
+            return cf
+        nobao_in = np.concatenate([cf[..., : self.idlow], cf[..., self.idhigh :]], axis=-1)
+        nobao = interp1d(self.snobao, self.snobao**2 * nobao_in, kind="linear", axis=-1)(self.sbao) * self.sbao**-2
+        return cf[..., self.idlow : self.idhigh] - nobao
+
     def _ir(self, XpYp, C):
         """IR[..., u, k] for correlation-function rows C[..., s] (pybird.py:1409-1441)."""
         co = self.co
+        C = self.extract_bao(C)
         lead = C.shape[:-1]
         out = np.zeros(lead + (self.Nn, co.Nk))
         prod = XpYp[(None,) * len(lead)] * C[..., None, :]  # (..., j, s)
-        coef = fftlog_coef(self.grid, co.s, prod, extrap="padding", window=None)
+        coef = fftlog_coef(self.grid, self.sr, prod, extrap="padding", window=None)
         for j in range(2 * self.NIR):
             ir = np.real(np.einsum("vn,...n,nk->...vk", self.M[: self.Na], coef[..., j, :], self.kPow))
             out[..., j * self.Na : (j + 1) * self.Na, co.Nklow :] = self.k2p[j] * ir

@@ -43,3 +43,9 @@ def fftlog_kat():
 @pytest.fixture(scope="session")
 def fiber_kat():
     return dict(np.load(os.path.join(GOLDEN, "fiber_kat.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_opts():
+    """reference outputs for optiresum / IRcutoff / LambdaIR variants (tests/golden/make_golden_options.py)"""
+    return dict(np.load(os.path.join(GOLDEN, "options_resum.npz")))

@@ -50,12 +50,13 @@ def antidiag(pl, cre, cim):
     return D
 
 
-def spectral(pl, D):
-    """GEMMs `Ak @ D_b` and `As[l] @ D_ch`."""
+def spectral(pl, D, Dcf=None):
+    """GEMMs `Ak @ D_b` and `As[l] @ D_ch`; Dcf: anti-diagonal sums of the configuration-space coefficient set
+    when it differs from the k-space one (IRcutoff "loop" / "resum")."""
     B = D.shape[-1]
     Dm = D.reshape(P.NCH, -1, B)
     P22 = np.einsum("kt,btB->bkB", pl.Ak, Dm[: P.N22])
-    Cs = np.einsum("lst,ctB->lcsB", pl.As, Dm)
+    Cs = np.einsum("lst,ctB->lcsB", pl.As, (D if Dcf is None else Dcf).reshape(P.NCH, -1, B))
     return P22, Cs
 
 
@@ -176,7 +177,8 @@ def run_chain(pl, plin, f, DA=None, H=None, upto="project"):
     u = front_inputs(pl, plin)
     F = pl.Wf @ u
     D = antidiag(pl, rows(pl, F, "cre"), rows(pl, F, "cim"))
-    P22, Cs = spectral(pl, D)
+    Dcf = antidiag(pl, rows(pl, F, "cre_cf"), rows(pl, F, "cim_cf")) if "cre_cf" in pl.front.rows else None
+    P22, Cs = spectral(pl, D, Dcf)
     T, Cr = group(pl, F, P22, Cs, f)
     out = dict(F=F, D=D, P22=P22, Cs=Cs, T_pre=T, Cr=Cr)
     if pl.resum is not None:

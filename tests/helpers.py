@@ -27,3 +27,15 @@ def config2_plan(g, with_projection=True, chained=False):
 def split_terms(T):
     """(.., l, i, k) -> dict of the reference's term arrays."""
     return dict(P11l=T[..., 0:3, :], Pctl=T[..., 3:9, :], Ploopl=T[..., 9:21, :], Pstl=T[..., 21:24, :])
+
+
+def option_variants(g):
+    """{name: (Common kwargs, Resum kwargs)} of the options fixture `g` (tests/golden/options_resum.npz)."""
+    return {k: (v["common"], v["resum"]) for k, v in json.loads(str(g["variants"])).items()}
+
+
+def option_plan(common, resum):
+    """host plan of one option variant (Nl=3 unless the variant says otherwise)"""
+    return P.build_tracer_plan(Nl=common.get("Nl", 3), optiresum=common.get("optiresum", False),
+                               ircutoff=common.get("IRcutoff", False), kIR=common.get("kIR"),
+                               lambda_ir=resum.get("LambdaIR", 0.2))

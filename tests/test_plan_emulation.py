@@ -73,3 +73,39 @@ def test_pair_table_counts():
     n = pl.Nmax
     assert pl.pair_offsets[-1] == pl.pair_table.shape[0] == sum(t // 2 + 1 for t in range(n + 1))
     assert pl.pair_table.shape[1] == P.NCH
+
+
+# ---- non-default options of the loop / resummation rows: optiresum, IRcutoff, LambdaIR ----
+VARIANTS = ["optiresum", "optiresum_lambda1", "ircut_all", "ircut_loop", "ircut_resum", "nl2_optiresum_ircut"]
+
+
+@pytest.mark.parametrize("name", VARIANTS)
+def test_option_variants(golden_opts, name):
+    g = golden_opts
+    common, resum = helpers.option_variants(g)[name]
+    pl = helpers.option_plan(common, resum)
+    grid = pl.grid
+    r = E.run_chain(pl, g["plin"], g["f"])
+    B, Nl = g["plin"].shape[0], grid.Nl
+    ref = lambda key: g[f"{name}__{key}"]
+    on_sr = lambda C: C if grid.E is None else np.einsum("rs,...s->...r", grid.E, C)  # the device holds E.C only
+    F = r["F"]
+    c = E.rows(pl, F, "cre") + 1j * E.rows(pl, F, "cim")
+    assert np.abs(c.T - ref("coef")[:, :129]).max() <= 1e-13 * np.abs(ref("coef")).max()
+    assert ("cre_cf" in pl.front.rows) == (common.get("IRcutoff") in ("loop", "resum"))
+    assert rowmax_rel(r["P22"].transpose(2, 0, 1), ref("P22")) <= TOL
+    assert rowmax_rel(E.rows(pl, F, "X").T, ref("X")) <= TOL
+    assert rowmax_rel(E.rows(pl, F, "Y").T, ref("Y")) <= TOL
+    assert rowmax_rel(E.rows(pl, F, "C11").reshape(Nl, grid.Ns, B).transpose(2, 0, 1), on_sr(ref("C11"))) <= TOL
+    assert rowmax_rel(E.rows(pl, F, "Cct").reshape(Nl, grid.Ns, B).transpose(2, 0, 1), on_sr(ref("Cct"))) <= TOL
+    assert rowmax_rel(r["Cr"][:, 2:14].transpose(3, 0, 1, 2), on_sr(ref("pre_Cloopl"))) <= TOL
+    T = helpers.split_terms(r["T_res"].transpose(3, 0, 2, 1))
+    for key in ("P11l", "Pctl", "Ploopl"):
+        assert rowmax_rel(T[key], ref("res_" + key)) <= TOL, key
+
+
+def test_option_errors():
+    with pytest.raises(ValueError):
+        P.build_tracer_plan(Nl=2, ircutoff="all")  # kIR missing (pybird.py:528-529)
+    with pytest.raises(ValueError):
+        P.build_tracer_plan(Nl=2, ircutoff="sometimes", kIR=1e-3)  # pybird.py:1160
