@@ -602,7 +602,10 @@ def stage_profile(dp, like, lib, S, d_plin, d_f, d_DA, d_H, d_cols, terms_bm, B,
         "front": 2.0 * dp.host.Wf.size,
         "antidiag": 2.0 * npair * (4 + 4 * P.NCH),
         "spectral": 2.0 * (28 * g.Nk + g.Nl * 12 * g.Ns + g.Nl * 38) * 2 * (Nmax + 1),
-        "resum": 2.0 * g.Nl * g.Nkr * g.Ns * (2 * dp.host.resum["NIR"] * nslots + 2 * nslots + 14 * g.Nl),
+        # a = 1 half: Horner sweep of the nslots polynomials + slot sums + 13 row dots per (l, l', k, s);
+        # a = 0 half: per slot a (Nkr x Ns)(Ns x NIR) product on the tensor pipe + the Q_0 k^{2(p+1)} fold
+        "resum": 2.0 * (g.Nl * g.Nkr * g.Ns * (dp.host.resum["NIR"] * nslots + nslots + 13 * g.Nl)
+                        + nslots * dp.host.resum["NIR"] * g.Nkr * (g.Ns + 2 * g.Nl)),
         "ap": 2.0 * (g.Nl * g.Nk * g.Nk * g.nterm + g.Nk * dp.host.ap["mu"].size * (4 * g.Nl * g.Nl + g.Nl * g.Nl + 40)
                      + g.Nl * g.Nk * g.nterm * g.Nl * 8),
         "project": 2.0 * dp.host.project.size * g.nterm,

@@ -162,7 +162,7 @@ int eftb_plan_create(const eftb_config* cfg, const eftb_constants* h, eftb_plan*
 void eftb_plan_destroy(eftb_plan* p) {
   if (!p) return;
   void* ptrs[] = {p->k, p->l11, p->lct, p->lctnnlo, p->l22, p->l13, p->lr, p->lrx,
-                  p->rs.Rt, p->rs.qpack, p->kr2, p->knot_lo, p->basis, p->mu, p->wl, p->perm_out};
+                  p->rs.Rt, p->rs.Rk, p->rs.qpack, p->kr2, p->knot_lo, p->basis, p->mu, p->wl, p->perm_out};
   for (void* q : ptrs) if (q) cudaFree(q);
   antidiag_free(p);
   gemm_free(&p->Wf); gemm_free(&p->Ak); gemm_free(&p->As); gemm_free(&p->Cinv); gemm_free(&p->project); gemm_free(&p->project_st);

@@ -52,8 +52,11 @@ struct AntidiagPack;  // fragment-ordered pair table + warp schedules (antidiag.
 // IR-resummation constants in kernel layout (resum.cu resum_pack)
 struct ResumPack {
   double *qpack = nullptr, *Rt = nullptr;  // [qdeg][2][Nl][Nl][NIR][4],  [Na][NsP][Nkr]
-  int NsP = 0, NQ = 0;
+  double* Rk = nullptr;                    // [Na][KPAD][NsP]: k-major copy, rows zero-padded to KPAD (linear-term GEMM)
+  int NsP = 0, NQ = 0, KPAD = 0;
   int nslot[3] = {};  // canonical slots per l': (X, v = l'), (Y, 0), (Y, 1)[, (Y, 2)]
+  int nslots = 0;     // all non-zero (l', kind, v) polynomials, listed as (l', canonical slot) pairs
+  int slot_lp[12] = {}, slot_s[12] = {};
 };
 
 // ---- plan ---------------------------------------------------------------------------------------

@@ -16,7 +16,14 @@
 // s in chunks of 4: 2 x 4 slots x 4 points = 32 independent Horner chains fed by broadcast 16-byte shared
 // loads (1 load per 4 DFMA).  A task count that is not a multiple of 128 (3 x 43 = 129) leaves <= 4 tasks
 // over; each is swept by one warp with the s-chunks spread over its lanes and a shuffle reduction.
-// FP64-FMA bound: ~4.6e6 DFMA per cosmology at Nl=3.
+// FP64-FMA bound: ~2.4e6 DFMA per cosmology at Nl=3 for the a = 1 half.
+//
+// The a = 0 half (linear terms) contracts with ONE row per l' (C11), so there the separable form of the reference
+// itself (pybird.py:1409-1441) is 3x cheaper than the sweep:  z^p = k^{2p} X(s)^p, hence
+//   IR0[l,l',k] = sum_{slot,p} Q_0[l,l',p,slot] k^{2(p+1)} G_slot[k,p],   G_slot[k,p] = sum_s R_v[k,s] W_slot[p,s],
+//   W_(l',X)[p,s] = X^{p+1} C11_l',  W_(l',Y,v)[p,s] = Y X^p C11_l'
+// - per slot a (Nkr x Ns)(Ns x NIR) product with a FIXED left operand: DMMA m8n8k4 with the B fragments built on the
+// fly as base_slot[s] * X(s)^p from two small shared-memory tables (resum_linear_body).
 #include <vector>
 #include "common.cuh"
 
@@ -27,11 +34,17 @@ constexpr int RS_C = 4;      // s points per chunk
 constexpr int RS_SLOTS = 4;  // polynomial slots per l'
 
 struct ResumArgs {
-  const double *F, *Cr, *f, *Rt, *qpack, *kr2, *l11, *lct, *lctnnlo;
+  const double *F, *Cr, *f, *Rt, *Rk, *qpack, *kr2, *l11, *lct, *lctnnlo;
   double *T, *Qf;   // Qf: [B][NQ] expanded Q(f) (scratch)
-  int B, Bp, Nk, Ns, NsP, nterm, ncr, Nkr, Nklow, qdeg, row_x, row_y, NQ;
+  int B, Bp, Nk, Ns, NsP, nterm, ncr, Nkr, Nklow, qdeg, row_x, row_y, NQ, KPAD;
   int nslot[3];     // canonical slots of l': 0 = (X, v = l'), 1 + v = (Y, v); nslot = 1 + number of Y orders used
+  int nslots;       // every non-zero polynomial as (l', canonical slot)
+  signed char slot_lp[12], slot_s[12];
 };
+
+constexpr int RL_MCH = 3;  // m8 tiles (k rows) per warp task of the linear-term GEMM
+
+__host__ __device__ inline int rl_pitch(int NsP) { return NsP + ((4 - NsP % 16) + 16) % 16; }  // = 4 mod 16: conflict-free B fragments
 
 // accumulators of one (l, k) output column: IA = 0 (linear terms, Q_0, contracted with C11) keeps one sum per l';
 // IA = 1 (Q_1) keeps Cct per l', the 12 loop rows and, with NNLO, CctNNLO per l'
@@ -230,11 +243,134 @@ __device__ __forceinline__ void resum_body(const ResumArgs& a) {
   }
 }
 
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// a = 0 half on the tensor pipe: one CTA = one cosmology; a warp task = (slot, chunk of RL_MCH m8-tiles of k) with all
+// NIR/8 n8-tiles of p, K = s in steps of 4.  Fragment layout of mma.m8n8k4.f64: a = A[lane>>2][lane&3],
+// b = B[lane&3][lane>>2], c = C[lane>>2][2(lane&3) + {0,1}].
+template <int NL, int NIR>
+__device__ __forceinline__ void resum_linear_body(const ResumArgs& a) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int NT = NIR / 8;
+  const int NsP = a.NsP, pitch = rl_pitch(NsP), KP = a.KPAD;
+  double* Xpow = sm;                           // [NIR][pitch]   X(s)^p
+  double* base = Xpow + NIR * pitch;           // [2][NL][NsP]   X C11_l' | Y C11_l'
+  double* k2p = base + 2 * NL * NsP;           // [KP][NIR]      k^{2(p+1)}
+  double* part = k2p + KP * NIR;               // [nslots][NL][KP] per-slot partial sums (fixed summation order)
+  double* Qs = part + a.nslots * NL * KP;      // [NL][NL][NIR][4]  Q_0(f)
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t Bp = a.Bp;
+
+  {
+    const double* crb = a.Cr + (size_t)b * NL * a.ncr * a.Ns;  // point-major Cr[b][l][ncr][Ns], row 0 = C11
+    for (int s = tid; s < NsP; s += RS_THREADS) {
+      const bool ok = s < a.Ns;
+      const double x = ok ? a.F[(size_t)(a.row_x + s) * Bp + b] : 0.0;
+      const double y = ok ? a.F[(size_t)(a.row_y + s) * Bp + b] : 0.0;
+      double xp = 1.0;
+#pragma unroll
+      for (int p = 0; p < NIR; ++p) { Xpow[p * pitch + s] = xp; xp *= x; }
+#pragma unroll
+      for (int lp = 0; lp < NL; ++lp) {
+        const double c = ok ? crb[(size_t)lp * a.ncr * a.Ns + s] : 0.0;
+        base[lp * NsP + s] = x * c;
+        base[(NL + lp) * NsP + s] = y * c;
+      }
+    }
+    for (int k = tid; k < KP; k += RS_THREADS) {
+      const double k2 = k < a.Nkr ? a.kr2[k] : 0.0;
+      double kp = k2;
+#pragma unroll
+      for (int p = 0; p < NIR; ++p) { k2p[k * NIR + p] = kp; kp *= k2; }
+    }
+    constexpr int NQH = NL * NL * NIR * RS_SLOTS;
+    const double* qf = a.Qf + (size_t)b * (2 * NQH);  // a = 0 half of the expanded table
+    for (int i = tid; i < NQH; i += RS_THREADS) Qs[i] = qf[i];
+  }
+  __syncthreads();
+
+  const int mchunks = KP / (8 * RL_MCH), ntask = a.nslots * mchunks, nks = NsP / 4;
+  const int r = lane >> 2, c4 = lane & 3;
+  for (int task = warp; task < ntask; task += RS_THREADS / 32) {
+    const int slot = task / mchunks, mh = task - slot * mchunks;
+    const int lp = a.slot_lp[slot], sc = a.slot_s[slot];
+    const int v = sc == 0 ? lp : sc - 1;                       // Bessel order of this slot
+    const double* bb = base + ((sc == 0 ? 0 : NL) + lp) * NsP + c4;
+    const double* xp = Xpow + r * pitch + c4;
+    const double* ap = a.Rk + ((size_t)v * KP + mh * (8 * RL_MCH) + r) * NsP + c4;
+    double acc[RL_MCH][NT][2];
+#pragma unroll
+    for (int i = 0; i < RL_MCH; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 4
+    for (int ks = 0; ks < nks; ++ks) {
+      double af[RL_MCH], bf[NT];
+#pragma unroll
+      for (int i = 0; i < RL_MCH; ++i) af[i] = __ldg(ap + (size_t)i * 8 * NsP + 4 * ks);
+      const double bs = bb[4 * ks];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) bf[j] = bs * xp[j * 8 * pitch + 4 * ks];
+#pragma unroll
+      for (int i = 0; i < RL_MCH; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    // fold Q_0[l,l',p,slot] k^{2(p+1)} over this lane's p columns, then over the 4 lanes of the row
+#pragma unroll
+    for (int i = 0; i < RL_MCH; ++i) {
+      const int k = (mh * RL_MCH + i) * 8 + r;
+      double w[NT][2];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const double2 kk = *reinterpret_cast<const double2*>(k2p + k * NIR + j * 8 + 2 * c4);
+        w[j][0] = kk.x * acc[i][j][0];
+        w[j][1] = kk.y * acc[i][j][1];
+      }
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        const double* q = Qs + (size_t)((l * NL + lp) * NIR) * RS_SLOTS + sc;
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const int p = j * 8 + 2 * c4;
+          sum = fma(q[p * RS_SLOTS], w[j][0], sum);
+          sum = fma(q[(p + 1) * RS_SLOTS], w[j][1], sum);
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        if (c4 == 0) part[(size_t)(slot * NL + l) * KP + k] = sum;
+      }
+    }
+  }
+  __syncthreads();
+  for (int task = tid; task < NL * a.Nkr; task += RS_THREADS) {
+    const int l = task / a.Nkr, ik = task - l * a.Nkr;
+    double lin[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) lin[i] = 0.0;
+    for (int slot = 0; slot < a.nslots; ++slot) {
+      const double val = part[(size_t)(slot * NL + l) * KP + ik];
+#pragma unroll
+      for (int i = 0; i < NL; ++i) lin[i] += a.slot_lp[slot] == i ? val : 0.0;
+    }
+    double* out = a.T + ((size_t)(l * a.Nk + a.Nklow + ik) * a.nterm) * Bp + b;
+    for (int i = 0; i < 3; ++i) {
+      double val = 0.0;
+#pragma unroll
+      for (int lp = 0; lp < NL; ++lp) val = fma(a.l11[lp * 3 + i], lin[lp], val);
+      atomicAdd(out + (size_t)i * Bp, val);  // pybird.py:1442, :1445
+    }
+  }
+}
+
 // grid (B, 2): blockIdx.y = 0 runs the heavier a = 1 half (issued first), blockIdx.y = 1 the a = 0 half that fills the tail
 template <int NL, int NIR, bool NNLO>
 __global__ void __launch_bounds__(RS_THREADS, 3) resum_kernel(ResumArgs a) {
   if (blockIdx.y == 0) resum_body<NL, NIR, NNLO, 1>(a);
-  else resum_body<NL, NIR, NNLO, 0>(a);
+  else resum_linear_body<NL, NIR>(a);
 }
 
 // Q^{ll'}_u(f) = sum_d q[u][d] f^d for every cosmology (pybird.py:1367-1380 evaluates the reference's lambdas);
@@ -259,6 +395,10 @@ int run(const ResumArgs& a, cudaStream_t s) {
   resum_q_kernel<<<qgrid, 256, 0, s>>>(a.qpack, a.f, a.NQ, a.qdeg, a.B, a.Qf);
   EFTB_LAUNCH_CHECK();
   size_t smem = sizeof(double) * ((size_t)NL * NL * NIR * RS_SLOTS + 2 * a.NsP + (size_t)NL * (a.ncr - 1) * a.NsP);
+  const size_t smem_lin = sizeof(double) * ((size_t)NIR * rl_pitch(a.NsP) + 2 * NL * a.NsP + (size_t)a.KPAD * NIR +
+                                            (size_t)a.nslots * NL * a.KPAD + (size_t)NL * NL * NIR * RS_SLOTS);
+  if (smem_lin > smem) smem = smem_lin;
+  if (smem > 200 * 1024) { eftb_set_error("resum: %zu bytes of shared memory needed", smem); return EFTB_ERR_ARG; }
   static size_t configured = 0;
   if (smem > configured) {
     EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NNLO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -300,6 +440,8 @@ int resum_pack(eftb_plan* p, const double* R, const double* q) {
         if (kind == 1) ymax = v;
       }
     P.nslot[lp] = 2 + ymax < 3 ? 3 : 2 + ymax;  // kernels are instantiated for 3 and 4 slots
+    P.slot_lp[P.nslots] = lp; P.slot_s[P.nslots++] = 0;        // (X, v = l')
+    for (int v = 0; v <= ymax; ++v) { P.slot_lp[P.nslots] = lp; P.slot_s[P.nslots++] = 1 + v; }  // (Y, v)
   }
   const size_t NQ = (size_t)2 * Nl * Nl * NIR * RS_SLOTS;
   std::vector<double> qp(NQ * c.qdeg, 0.0), rt((size_t)Na * NsP * c.Nkr, 0.0);
@@ -315,6 +457,15 @@ int resum_pack(eftb_plan* p, const double* R, const double* q) {
   for (int v = 0; v < Na; ++v)
     for (int k = 0; k < c.Nkr; ++k)
       for (int s = 0; s < c.Ns; ++s) rt[((size_t)v * NsP + s) * c.Nkr + k] = R[((size_t)v * c.Nkr + k) * c.Ns + s];
+  // k-major copy for the linear-term GEMM, rows padded with zeros to whole warp tasks
+  const int KPAD = eftb_round_up(c.Nkr, 8 * RL_MCH);
+  std::vector<double> rk((size_t)Na * KPAD * NsP, 0.0);
+  for (int v = 0; v < Na; ++v)
+    for (int k = 0; k < c.Nkr; ++k)
+      for (int s = 0; s < c.Ns; ++s) rk[((size_t)v * KPAD + k) * NsP + s] = R[((size_t)v * c.Nkr + k) * c.Ns + s];
+  P.KPAD = KPAD;
+  EFTB_CUDA_CHECK(cudaMalloc((void**)&P.Rk, rk.size() * sizeof(double)));
+  EFTB_CUDA_CHECK(cudaMemcpy(P.Rk, rk.data(), rk.size() * sizeof(double), cudaMemcpyHostToDevice));
   P.NsP = NsP;
   P.NQ = (int)NQ;
   EFTB_CUDA_CHECK(cudaMalloc((void**)&P.qpack, qp.size() * sizeof(double)));
@@ -333,7 +484,8 @@ int launch_resum(const eftb_plan* p, int B, int Bp, const double* F, const doubl
   a.F = F; a.Cr = Cr; a.f = f; a.Rt = p->rs.Rt; a.qpack = p->rs.qpack; a.kr2 = p->kr2; a.l11 = p->l11; a.lct = p->lct;
   a.lctnnlo = p->lctnnlo; a.T = T; a.Qf = scratch; a.B = B; a.Bp = Bp; a.Nk = c.Nk; a.Ns = c.Ns; a.NsP = p->rs.NsP;
   a.nterm = c.nterm; a.ncr = 14 + (c.with_nnlo ? 1 : 0); a.Nkr = c.Nkr; a.Nklow = c.Nklow; a.qdeg = c.qdeg;
-  a.row_x = c.row_x; a.row_y = c.row_y; a.NQ = p->rs.NQ;
+  a.row_x = c.row_x; a.row_y = c.row_y; a.NQ = p->rs.NQ; a.Rk = p->rs.Rk; a.KPAD = p->rs.KPAD; a.nslots = p->rs.nslots;
+  for (int i = 0; i < 12; ++i) { a.slot_lp[i] = (signed char)p->rs.slot_lp[i]; a.slot_s[i] = (signed char)p->rs.slot_s[i]; }
   for (int lp = 0; lp < 3; ++lp) a.nslot[lp] = lp < c.Nl ? p->rs.nslot[lp] : 0;
   const bool nnlo = c.with_nnlo != 0;
   if (c.Nl == 3 && c.NIR == 16 && c.Na == 3) return nnlo ? run<3, 16, true>(a, s) : run<3, 16, false>(a, s);
