@@ -22,7 +22,6 @@ namespace {
 struct ApArgs {
   const double *coef, *Tin, *DA, *H, *k, *knot_lo, *basis, *mu, *wl;
   double *Tout, *G;
-  double* mutab;    // [nb][nmu][AP_TAB]: sqrt(root) and w_l(mu) L_l'(mu') of every (cosmology, mu) node
   int2* meta;       // per (b, k): first B-spline index of the window, window length
   int b0, nb;       // this launch handles cosmologies [b0, b0 + nb)
   int Bp, Nk, nterm, nmu, nint, ap_st, wcap;
@@ -48,17 +47,13 @@ constexpr int APPLY_THREADS = 256;
 // Everything of the resampling geometry that depends on (cosmology, mu) only - NOT on the k node:
 //   k'(k, mu) = (k / q_perp) * sqrt(root),  root = 1 + mu^2 (F^-2 - 1)                 (pybird.py:1608)
 //   mu'^2 = mu^2 F^-2 / root  ->  even Legendre L_l'(mu'), times the quadrature weight w_l(mu)   (pybird.py:1609, :1595)
-// one thread per (cosmology, mu node); AP_TAB doubles per node: sqrt(root), then w_l L_l' for (l, l').
+// AP_TAB doubles per node: sqrt(root), then w_l L_l' for (l, l').  ap_geom_kernel builds these rows in shared memory for
+// the (at most GEOM_COS) cosmologies its threads belong to, one tile of mu nodes at a time.
 constexpr int AP_TAB = 10;
+constexpr int GEOM_MU_TILE = 200;
 
 template <int NL>
-__global__ void __launch_bounds__(128) ap_mu_kernel(ApArgs a) {
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= a.nb * a.nmu) return;
-  const int bl = gid / a.nmu, t = gid - bl * a.nmu, b = a.b0 + bl;
-  const double qperp = a.DA[b] / a.da_fid, qpar = a.h_fid / a.H[b];  // pybird.py:1560-1561
-  const double Fap = qpar / qperp;
-  const double invF2 = 1.0 / (Fap * Fap);
+__device__ __forceinline__ void mu_row(const ApArgs& a, double invF2, int t, double* out) {
   const double m = a.mu[t], m2 = m * m;
   const double root = fma(m2, invF2 - 1.0, 1.0);
   const double rs = rsqrt_newton(root);
@@ -67,12 +62,17 @@ __global__ void __launch_bounds__(128) ap_mu_kernel(ApArgs a) {
   L[0] = 1.0;
   L[1] = 0.5 * (3.0 * mp2 - 1.0);
   L[2] = (35.0 * mp2 * mp2 - 30.0 * mp2 + 3.0) * 0.125;
-  double* out = a.mutab + (size_t)gid * AP_TAB;
   out[0] = root * rs;
 #pragma unroll
   for (int l = 0; l < NL; ++l)
 #pragma unroll
     for (int lp = 0; lp < NL; ++lp) out[1 + l * NL + lp] = a.wl[l * a.nmu + t] * L[lp];
+}
+
+__device__ __forceinline__ double ap_invF2(const ApArgs& a, int b) {
+  const double qperp = a.DA[b] / a.da_fid, qpar = a.h_fid / a.H[b];  // pybird.py:1560-1561
+  const double Fap = qpar / qperp;
+  return 1.0 / (Fap * Fap);
 }
 
 template <int NL>
@@ -82,18 +82,32 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
   extern __shared__ __align__(16) double sm[];
   double* knots = sm;                      // [nint]
   double* bas = knots + a.nint;            // [nint][4][4]
+  double* tabs = bas + a.nint * 16;        // [ncos][tile][AP_TAB] (16-byte aligned: nint * 17 is even or padded below)
+  tabs += (a.nint * 17) & 1;
   const int tid = threadIdx.x;
   for (int i = tid; i < a.nint; i += GEOM_THREADS) knots[i] = a.knot_lo[i];
   for (int i = tid; i < a.nint * 16; i += GEOM_THREADS) bas[i] = a.basis[i];
+  const int ntot = a.nb * a.Nk;
+  const int gid0 = blockIdx.x * GEOM_THREADS, gid = gid0 + tid;
+  const bool active = gid < ntot;
+  const int blA = gid0 / a.Nk, blB = (min(gid0 + GEOM_THREADS, ntot) - 1) / a.Nk, ncos = blB - blA + 1;
+  const int tile = min(a.nmu, GEOM_MU_TILE);
+  // fill the rows of mu nodes [t0, t0 + nt) of this CTA's cosmologies (every thread helps, also inactive ones)
+  auto fill_tile = [&](int t0, int nt) {
+    for (int i = tid; i < ncos * nt; i += GEOM_THREADS) {
+      const int c = i / nt, t = i - c * nt;
+      mu_row<NL>(a, ap_invF2(a, a.b0 + blA + c), t0 + t, tabs + ((size_t)c * tile + t) * AP_TAB);
+    }
+  };
+  fill_tile(0, tile);
   __syncthreads();
-  const int gid = blockIdx.x * GEOM_THREADS + tid;
-  if (gid >= a.nb * a.Nk) return;
-  const int bl = gid / a.Nk, ik = gid - bl * a.Nk, b = a.b0 + bl;
+  const int gidc = active ? gid : ntot - 1;  // inactive threads shadow the last node (no stores) so that they reach the barriers
+  const int bl = gidc / a.Nk, ik = gidc - bl * a.Nk, b = a.b0 + bl;
 
   const double qperp = a.DA[b] / a.da_fid;  // pybird.py:1560
   const double kq = a.k[ik] / qperp;
-  // this cosmology's mu table; the lanes of a warp are consecutive k of (mostly) one cosmology: broadcast loads
-  const double* tab = a.mutab + (size_t)bl * a.nmu * AP_TAB;
+  // this cosmology's rows; the lanes of a warp are consecutive k of (mostly) one cosmology: broadcast loads
+  const double* tab = tabs + (size_t)(bl - blA) * tile * AP_TAB;
 
   auto locate = [&](double x) {  // largest j with knots[j] <= x, clamped (end polynomials extrapolate)
     int lo = 0, hi = a.nint - 1;
@@ -103,12 +117,14 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
     }
     return lo;
   };
+  double endrow[AP_TAB];
+  mu_row<NL>(a, ap_invF2(a, b), a.nmu - 1, endrow);
   const int jfirst = locate(kq * tab[0]);
-  const int jlast = locate(kq * tab[(size_t)(a.nmu - 1) * AP_TAB]);
+  const int jlast = locate(kq * endrow[0]);
   const int jlo = min(jfirst, jlast), jhi = max(jfirst, jlast);
   const int wn = jhi - jlo + 4;
   double* Grow = a.G + ((size_t)bl * a.Nk + ik) * NQ * a.wcap;
-  a.meta[(size_t)bl * a.Nk + ik] = make_int2(jlo, wn);
+  if (active) a.meta[(size_t)bl * a.Nk + ik] = make_int2(jlo, wn);
   // k'(mu) is monotone, so the live window is only ever moved in the direction jfirst -> jlast (a k' that dips back
   // across a knot by rounding keeps its current interval: the spline is C2, the value agrees to ~1e-14).  Every
   // column of the window is therefore retired exactly once, with a plain store: no zero-fill, no atomics.
@@ -125,13 +141,20 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
   for (int i = 0; i < 16; ++i) bc[i] = bas[j * 16 + i];
   double knot = knots[j];
 
-  for (int t = 0; t < a.nmu; ++t) {
+  for (int t0 = 0; t0 < a.nmu; t0 += tile) {
+   const int nt = min(tile, a.nmu - t0);
+   if (t0 > 0) {  // next tile of mu nodes (nmu > GEOM_MU_TILE only)
+     __syncthreads();
+     fill_tile(t0, nt);
+     __syncthreads();
+   }
+   for (int t = 0; t < nt; ++t) {
     // 80 bytes per node, 16-byte aligned: sqrt(root) | w_l L_l'
     const double2* row = reinterpret_cast<const double2*>(tab + (size_t)t * AP_TAB);
     double wL[AP_TAB];
 #pragma unroll
     for (int i = 0; i < AP_TAB / 2; ++i) {
-      const double2 v = __ldg(row + i);
+      const double2 v = row[i];
       wL[2 * i] = v.x;
       wL[2 * i + 1] = v.y;
     }
@@ -140,7 +163,7 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
       double* g = Grow + (j - jlo);          // B-spline j has no support beyond this knot: retire its column
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        g[q * a.wcap] = acc[q][0];
+        if (active) g[q * a.wcap] = acc[q][0];
         acc[q][0] = acc[q][1]; acc[q][1] = acc[q][2]; acc[q][2] = acc[q][3]; acc[q][3] = 0.0;
       }
       ++j;
@@ -152,7 +175,7 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
       double* g = Grow + (j + 3 - jlo);
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        g[q * a.wcap] = acc[q][3];
+        if (active) g[q * a.wcap] = acc[q][3];
         acc[q][3] = acc[q][2]; acc[q][2] = acc[q][1]; acc[q][1] = acc[q][0]; acc[q][0] = 0.0;
       }
       --j;
@@ -168,7 +191,9 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
     for (int q = 0; q < NQ; ++q)
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[q][r] = fma(wL[1 + q], bv[r], acc[q][r]);
+   }
   }
+  if (!active) return;
   double* g = Grow + (j - jlo);
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
@@ -268,7 +293,9 @@ int ap_chunk(const eftb_config& c, int B) {
 
 template <int NL>
 int run(ApArgs a, int B, cudaStream_t s) {
-  const size_t smem_g = sizeof(double) * (a.nint + (size_t)a.nint * 16);
+  const int geom_cos = (GEOM_THREADS - 2 + a.Nk) / a.Nk + 1;  // cosmologies a CTA's GEOM_THREADS consecutive (b, k) nodes can touch
+  const int mu_tile = a.nmu < GEOM_MU_TILE ? a.nmu : GEOM_MU_TILE;
+  const size_t smem_g = sizeof(double) * (a.nint + (size_t)a.nint * 16 + 1 + (size_t)geom_cos * mu_tile * AP_TAB);
   const size_t smem_a = sizeof(double) * ((size_t)NL * a.Nk * a.nterm + (size_t)2 * (APPLY_THREADS / (NL * a.nterm)) * NL * NL * APPLY_WS) +
                         sizeof(int2) * a.Nk;
   if (NL * a.nterm > APPLY_THREADS || smem_g > 200 * 1024 || smem_a > 200 * 1024) {
@@ -289,8 +316,6 @@ int run(ApArgs a, int B, cudaStream_t s) {
     a.b0 = b0;
     a.nb = B - b0 < chunk ? B - b0 : chunk;
     const int nthreads = a.nb * a.Nk;
-    ap_mu_kernel<NL><<<(a.nb * a.nmu + 127) / 128, 128, 0, s>>>(a);
-    EFTB_LAUNCH_CHECK();
     ap_geom_kernel<NL><<<(nthreads + GEOM_THREADS - 1) / GEOM_THREADS, GEOM_THREADS, smem_g, s>>>(a);
     EFTB_LAUNCH_CHECK();
     ap_apply_kernel<NL><<<a.nb, APPLY_THREADS, smem_a, s>>>(a);
@@ -304,7 +329,7 @@ int run(ApArgs a, int B, cudaStream_t s) {
 size_t ap_scratch_doubles(const eftb_plan* p, int B) {
   const eftb_config& c = p->cfg;
   const size_t chunk = ap_chunk(c, B);
-  return chunk * c.Nk * c.Nl * c.Nl * c.Nk + chunk * c.Nk + 1 + chunk * c.nmu * AP_TAB;  // G | meta (int2 = 8 bytes) | pad | mu table
+  return chunk * c.Nk * c.Nl * c.Nl * c.Nk + chunk * c.Nk;  // G | meta (int2 = 8 bytes each)
 }
 
 int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const double* Tin, const double* DA, const double* H,
@@ -318,10 +343,6 @@ int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const doubl
   a.b0 = 0;
   a.G = scratch;
   a.meta = reinterpret_cast<int2*>(scratch + (size_t)a.nb * c.Nk * c.Nl * c.Nl * c.Nk);
-  {
-    size_t off = (size_t)a.nb * c.Nk * c.Nl * c.Nl * c.Nk + (size_t)a.nb * c.Nk;
-    a.mutab = scratch + off + (off & 1);  // 16-byte aligned rows (scratch itself is 16-byte aligned)
-  }
   if (c.Nl == 3) return run<3>(a, B, s);
   if (c.Nl == 2) return run<2>(a, B, s);
   eftb_set_error("ap: unsupported Nl=%d", c.Nl);
