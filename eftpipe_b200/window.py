@@ -37,9 +37,42 @@ _CALQ = np.array([
 ])
 
 
+def _device_real_products(A_list, X):
+    """[A @ X for A in A_list] on the GPU through the library's fixed-operator DMMA GEMM (`eftb_operator_*`):
+    A (M, K) host arrays, X (K, N) host array; returns host arrays (M, N)."""
+    import ctypes as C
+
+    from . import _lib
+
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    K, N = X.shape
+    Np = (N + 31) // 32 * 32
+    Xd = torch.zeros((K, Np), dtype=torch.float64, device="cuda")
+    Xd[:, :N] = torch.as_tensor(X, device="cuda")
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = []
+    for A in A_list:
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        h = C.c_void_p()
+        _lib.check(lib.eftb_operator_create(A.shape[0], K, _lib.as_ptr(A), C.byref(h)), "eftb_operator_create")
+        Cd = torch.empty((A.shape[0], Np), dtype=torch.float64, device="cuda")
+        try:
+            _lib.check(lib.eftb_operator_apply(h, C.c_void_p(Xd.data_ptr()), C.c_void_p(Cd.data_ptr()), Np, stream),
+                       "eftb_operator_apply")
+            out.append(Cd[:, :N].cpu().numpy())
+        finally:
+            lib.eftb_operator_destroy(h)
+    return out
+
+
 def compute_Wal(s_Q, k, Na, Nl, Nq=3, pmax=None, accboost=1, Nmax=4096, xmin_factor=1.0, xmax_factor=100.0,
-                bias=-1.6, window_param=1):
-    """Fourier-space window matrix (window.py:262-346).  s_Q: (ns, 1+nq) columns s, Q0, Q2, ..."""
+                bias=-1.6, window_param=1, device=False):
+    """Fourier-space window matrix (window.py:262-346).  s_Q: (ns, 1+nq) columns s, Q0, Q2, ...
+
+    The dominant cost is the sum over the 4097 FFTLog frequencies, Re sum_n coef[l,k,n] M[l,n] p^{-eta_n-3}: a real
+    product [Re(coef M) | -Im(coef M)] (Nl*Nk x 2N) times [Re pPow; Im pPow] (2N x Np).  With `device=True` it runs
+    on the GPU through the library's DMMA GEMM (SURVEY.md 8f #3), otherwise through the host BLAS."""
     k = np.asarray(k, float)
     pmax = float(k.max()) if pmax is None else pmax
     p = window_pgrid(pmax, accboost)
@@ -52,13 +85,16 @@ def compute_Wal(s_Q, k, Na, Nl, Nq=3, pmax=None, accboost=1, Nmax=4096, xmin_fac
     fft = FFTLog(Nmax=Nmax, xmin=sw[0] * xmin_factor, xmax=sw[-1] * xmax_factor, bias=bias)
     pPow = np.exp(np.outer(-fft.Pow - 3.0, np.log(p)))
     M = np.array([4 * np.pi * tables.bessel_power(2 * l, -0.5 * fft.Pow) for l in range(Nl)])
-    Wal = np.empty((Na, Nl, k.size, p.size))
-    for a in range(Na):  # one output multipole at a time keeps the (k, n, p) work arrays small
+    X = np.concatenate([pPow.real, pPow.imag], axis=0)  # (2N, Np), shared by every (a, l)
+    lhs = []
+    for a in range(Na):  # one output multipole at a time keeps the (k, n) work arrays small
         kern = lambda x, a=a: spherical_jn(2 * a, x[None, None, :] * k[None, :, None])
         coef = fft.coef_host(sw, Qal[a][:, None, :], extrap="padding", window=window_param, kernel=kern)
         phase = ((-1j) ** (2 * a)) * ((1j) ** (2 * np.arange(Nl)))[:, None, None]
-        coef = phase * coef  # (Nl, Nk, N)
-        Wal[a] = p**2 * np.real(np.einsum("lkn,np,ln->lkp", coef, pPow, M))
+        cm = (phase * coef * M[:, None, :]).reshape(Nl * k.size, -1)  # (Nl*Nk, N): coef[l,k,n] M[l,n]
+        lhs.append(np.concatenate([cm.real, -cm.imag], axis=1))
+    prods = _device_real_products(lhs, X) if device else [A @ X for A in lhs]
+    Wal = np.stack([pr.reshape(Nl, k.size, p.size) for pr in prods]) * p**2
     return Wal, p
 
 
@@ -68,8 +104,19 @@ class Window:
     def __init__(self, window_fourier_file=None, window_configspace_file=None, co=None, load=True, save=True,
                  check_meta=True, Na=None, Nl=None, Nq=3, pmax=None, accboost=1, withmask=True, windowk=0.05,
                  Nmax=4096, xmin_factor=1.0, xmax_factor=100.0, bias=-1.6, window_param=1, window_st=True,
-                 icc=None, name="pybird.window", snapshot=False, window_configspace_array=None):
+                 icc=None, name="pybird.window", snapshot=False, window_configspace_array=None, device=None):
+        """`device`: build the Fourier-space matrix on the GPU (True), on the host (False), or on the GPU when one is
+        present (None, default)."""
         from .pybird import common
+
+        if device is None:
+            try:
+                import torch
+
+                device = bool(torch.cuda.is_available())
+            except Exception:
+                device = False
+        self._device_build = bool(device)
 
         self.co = co if co is not None else common
         if window_fourier_file is None and window_configspace_file is None and window_configspace_array is None:
@@ -148,7 +195,7 @@ class Window:
         m = self.meta
         Wal, _ = compute_Wal(tab, self.co.k, m["Na"], m["Nl"], Nq=m["Nq"], pmax=m["pmax"], accboost=m["accboost"],
                              Nmax=m["Nmax"], xmin_factor=m["xmin_factor"], xmax_factor=m["xmax_factor"], bias=m["bias"],
-                             window_param=m["window_param"])
+                             window_param=m["window_param"], device=self._device_build)
         return Wal
 
     def _save_Wal(self):
