@@ -402,13 +402,17 @@ def run_ours(args):
         "logp_check": {"finite": bool(torch.isfinite(logp).all()), "status_nonzero": int((status != 0).sum())},
     }
     if world == 1 and not args.no_cpu:
-        ncheck = 8
-        rates, ref_logp = cpu_arm(S, 1, ncheck, repeats=2)
+        # same arrangement as `--impl reference`: one single-threaded worker process per host core (the fastest way to
+        # run the numpy path: ~12x the rate of one process with all BLAS threads), 2 evaluations per worker, 2 repeats
+        cores = os.cpu_count() or 1
+        nproc = max(1, min(cores, 96))
+        ncheck = min(B, 2 * nproc)
+        rates, ref_logp = cpu_arm(S, nproc, ncheck, repeats=2)
         got = logp[:ncheck].cpu().numpy()
-        line["cpu_baseline"] = {"value": float(max(rates)), "unit": UNIT, "cores": int(os.environ.get("OPENBLAS_NUM_THREADS", os.cpu_count() or 1)),
-                                "kind": "port",
-                                "sample": f"first {ncheck} points of the batch, 2 repeats, one process, numpy/OpenBLAS threads = all host cores "
-                                          f"({os.cpu_count()}); oracle/pybird_oracle.py restatement of the reference path"}
+        line["cpu_baseline"] = {"value": float(max(rates)), "unit": UNIT, "cores": nproc, "kind": "port",
+                                "sample": f"first {ncheck} points of the batch, best of 2 repeats, {nproc} single-threaded worker "
+                                          f"processes (host has {cores} cores); oracle/pybird_oracle.py restatement of the "
+                                          "reference numpy path"}
         line["logp_check"]["max_rel_err_vs_oracle"] = float(np.max(np.abs(got - ref_logp) / np.abs(ref_logp)))
     print(json.dumps(line))
     if world > 1:
@@ -615,7 +619,9 @@ def stage_profile(dp, like, lib, S, d_plin, d_f, d_DA, d_H, d_cols, terms_bm, B,
     peak = max(tf.value, dgemm_tf)
     achieved = flops[top] * B / (ms[top] * 1e-3) / 1e12
     roof = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the committed
+            # `ncu --set full` capture at B = 1024 (profiles/r1_top_kernels_v5.txt), scaled to this batch
+            "traffic": NCU_DRAM_BYTES_PER_POINT.get(top, 0.0) * B or None,
             "peak_source": "FP64 measured live on this GPU: max(DFMA probe %.1f, cuBLAS DGEMM 8192^3 %.1f TFLOP/s); "
                            "MEASURED_PEAKS.json has no FP64 entry" % (tf.value, dgemm_tf),
             "per_stage_tflops": {k: flops[k] * B / (ms[k] * 1e-3) / 1e12 for k in flops},
@@ -625,6 +631,12 @@ def stage_profile(dp, like, lib, S, d_plin, d_f, d_DA, d_H, d_cols, terms_bm, B,
 
 
 from eftpipe_b200 import plan as P  # noqa: E402  (host-only module; used in stage_profile)
+
+# DRAM bytes (read + write) per evaluation point of each stage's kernels, from profiles/r1_top_kernels_v5.txt
+# (ncu --set full --clock-control none, B = 1024, config 2): resum_kernel 60.75 + 0.25 MB; antidiag_kernel 13.0 + 100.9 MB;
+# spectral = regroup 160.0 + 104.7, P22 GEMM 118.2 + 4.1, C(s) GEMM 152.6 + 3.7 MB; ap = Cinv GEMM 29.6, geom 12.4 + 13.1,
+# apply 97.4 + 6.4 MB
+NCU_DRAM_BYTES_PER_POINT = {"resum": 61.0e6 / 1024, "antidiag": 113.9e6 / 1024, "spectral": 543.3e6 / 1024, "ap": 158.9e6 / 1024}
 
 
 def main():
