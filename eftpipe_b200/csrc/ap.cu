@@ -292,7 +292,7 @@ int ap_chunk(const eftb_config& c, int B) {
 }
 
 template <int NL>
-int run(ApArgs a, int B, cudaStream_t s) {
+int run(ApArgs a, int B, cudaStream_t s, int phase) {
   const int geom_cos = (GEOM_THREADS - 2 + a.Nk) / a.Nk + 1;  // cosmologies a CTA's GEOM_THREADS consecutive (b, k) nodes can touch
   const int mu_tile = a.nmu < GEOM_MU_TILE ? a.nmu : GEOM_MU_TILE;
   const size_t smem_g = sizeof(double) * (a.nint + (size_t)a.nint * 16 + 1 + (size_t)geom_cos * mu_tile * AP_TAB);
@@ -316,10 +316,14 @@ int run(ApArgs a, int B, cudaStream_t s) {
     a.b0 = b0;
     a.nb = B - b0 < chunk ? B - b0 : chunk;
     const int nthreads = a.nb * a.Nk;
-    ap_geom_kernel<NL><<<(nthreads + GEOM_THREADS - 1) / GEOM_THREADS, GEOM_THREADS, smem_g, s>>>(a);
-    EFTB_LAUNCH_CHECK();
-    ap_apply_kernel<NL><<<a.nb, APPLY_THREADS, smem_a, s>>>(a);
-    EFTB_LAUNCH_CHECK();
+    if (phase & EFTB_PHASE_FIRST) {
+      ap_geom_kernel<NL><<<(nthreads + GEOM_THREADS - 1) / GEOM_THREADS, GEOM_THREADS, smem_g, s>>>(a);
+      EFTB_LAUNCH_CHECK();
+    }
+    if (phase & EFTB_PHASE_SECOND) {
+      ap_apply_kernel<NL><<<a.nb, APPLY_THREADS, smem_a, s>>>(a);
+      EFTB_LAUNCH_CHECK();
+    }
   }
   return EFTB_OK;
 }
@@ -332,9 +336,18 @@ size_t ap_scratch_doubles(const eftb_plan* p, int B) {
   return chunk * c.Nk * c.Nl * c.Nl * c.Nk + chunk * c.Nk;  // G | meta (int2 = 8 bytes each)
 }
 
+int ap_chunk_count(const eftb_plan* p, int B) {
+  const int chunk = ap_chunk(p->cfg, B);
+  return (B + chunk - 1) / chunk;
+}
+
 int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const double* Tin, const double* DA, const double* H,
-              double* scratch, double* Tout, cudaStream_t s) {
+              double* scratch, double* Tout, cudaStream_t s, int phase) {
   const eftb_config& c = p->cfg;
+  if (phase != EFTB_PHASE_ALL && ap_chunk_count(p, B) != 1) {
+    eftb_set_error("ap: split phases need the whole batch in one chunk");
+    return EFTB_ERR_ARG;
+  }
   ApArgs a;
   a.coef = coef; a.Tin = Tin; a.DA = DA; a.H = H; a.k = p->k; a.knot_lo = p->knot_lo; a.basis = p->basis; a.mu = p->mu;
   a.wl = p->wl; a.Tout = Tout; a.Bp = Bp; a.Nk = c.Nk; a.nterm = c.nterm; a.nmu = c.nmu; a.nint = c.nint;
@@ -343,8 +356,8 @@ int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const doubl
   a.b0 = 0;
   a.G = scratch;
   a.meta = reinterpret_cast<int2*>(scratch + (size_t)a.nb * c.Nk * c.Nl * c.Nl * c.Nk);
-  if (c.Nl == 3) return run<3>(a, B, s);
-  if (c.Nl == 2) return run<2>(a, B, s);
+  if (c.Nl == 3) return run<3>(a, B, s, phase);
+  if (c.Nl == 2) return run<2>(a, B, s, phase);
   eftb_set_error("ap: unsupported Nl=%d", c.Nl);
   return EFTB_ERR_ARG;
 }

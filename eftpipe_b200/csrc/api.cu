@@ -154,6 +154,13 @@ int eftb_plan_create(const eftb_config* cfg, const eftb_constants* h, eftb_plan*
     p->perm_rows = (int)perm.size();
     rc |= upload(&p->perm_out, perm.data(), perm.size());
   }
+  if (!rc) {
+    cudaError_t e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_loops, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
+    if (e != cudaSuccess) { eftb_set_error("eftb_plan_create: %s", cudaGetErrorString(e)); rc = EFTB_ERR_CUDA; }
+  }
   if (rc) { eftb_plan_destroy(p); return rc < 0 ? rc : EFTB_ERR_CUDA; }
   *out = p;
   return EFTB_OK;
@@ -165,6 +172,10 @@ void eftb_plan_destroy(eftb_plan* p) {
                   p->rs.Rt, p->rs.Rk, p->rs.qpack, p->kr2, p->knot_lo, p->basis, p->mu, p->wl, p->perm_out};
   for (void* q : ptrs) if (q) cudaFree(q);
   antidiag_free(p);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_loops) cudaEventDestroy(p->ev_loops);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->side) cudaStreamDestroy(p->side);
   gemm_free(&p->Wf); gemm_free(&p->Ak); gemm_free(&p->As); gemm_free(&p->Cinv); gemm_free(&p->project); gemm_free(&p->project_st);
   delete p;
 }
@@ -226,6 +237,18 @@ int eftb_spectral(const eftb_plan* p, int B, const double* D, const double* Dcf,
   return gemm_run(p->As, Dcf, Cs, Bp, c.Nl * EFTB_NCH, EFTB_NCH, dch, 0, (size_t)c.Ns * Bp, (size_t)EFTB_NCH * c.Ns * Bp, s);
 }
 
+// configuration-space half of eftb_spectral_grouped: regroup the channels, then Cloopl[l][r] = As[l] @ Dg[l][r], written
+// straight into rows 2..13 of the point-major Cr[b][l][ncr][Ns]
+static int spectral_cf(const eftb_plan* p, int Bp, const double* Dcf, const double* f, double* Dg, double* Cr, cudaStream_t s) {
+  const eftb_config& c = p->cfg;
+  const size_t dch = (size_t)(c.Nmax + 1) * 2 * Bp;
+  const int ncr = 14 + (c.with_nnlo ? 1 : 0);
+  int rc = launch_regroup(p, Bp, Dcf, f, Dg, s);
+  if (rc) return rc;
+  GemmPointMajor pm{Bp, (size_t)c.Nl * ncr * c.Ns, 0};
+  return gemm_run(p->As, Dg, Cr + 2 * (size_t)c.Ns, Bp, c.Nl * 12, 12, dch, 12 * dch, (size_t)c.Ns, (size_t)ncr * c.Ns, s, &pm);
+}
+
 int eftb_spectral_grouped(const eftb_plan* p, int B, const double* D, const double* Dcf, const double* f, double* Dg, double* P22,
                           double* Cr, void* stream) {
   EFTB_NEED(p && D && f && Dg && P22 && Cr && B >= 1, "NULL/invalid argument");
@@ -234,13 +257,9 @@ int eftb_spectral_grouped(const eftb_plan* p, int B, const double* D, const doub
   const eftb_config& c = p->cfg;
   const int Bp = eftb_padded_batch(B);
   const size_t dch = (size_t)(c.Nmax + 1) * 2 * Bp;
-  const int ncr = 14 + (c.with_nnlo ? 1 : 0);
-  int rc = launch_regroup(p, Bp, Dcf, f, Dg, s);
+  int rc = gemm_run(p->Ak, D, P22, Bp, EFTB_N22, EFTB_N22, dch, 0, (size_t)c.Nk * Bp, 0, s);
   if (rc) return rc;
-  if ((rc = gemm_run(p->Ak, D, P22, Bp, EFTB_N22, EFTB_N22, dch, 0, (size_t)c.Nk * Bp, 0, s))) return rc;
-  // Cloopl[l][r] = As[l] @ Dg[l][r], written straight into rows 2..13 of the point-major Cr[b][l][ncr][Ns]
-  GemmPointMajor pm{Bp, (size_t)c.Nl * ncr * c.Ns, 0};
-  return gemm_run(p->As, Dg, Cr + 2 * (size_t)c.Ns, Bp, c.Nl * 12, 12, dch, 12 * dch, (size_t)c.Ns, (size_t)ncr * c.Ns, s, &pm);
+  return spectral_cf(p, Bp, Dcf, f, Dg, Cr, s);
 }
 
 int eftb_group(const eftb_plan* p, int B, const double* F, const double* P22, const double* Cs, const double* f, double* T,
@@ -268,7 +287,7 @@ size_t eftb_ap_scratch_bytes(const eftb_plan* p, int B) {
 }
 
 static int ap_stage(const eftb_plan* p, int B, const double* Tin, const double* DA, const double* H, double* coef,
-                    double* gscratch, double* Tout, cudaStream_t s) {
+                    double* gscratch, double* Tout, cudaStream_t s, int phase = EFTB_PHASE_ALL) {
   const eftb_config& c = p->cfg;
   const int Bp = eftb_padded_batch(B);
   const size_t per_l = (size_t)c.Nk * c.nterm * Bp;
@@ -280,7 +299,7 @@ static int ap_stage(const eftb_plan* p, int B, const double* Tin, const double* 
   if (Bp > B) {  // pad lanes are not processed by the per-cosmology kernels: keep them finite
     EFTB_CUDA_CHECK(cudaMemcpyAsync(Tout, Tin, (size_t)c.Nl * per_l * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
-  return launch_ap(p, B, Bp, coef, Tin, DA, H, gscratch, Tout, s);
+  return launch_ap(p, B, Bp, coef, Tin, DA, H, gscratch, Tout, s, phase);
 }
 
 int eftb_ap(const eftb_plan* p, int B, const double* Tin, const double* DA, const double* H, double* scratch, double* Tout,
@@ -325,22 +344,43 @@ int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double*
   double* out = w;
   double* Dcf = z.Dcf ? out + z.out + z.ap + z.rs : nullptr;
   int rc;
-  if ((rc = eftb_front(p, B, plin, u, F, stream))) return rc;
+  // Side stream (fork/join by events; capturable into a CUDA graph together with `stream`): everything that depends on
+  // the cosmology scalars only - the Q(f) expansion of the resummation and the AP resampling geometry - runs beside the
+  // front end and the loop kernels, and the D -> P22(k) GEMM runs beside the regrouping of the configuration-space
+  // channels.  All of them write buffers nothing else touches until the join.
+  const bool split_ap = c.has_ap && ap_chunk_count(p, B) == 1;
+  cudaStream_t s2 = p->side;
+  double* qf = out + z.out + z.ap;
   if ((rc = launch_to_batch_minor(f, B, Bp, 1, scal, s))) return rc;
   if (c.has_ap) {
     if ((rc = launch_to_batch_minor(DA, B, Bp, 1, scal + Bp, s))) return rc;
     if ((rc = launch_to_batch_minor(H, B, Bp, 1, scal + 2 * (size_t)Bp, s))) return rc;
   }
+  EFTB_CUDA_CHECK(cudaEventRecord(p->ev_fork, s));
+  EFTB_CUDA_CHECK(cudaStreamWaitEvent(s2, p->ev_fork, 0));
+  if (c.has_resum && (rc = launch_resum(p, B, Bp, F, Cr, scal, T, qf, s2, EFTB_PHASE_FIRST))) return rc;
+  if (split_ap && (rc = launch_ap(p, B, Bp, nullptr, nullptr, scal + Bp, scal + 2 * (size_t)Bp, out + z.out, nullptr, s2,
+                                  EFTB_PHASE_FIRST))) return rc;
+  if ((rc = eftb_front(p, B, plin, u, F, stream))) return rc;
   if ((rc = launch_antidiag(p, Bp, F, D, s))) return rc;
+  EFTB_CUDA_CHECK(cudaEventRecord(p->ev_loops, s));
+  EFTB_CUDA_CHECK(cudaStreamWaitEvent(s2, p->ev_loops, 0));
+  {  // D -> P22(k) on the side stream
+    const size_t dch = (size_t)(c.Nmax + 1) * 2 * Bp;
+    if ((rc = gemm_run(p->Ak, D, P22, Bp, EFTB_N22, EFTB_N22, dch, 0, (size_t)c.Nk * Bp, 0, s2))) return rc;
+  }
+  EFTB_CUDA_CHECK(cudaEventRecord(p->ev_join, s2));
   if (Dcf && (rc = launch_antidiag(p, Bp, F, Dcf, s, true))) return rc;
-  if ((rc = eftb_spectral_grouped(p, B, D, Dcf, scal, Dg, P22, Cr, stream))) return rc;
+  if ((rc = spectral_cf(p, Bp, Dcf ? Dcf : D, scal, Dg, Cr, s))) return rc;
+  EFTB_CUDA_CHECK(cudaStreamWaitEvent(s, p->ev_join, 0));
   if ((rc = launch_group(p, Bp, F, P22, nullptr, scal, T, Cr, s))) return rc;
-  if (c.has_resum && (rc = launch_resum(p, B, Bp, F, Cr, scal, T, out + z.out + z.ap, s))) return rc;
+  if (c.has_resum && (rc = launch_resum(p, B, Bp, F, Cr, scal, T, qf, s, EFTB_PHASE_SECOND))) return rc;
   double* cur = T;
   if (c.has_ap) {
     double* coef = D;
     double* T2 = D + z.T;
-    if ((rc = ap_stage(p, B, T, scal + Bp, scal + 2 * (size_t)Bp, coef, out + z.out, T2, s))) return rc;
+    if ((rc = ap_stage(p, B, T, scal + Bp, scal + 2 * (size_t)Bp, coef, out + z.out, T2, s,
+                       split_ap ? EFTB_PHASE_SECOND : EFTB_PHASE_ALL))) return rc;
     cur = T2;
   }
   if (c.has_project) {

@@ -72,6 +72,9 @@ struct eftb_plan {
   double *knot_lo = nullptr, *basis = nullptr, *mu = nullptr, *wl = nullptr;
   int32_t* perm_out = nullptr;  // point-major export permutation
   int perm_rows = 0;
+  // fused pipeline only: side stream + fork/join events (one eftb_eval_terms call at a time per plan)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_loops = nullptr, ev_join = nullptr;
 };
 
 // kernels' host launchers (defined in the respective .cu files)
@@ -83,11 +86,15 @@ int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cuda
 int launch_group(const eftb_plan* p, int Bp, const double* F, const double* P22, const double* Cs,
                  const double* f, double* T, double* Cr, cudaStream_t s);  // Cs == NULL: Cloopl rows of Cr already filled
 int launch_regroup(const eftb_plan* p, int Bp, const double* D, const double* f, double* Dg, cudaStream_t s);
+// phases of the two-kernel stages, so that the fused pipeline can run the cosmology-only halves (the Q(f) expansion,
+// the AP resampling geometry) on a side stream while the loop kernels run
+enum { EFTB_PHASE_ALL = 3, EFTB_PHASE_FIRST = 1, EFTB_PHASE_SECOND = 2 };
 int launch_resum(const eftb_plan* p, int B, int Bp, const double* F, const double* Cr, const double* f,
-                 double* T, double* scratch, cudaStream_t s);
+                 double* T, double* scratch, cudaStream_t s, int phase = EFTB_PHASE_ALL);  // FIRST: Q(f); SECOND: the sweep
 size_t resum_scratch_doubles(const eftb_plan* p, int B);  // expanded Q(f): [B][2 Nl Nl NIR 4]
 int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const double* Tin, const double* DA,
-              const double* H, double* scratch, double* Tout, cudaStream_t s);
+              const double* H, double* scratch, double* Tout, cudaStream_t s, int phase = EFTB_PHASE_ALL);  // FIRST: geometry
+int ap_chunk_count(const eftb_plan* p, int B);  // launches the AP stage splits the batch into (phases need 1)
 size_t ap_scratch_doubles(const eftb_plan* p, int B);  // banded AP operator G + window metadata
 int launch_to_batch_minor(const double* in, int B, int Bp, int R, double* out, cudaStream_t s);
 int launch_to_point_major(const double* in, int B, int Bp, int R, const int32_t* perm, double* out,

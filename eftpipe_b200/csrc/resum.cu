@@ -24,6 +24,7 @@
 //   W_(l',X)[p,s] = X^{p+1} C11_l',  W_(l',Y,v)[p,s] = Y X^p C11_l'
 // - per slot a (Nkr x Ns)(Ns x NIR) product with a FIXED left operand: DMMA m8n8k4 with the B fragments built on the
 // fly as base_slot[s] * X(s)^p from two small shared-memory tables (resum_linear_body).
+#include <stdlib.h>
 #include <vector>
 #include "common.cuh"
 
@@ -367,8 +368,8 @@ __device__ __forceinline__ void resum_linear_body(const ResumArgs& a) {
 }
 
 // grid (B, 2): blockIdx.y = 0 runs the heavier a = 1 half (issued first), blockIdx.y = 1 the a = 0 half that fills the tail
-template <int NL, int NIR, bool NNLO>
-__global__ void __launch_bounds__(RS_THREADS, 3) resum_kernel(ResumArgs a) {
+template <int NL, int NIR, bool NNLO, int MINB>
+__global__ void __launch_bounds__(RS_THREADS, MINB) resum_kernel(ResumArgs a) {
   if (blockIdx.y == 0) resum_body<NL, NIR, NNLO, 1>(a);
   else resum_linear_body<NL, NIR>(a);
 }
@@ -390,21 +391,27 @@ __global__ void __launch_bounds__(256) resum_q_kernel(const double* __restrict__
 }
 
 template <int NL, int NIR, bool NNLO>
-int run(const ResumArgs& a, cudaStream_t s) {
-  dim3 qgrid((a.NQ + 255) / 256, a.B);
-  resum_q_kernel<<<qgrid, 256, 0, s>>>(a.qpack, a.f, a.NQ, a.qdeg, a.B, a.Qf);
-  EFTB_LAUNCH_CHECK();
+int run(const ResumArgs& a, cudaStream_t s, int phase) {
+  if (phase & EFTB_PHASE_FIRST) {
+    dim3 qgrid((a.NQ + 255) / 256, a.B);
+    resum_q_kernel<<<qgrid, 256, 0, s>>>(a.qpack, a.f, a.NQ, a.qdeg, a.B, a.Qf);
+    EFTB_LAUNCH_CHECK();
+  }
+  if (!(phase & EFTB_PHASE_SECOND)) return EFTB_OK;
   size_t smem = sizeof(double) * ((size_t)NL * NL * NIR * RS_SLOTS + 2 * a.NsP + (size_t)NL * (a.ncr - 1) * a.NsP);
   const size_t smem_lin = sizeof(double) * ((size_t)NIR * rl_pitch(a.NsP) + 2 * NL * a.NsP + (size_t)a.KPAD * NIR +
                                             (size_t)a.nslots * NL * a.KPAD + (size_t)NL * NL * NIR * RS_SLOTS);
   if (smem_lin > smem) smem = smem_lin;
   if (smem > 200 * 1024) { eftb_set_error("resum: %zu bytes of shared memory needed", smem); return EFTB_ERR_ARG; }
   static size_t configured = 0;
+  static const int minb = getenv("EFTB_RESUM_MINB") ? atoi(getenv("EFTB_RESUM_MINB")) : 3;  // tuning knob: CTAs per SM
   if (smem > configured) {
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NNLO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NNLO, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NNLO, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  resum_kernel<NL, NIR, NNLO><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
+  if (minb == 4) resum_kernel<NL, NIR, NNLO, 4><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
+  else resum_kernel<NL, NIR, NNLO, 3><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;
 }
@@ -478,7 +485,7 @@ int resum_pack(eftb_plan* p, const double* R, const double* q) {
 size_t resum_scratch_doubles(const eftb_plan* p, int B) { return (size_t)p->rs.NQ * B; }
 
 int launch_resum(const eftb_plan* p, int B, int Bp, const double* F, const double* Cr, const double* f, double* T,
-                 double* scratch, cudaStream_t s) {
+                 double* scratch, cudaStream_t s, int phase) {
   const eftb_config& c = p->cfg;
   ResumArgs a;
   a.F = F; a.Cr = Cr; a.f = f; a.Rt = p->rs.Rt; a.qpack = p->rs.qpack; a.kr2 = p->kr2; a.l11 = p->l11; a.lct = p->lct;
@@ -488,8 +495,8 @@ int launch_resum(const eftb_plan* p, int B, int Bp, const double* F, const doubl
   for (int i = 0; i < 12; ++i) { a.slot_lp[i] = (signed char)p->rs.slot_lp[i]; a.slot_s[i] = (signed char)p->rs.slot_s[i]; }
   for (int lp = 0; lp < 3; ++lp) a.nslot[lp] = lp < c.Nl ? p->rs.nslot[lp] : 0;
   const bool nnlo = c.with_nnlo != 0;
-  if (c.Nl == 3 && c.NIR == 16 && c.Na == 3) return nnlo ? run<3, 16, true>(a, s) : run<3, 16, false>(a, s);
-  if (c.Nl == 2 && c.NIR == 8 && c.Na == 2) return nnlo ? run<2, 8, true>(a, s) : run<2, 8, false>(a, s);
+  if (c.Nl == 3 && c.NIR == 16 && c.Na == 3) return nnlo ? run<3, 16, true>(a, s, phase) : run<3, 16, false>(a, s, phase);
+  if (c.Nl == 2 && c.NIR == 8 && c.Na == 2) return nnlo ? run<2, 8, true>(a, s, phase) : run<2, 8, false>(a, s, phase);
   eftb_set_error("resum: unsupported (Nl, NIR, Na) = (%d, %d, %d)", c.Nl, c.NIR, c.Na);
   return EFTB_ERR_ARG;
 }
