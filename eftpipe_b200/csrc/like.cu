@@ -12,7 +12,7 @@ struct eftb_like {
   int32_t *nout = nullptr, *nterm = nullptr, *par_index = nullptr, *eastcoast = nullptr;
   int32_t h_nout[EFTB_MAX_TRACERS], h_nterm[EFTB_MAX_TRACERS];
   double* scales = nullptr;
-  int32_t *d_tracer = nullptr, *d_row = nullptr;
+  int32_t *d_tracer = nullptr, *d_row = nullptr, *d_row_g = nullptr;
   double *data = nullptr, *picc = nullptr;
   GemmMatrix invcov;
   int32_t *g_count = nullptr, *g_tracer = nullptr, *g_term = nullptr, *g_var = nullptr;
@@ -29,7 +29,7 @@ struct TracerPtrs {
 
 struct VecArgs {
   TracerPtrs tp;
-  const int32_t *nterm, *par_index, *eastcoast, *d_tracer, *d_row, *g_count, *g_tracer, *g_term, *g_var;
+  const int32_t *nterm, *par_index, *eastcoast, *d_tracer, *d_row, *d_row_g, *g_count, *g_tracer, *g_term, *g_var;
   const double *scales, *data, *picc, *g_coef, *nuis;
   double* V;  // [ndata][ngauss+1][Bp]
   int Bp, ndata, ngauss;
@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(128) like_vectors_kernel(VecArgs a) {
   const size_t Bp = a.Bp;
   const int tr = a.d_tracer[d], nt = a.nterm[tr];
   const double* term = a.tp.terms[tr] + ((size_t)a.d_row[d] * nt) * Bp + b;
+  const double* termg = a.tp.terms[tr] + ((size_t)a.d_row_g[d] * nt) * Bp + b;  // rows of the marginalised derivatives
   const double f = a.tp.fg[tr][b];
   double par[17];
 #pragma unroll
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(128) like_vectors_kernel(VecArgs a) {
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const double c = a.g_coef[base + q];
-        if (c != 0.0) v += c * vars[a.g_var[base + q]] * term[(size_t)a.g_term[base + q] * Bp];
+        if (c != 0.0) v += c * vars[a.g_var[base + q]] * termg[(size_t)a.g_term[base + q] * Bp];
       }
     }
     out[(size_t)(1 + g) * Bp] = v;
@@ -237,7 +238,7 @@ int fill_vectors(const eftb_like* L, int Bp, const double* const* terms, const d
     a.tp.terms[t] = t < L->cfg.ntracer ? terms[t] : nullptr;
     a.tp.fg[t] = t < L->cfg.ntracer ? fg[t] : nullptr;
   }
-  a.nterm = L->nterm; a.par_index = L->par_index; a.eastcoast = L->eastcoast; a.d_tracer = L->d_tracer; a.d_row = L->d_row;
+  a.nterm = L->nterm; a.par_index = L->par_index; a.eastcoast = L->eastcoast; a.d_tracer = L->d_tracer; a.d_row = L->d_row; a.d_row_g = L->d_row_g;
   a.g_count = L->g_count; a.g_tracer = L->g_tracer; a.g_term = L->g_term; a.g_var = L->g_var; a.scales = L->scales;
   a.data = L->data; a.picc = L->picc; a.g_coef = L->g_coef; a.nuis = nuis; a.V = V; a.Bp = Bp; a.ndata = L->cfg.ndata;
   a.ngauss = L->cfg.ngauss;
@@ -269,6 +270,7 @@ int eftb_like_create(const eftb_like_config* cfg, const eftb_like_constants* h, 
   rc |= upload(&L->eastcoast, h->eastcoast, nt);
   rc |= upload(&L->d_tracer, h->d_tracer, nd);
   rc |= upload(&L->d_row, h->d_row, nd);
+  rc |= upload(&L->d_row_g, h->d_row_g ? h->d_row_g : h->d_row, nd);
   rc |= upload(&L->data, h->data, nd);
   rc |= upload(&L->picc, h->picc, nd);
   rc |= gemm_upload(h->invcov, 1, nd, nd, &L->invcov);
@@ -287,7 +289,7 @@ int eftb_like_create(const eftb_like_config* cfg, const eftb_like_constants* h, 
 
 void eftb_like_destroy(eftb_like* L) {
   if (!L) return;
-  void* ptrs[] = {L->nout, L->nterm, L->scales, L->par_index, L->eastcoast, L->d_tracer, L->d_row, L->data, L->picc,
+  void* ptrs[] = {L->nout, L->nterm, L->scales, L->par_index, L->eastcoast, L->d_tracer, L->d_row, L->d_row_g, L->data, L->picc,
                   L->g_count, L->g_tracer, L->g_term, L->g_var, L->g_coef, L->sigma_inv, L->sigma_inv_mu};
   for (void* p : ptrs) if (p) cudaFree(p);
   gemm_free(&L->invcov);

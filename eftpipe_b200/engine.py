@@ -272,6 +272,7 @@ class DeviceLikelihood:
         cst.sigma_inv = dp(spec["sigma_inv"] if spec["ngauss"] else np.zeros((ng, ng)))
         cst.sigma_inv_mu = dp(spec["sigma_inv_mu"] if spec["ngauss"] else np.zeros(ng))
         cst.mu_sigma_mu = float(spec["mu_sigma_mu"])
+        cst.d_row_g = ip(spec.get("d_row_g", spec["d_row"]))
         handle = C.c_void_p()
         _lib.check(self.lib.eftb_like_create(C.byref(cfg), C.byref(cst), C.byref(handle)), "eftb_like_create")
         self.handle, self.cfg = handle, cfg

@@ -119,6 +119,8 @@ def build_spec(tracers, data, invcov, gaussian=(), sigma_inv=None, mu=None, jeff
     nt = len(tracers)
     d_tracer = np.concatenate([np.full(len(t["rows"]), i, dtype=np.int32) for i, t in enumerate(tracers)])
     d_row = np.concatenate([np.asarray(t["rows"], dtype=np.int32) for t in tracers])
+    # rows the marginalised-parameter derivatives read (un-binned interpolated products: a different operator)
+    d_row_g = np.concatenate([np.asarray(t.get("rows_g", t["rows"]), dtype=np.int32) for t in tracers])
     picc = np.concatenate([np.asarray(t["picc"], float)[np.asarray(t["rows"])] for t in tracers])
     ndata = d_row.size
     data = np.asarray(data, float)
@@ -155,7 +157,7 @@ def build_spec(tracers, data, invcov, gaussian=(), sigma_inv=None, mu=None, jeff
         nterm=np.array([t["nterm"] for t in tracers], dtype=np.int32), scales=scales,
         par_index=np.arange(17 * nt, dtype=np.int32).reshape(nt, 17),
         eastcoast=np.array([int(t["basis"].counterform() == "eastcoast") for t in tracers], dtype=np.int32),
-        d_tracer=d_tracer, d_row=d_row, data=data, picc=picc, invcov=np.ascontiguousarray(invcov, float),
+        d_tracer=d_tracer, d_row=d_row, d_row_g=d_row_g, data=data, picc=picc, invcov=np.ascontiguousarray(invcov, float),
         g_count=g_count, g_tracer=g_tracer, g_term=g_term, g_var=g_var, g_coef=g_coef,
         sigma_inv=sigma_inv, sigma_inv_mu=sigma_inv @ mu, mu_sigma_mu=float(mu @ sigma_inv @ mu),
     )
@@ -242,13 +244,12 @@ class EFTLike(Marginalizable):
             {t: x[i] for i, t in enumerate(self.tracers)} if isinstance(x, list) else {t: x for t in self.tracers})
         self.data = data if set(data) == set(self.tracers) else {self.tracers[0]: data}
         self.chained, self.with_binning = as_dict(chained), as_dict(with_binning)
+        self.with_interp = as_dict(with_interp)
         self.binning = as_dict(binning or {})
         self.cov = cov if isinstance(cov, dict) else {"matrix": cov}
         self.marg, self.jeffreys = marg or {}, jeffreys
         self.likelihood_prefix = likelihood_prefix or "eftlike_"
         self.marg_param_prefix = marg_param_prefix
-        if not all(self.with_binning.values()):
-            raise NotImplementedError("the batched path evaluates binned theory only (with_binning: true)")
         self.initialize()
 
     def initialize(self):
@@ -272,11 +273,20 @@ class EFTLike(Marginalizable):
         self.invcov = np.linalg.inv(mask_covariance(cov, *args))
 
     def get_requirements(self):
-        """likelihood.py:386-432 (binned grids only)."""
-        reqs = {"nonlinear_Plk_grid": {}, "nonlinear_Plk_gaussian_grid": {}}
+        """likelihood.py:386-432: binned grid, interpolator (with the evaluation points, see EFTLSS.must_provide) or
+        the raw un-binned grid per tracer."""
+        reqs = {"nonlinear_Plk_grid": {}, "nonlinear_Plk_interpolator": {}, "nonlinear_Plk_gaussian_grid": {}}
         for t, m in self.minfodict.items():
-            req = {"ls": m.ls, "chained": self.chained[t], "binned": True, "binning": self.binning[t]}
-            reqs["nonlinear_Plk_grid"][t] = req
+            if self.with_binning[t]:
+                req = {"ls": m.ls, "chained": self.chained[t], "binned": True, "binning": self.binning[t]}
+                reqs["nonlinear_Plk_grid"][t] = req
+            elif self.with_interp[t]:
+                req = {"ls": m.ls, "chained": self.chained[t]}
+                reqs["nonlinear_Plk_interpolator"][t] = dict(req, kout=m.kout)
+                req = dict(req, binned=False)
+            else:
+                req = {"ls": m.ls, "chained": self.chained[t], "binned": False}
+                reqs["nonlinear_Plk_grid"][t] = req
             if self.marg:
                 reqs["nonlinear_Plk_gaussian_grid"][t] = req
         return {k: v for k, v in reqs.items() if v}
@@ -314,13 +324,26 @@ class EFTLike(Marginalizable):
         specs = []
         for t in self.tracers:
             m = self.minfodict[t]
-            info = theory.product_info(t, chained=self.chained[t], binned=True)
-            nk = info["nk"]
-            if nk != m.kout.size:
-                raise ValueError(f"{t}: theory bins ({nk}) do not match the data k-range ({m.kout.size})")
-            rows = flatten_rows(m.ls, nk, m.kout_mask)
-            specs.append(dict(basis=theory.bases[t], co=theory.commons[t], nout=info["nout"], nterm=info["nterm"],
-                              rows=rows, picc=info["picc"]))
+            info = theory.product_info(t, chained=self.chained[t], binned=self.with_binning[t])
+            nk, rows_g = info["nk"], None
+            if self.with_binning[t]:
+                if nk != m.kout.size or info.get("interp_nk") is not None:
+                    raise ValueError(f"{t}: theory bins ({nk}) do not match the data k-range ({m.kout.size})")
+                rows = flatten_rows(m.ls, nk, m.kout_mask)
+            elif self.with_interp[t]:  # likelihood.py:510-513, :541-544
+                if info.get("interp_nk") != m.kout.size:
+                    raise ValueError(f"{t}: the theory was not asked for the interpolator at this tracer's {m.kout.size} data points")
+                rows = flatten_rows(m.ls, nk, m.kout_mask)  # first half of each multipole's rows: PlkInterpolator
+                rows_g = rows + m.kout.size                 # second half: plain cubic interpolation
+            else:  # likelihood.py:515-516, :546-547: every node of the internal grid, no mask
+                if info.get("interp_nk") is not None:
+                    raise ValueError(f"{t}: raw-grid likelihood on a plan built for interpolated products")
+                rows = flatten_rows(m.ls, nk, None)
+            spec = dict(basis=theory.bases[t], co=theory.commons[t], nout=info["nout"], nterm=info["nterm"],
+                        rows=rows, picc=info["picc"])
+            if rows_g is not None:
+                spec["rows_g"] = rows_g
+            specs.append(spec)
         sig = self.sigma_inv if gaussian else None
         mu = self.mu_G if gaussian else None
         self.spec = build_spec(specs, self.data_vector, self.invcov, gaussian=gaussian, sigma_inv=sig, mu=mu,
@@ -335,7 +358,7 @@ class EFTLike(Marginalizable):
         th = self.provider
         terms, fs = [], []
         for t in self.tracers:
-            bm, f_bm = th.get_nonlinear_Plk_terms(t, chained=self.chained[t], binned=True)
+            bm, f_bm = th.get_nonlinear_Plk_terms(t, chained=self.chained[t], binned=self.with_binning[t])
             terms.append(bm)
             fs.append(f_bm)
         B = th.B

@@ -406,6 +406,17 @@ def binning_matrix(k, kout, accboost=1, decimals=2, kedges=None):
     return mat, keff, bmin, bmax
 
 
+def interp_matrices(k, kout):
+    """Operators of the un-binned ("with_interp") likelihood products on the internal nodes `k`:
+      S_png (nkout, Nk): `PlkInterpolator` (theory.py:75-106) - cubic interpolation of k P(k) through the nodes plus an
+                         inserted (0, 0) point, divided by kout;
+      S_pg  (nkout, Nk): the marginalised rows (likelihood.py:510-513) - the same WITHOUT the inserted origin."""
+    k, kout = np.asarray(k, float), np.asarray(kout, float)
+    S_png = cubic_matrix(np.hstack(([0.0], k)), kout)[:, 1:] * k[None, :] / kout[:, None]
+    S_pg = cubic_matrix(k, kout) * k[None, :] / kout[:, None]
+    return S_png, S_pg
+
+
 def fiber_matrix(k, Nl, fs, Dfc, ktrust=0.25):
     """(Nl, Nk, Nl, Nk) operator F of `FiberCollision.dPcorr` (pybird.py:1703-1756), so that the corrected spectrum
     is P + F.P: linear interpolation of P_l'(k) onto 1024 log-spaced q in [k_0, ktrust] (pybird.py:1714-1721),

@@ -52,17 +52,27 @@ class EFTLSS:
 
     # ---- requirements (theory.py:773-799) ----
     def must_provide(self, requirements: dict):
+        """`nonlinear_Plk_interpolator` (theory.py:785-790) takes one extra key here, `kout`: the abscissae the
+        consumer will evaluate the interpolator at.  The reference hands out a callable; on the batched path the
+        interpolation is a fixed operator composed into the tracer's projection (plan.interp_matrices), so the theory
+        has to know the points when the plan is built."""
         for product, per_tracer in requirements.items():
-            if product not in ("nonlinear_Plk_grid", "nonlinear_Plk_gaussian_grid"):
+            if product not in ("nonlinear_Plk_grid", "nonlinear_Plk_gaussian_grid", "nonlinear_Plk_interpolator"):
                 raise LoggedError(f"unsupported requirement {product} on the batched path")
             for tracer, req in per_tracer.items():
                 if tracer not in self.tracers:
                     raise LoggedError(f"unknown tracer {tracer}")
                 old = self.requirements.get(tracer)
                 new = dict(ls=sorted(req["ls"]), chained=bool(req.get("chained", False)),
-                           binned=bool(req.get("binned", False)), binning=req.get("binning"))
+                           binned=bool(req.get("binned", False)), binning=req.get("binning"), interp=None)
+                if product == "nonlinear_Plk_interpolator":
+                    if "kout" not in req:
+                        raise LoggedError("nonlinear_Plk_interpolator: the batched path needs the evaluation points `kout`")
+                    new["binned"], new["interp"] = False, np.asarray(req["kout"], float)
                 if old is not None and (old["ls"], old["chained"], old["binned"]) != (new["ls"], new["chained"], new["binned"]):
                     raise LoggedError("does not support multiple different product requirements per tracer")
+                if old is not None and new["interp"] is None:
+                    new["interp"] = old["interp"]
                 self.requirements[tracer] = new
         return self
 
@@ -120,6 +130,11 @@ class EFTLSS:
             if req["binned"]:
                 bo = Binning(co=co, **(req["binning"] or cfg.get("binning") or {}))
                 binm, keff = bo.matrix, bo.keff
+            elif req["interp"] is not None:
+                # un-binned interpolated products: rows [0, nkout) = PlkInterpolator (theory.py:75-106), rows
+                # [nkout, 2 nkout) = the plain cubic interpolation of the marginalised rows (likelihood.py:510-513)
+                keff = req["interp"]
+                binm = np.vstack(P.interp_matrices(co.k, keff))
             g = P.GridConfig(Nl=Nl, kmax=cfg.get("kmax", 0.3), with_NNLO=co.with_NNLO, optiresum=co.optiresum)
             proj = None
             if window is not None or binm is not None or req["chained"] or fiber is not None:
@@ -139,7 +154,8 @@ class EFTLSS:
             nl_out, nk = host.out_shape if proj is not None else (Nl, g.Nk)
             picc = host.picc_out if proj is not None else np.zeros(Nl * g.Nk)
             self.info.setdefault(name, {}).update(nout=nl_out * nk, nterm=g.nterm, nk=nk, picc=picc, kout=keff,
-                                                  ls=[2 * i for i in range(nl_out)], No=No)
+                                                  ls=[2 * i for i in range(nl_out)], No=No,
+                                                  interp_nk=None if req["interp"] is None else len(keff))
         return self
 
     def product_info(self, tracer, chained=False, binned=True):
@@ -165,12 +181,28 @@ class EFTLSS:
         bird = self._view(tracer)
         comp = self.bases[tracer].reduce_Plk(bird, params)
         info = self.info[tracer]
-        return info["ls"], info["kout"], comp.sum()
+        plk = comp.sum()
+        if info["interp_nk"] is not None:  # interpolated products: the PlkInterpolator rows
+            plk = plk[..., : info["interp_nk"]]
+        return info["ls"], info["kout"], plk
 
     def get_nonlinear_Plk_gaussian_grid(self, tracer, params, chained=False, binned=True):
         bird = self._view(tracer)
         info = self.info[tracer]
-        return info["ls"], info["kout"], self.bases[tracer].reduce_Plk_gaussian_table(bird, params)
+        table = self.bases[tracer].reduce_Plk_gaussian_table(bird, params)
+        if info["interp_nk"] is not None:  # the rows interpolated without the inserted origin
+            table = {name: v[..., info["interp_nk"]:] for name, v in table.items()}
+        return info["ls"], info["kout"], table
+
+    def get_nonlinear_Plk_interpolator(self, tracer, params, chained=False):
+        """theory.py:254-258: a `PlkInterpolator` over the tracer's un-binned grid (request `nonlinear_Plk_grid` with
+        `binned: False`).  A tracer whose plan was built for fixed evaluation points (`nonlinear_Plk_interpolator`
+        requirement with `kout`) already holds the interpolated values: use `get_nonlinear_Plk_grid` there."""
+        info = self.info[tracer]
+        if info["interp_nk"] is not None or self.requirements[tracer]["binned"]:
+            raise LoggedError("get_nonlinear_Plk_interpolator needs the un-binned grid of the tracer")
+        ls, k, plk = self.get_nonlinear_Plk_grid(tracer, params, chained=chained, binned=False)
+        return PlkInterpolator(ls[: plk.shape[-2]], k, plk)
 
     def _view(self, tracer):
         from .transformer import PlainBird
@@ -183,6 +215,36 @@ class EFTLSS:
         view = PlainBird(None, co, T, np.asarray(info["picc"]).reshape(nl_out, info["nk"]), self.B, False, f_bm)
         # the reduction honours co.No: chained products expose one multipole fewer (theory.py:599-602)
         return view
+
+
+class PlkInterpolator:
+    """theory.py:75-106 with a leading batch axis: cubic interpolation of k P_l(k) through the grid plus an inserted
+    (0, 0) point, extrapolating.  `Plk`: (..., len(ls), nk) torch tensor or array; `fn(l, k)` returns (..., nk') for
+    one multipole or (..., len(l), nk') for a list, like the reference.  The interpolation is the fixed operator
+    `plan.interp_matrices`; it is applied with one small matrix product (a convenience product, not the likelihood
+    path, which composes the same operator into the projection GEMM)."""
+
+    def __init__(self, ls, kgrid, Plk):
+        self.ls = list(ls)
+        self.kgrid = np.asarray(kgrid, float)
+        self.Plk = Plk
+
+    def fn(self, k):
+        S = P.interp_matrices(self.kgrid, np.atleast_1d(np.asarray(k, float)))[0]
+        if isinstance(self.Plk, np.ndarray):
+            return self.Plk @ S.T
+        import torch
+
+        return self.Plk @ torch.as_tensor(S.T, dtype=self.Plk.dtype, device=self.Plk.device)
+
+    def __call__(self, l, k):
+        l = [l] if isinstance(l, (int, np.integer)) else list(l)
+        try:
+            idx = [self.ls.index(ll) for ll in l]
+        except ValueError as ex:
+            raise ValueError(f"l={l} not in {self.ls}") from ex
+        out = self.fn(k)
+        return out[..., idx[0], :] if len(idx) == 1 else out[..., idx, :]
 
 
 def window_matrix(window: Window):

@@ -201,6 +201,10 @@ typedef struct {
   const double* sigma_inv;    /* [ngauss][ngauss]  (marginal.py:69-77) */
   const double* sigma_inv_mu; /* [ngauss] */
   double mu_sigma_mu;
+  const int32_t* d_row_g;     /* [ndata] or NULL (= d_row): row of the projected terms the marginalised-parameter
+                                 derivatives PG read.  Differs from d_row for the un-binned interpolated products,
+                                 where PNG goes through PlkInterpolator (theory.py:75-106, origin inserted) and PG
+                                 through a plain cubic interpolation (likelihood.py:510-513) */
 } eftb_like_constants;
 
 int eftb_like_create(const eftb_like_config*, const eftb_like_constants* host, eftb_like** out);

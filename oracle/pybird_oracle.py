@@ -746,3 +746,20 @@ def marginalized_logp(PNG, PG, data, invcov, mu_G=None, sigma_inv=None, jeffreys
 
 def hartlap(Nreal, ndata):
     return (Nreal - ndata - 2) / (Nreal - 1)  # likelihood.py:163-164
+
+
+# --------------------------------------------------------------------------------------
+# un-binned likelihood products (theory.py:75-106, likelihood.py:503-547)
+# --------------------------------------------------------------------------------------
+def plk_interpolator(kgrid, Plk):
+    """theory.py:75-106 `PlkInterpolator`: cubic interpolation of k P_l(k) through the nodes plus an inserted
+    (k, kP) = (0, 0) point, extrapolating; returns fn(k) -> P_l(k) of shape Plk.shape[:-1] + k.shape."""
+    kg = np.hstack(([0.0], kgrid))
+    P = np.insert(np.asarray(Plk, float), 0, 0.0, axis=-1)
+    tmp = interp1d(kg, kg * P, axis=-1, kind="cubic", bounds_error=False, fill_value="extrapolate")
+    return lambda k: tmp(k) / k
+
+
+def gaussian_row_interp(kgrid, plk, kout):
+    """likelihood.py:510-513: the marginalised-parameter rows are interpolated WITHOUT the inserted origin"""
+    return interp1d(kgrid, kgrid * np.asarray(plk, float), kind="cubic", axis=-1)(kout) / kout

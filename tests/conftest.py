@@ -49,3 +49,9 @@ def fiber_kat():
 def golden_opts():
     """reference outputs for optiresum / IRcutoff / LambdaIR variants (tests/golden/make_golden_options.py)"""
     return dict(np.load(os.path.join(GOLDEN, "options_resum.npz")))
+
+
+@pytest.fixture(scope="session")
+def interp_kat():
+    """reference outputs for the un-binned likelihood products (tests/golden/make_golden_interp.py)"""
+    return dict(np.load(os.path.join(GOLDEN, "interp_kat.npz")))

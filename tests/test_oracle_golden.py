@@ -104,3 +104,25 @@ def test_oracle_rejects_non_pd():
     PG = np.zeros((2, 4))
     with pytest.raises(RuntimeError):
         orc.marginalized_logp(np.ones(4), PG, np.zeros(4), np.eye(4))
+
+
+def test_unbinned_products_against_reference(interp_kat):
+    """theory.py:75-106 PlkInterpolator and likelihood.py:510-513, restated in the oracle and as the fixed operators
+    the CUDA path composes into its projection (plan.interp_matrices), against outputs of the live reference."""
+    import pybird_oracle as orc
+    from eftpipe_b200 import plan as P
+
+    g = interp_kat
+    k, kout = P.GridConfig(Nl=3).k, g["kout"]
+    S_png, S_pg = P.interp_matrices(k, kout)
+    assert np.abs(S_png - S_pg).max() > 1e-7  # the two interpolations really differ (inserted origin)
+    for i in range(g["Plk"].shape[0]):
+        png = orc.plk_interpolator(k, g["Plk"][i])(kout).reshape(-1)
+        assert np.max(np.abs(png - g["PNG_interp"][i])) <= 1e-12 * np.abs(g["PNG_interp"][i]).max()
+        assert np.max(np.abs((g["Plk"][i] @ S_png.T).reshape(-1) - g["PNG_interp"][i])) <= 1e-11 * np.abs(g["PNG_interp"][i]).max()
+        # marginalised rows: rebuild them from the raw-grid rows with the second operator
+        pg = (g["PG_raw"][i].reshape(-1, 3, k.size) @ S_pg.T).reshape(g["PG_interp"][i].shape)
+        scale = np.abs(g["PG_interp"][i]).max(axis=-1, keepdims=True)
+        assert np.max(np.abs(pg - g["PG_interp"][i]) / scale) <= 1e-11
+        lp = orc.marginalized_logp(g["PNG_interp"][i], g["PG_interp"][i], g["data"], g["invcov"], jeffreys=True)
+        assert abs(lp - g["logp_interp"][i]) <= 1e-10 * abs(g["logp_interp"][i])
