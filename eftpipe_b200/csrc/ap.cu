@@ -21,7 +21,8 @@ namespace {
 
 struct ApArgs {
   const double *coef, *Tin, *DA, *H, *k, *knot_lo, *basis, *mu, *wl;
-  double *Tout, *G;
+  double *Tout, *G;  // G: dense overflow operator [nb][Nk][NQ][wcap] (columns >= APPLY_WS of wide windows only)
+  double* Gc;       // compact operator [nb][Nk][NL][KP]: row (k, l) = [l'][c < APPLY_WS] zero padded - what ap_apply streams
   int2* meta;       // per (b, k): first B-spline index of the window, window length
   int b0, nb;       // this launch handles cosmologies [b0, b0 + nb)
   int Bp, Nk, nterm, nmu, nint, ap_st, wcap;
@@ -42,6 +43,8 @@ __device__ __forceinline__ double rsqrt_newton(double x) {
 }
 
 constexpr int GEOM_THREADS = 128;
+constexpr int APPLY_WS = 10;  // window columns of a node held in the compact operator (wider windows: rest in the dense overflow)
+__host__ __device__ constexpr int apply_kp(int NL) { return (NL * APPLY_WS + 3) / 4 * 4; }  // K of the per-node product, padded to k4 steps
 constexpr int APPLY_THREADS = 256;
 
 // Everything of the resampling geometry that depends on (cosmology, mu) only - NOT on the k node:
@@ -124,6 +127,12 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
   const int jlo = min(jfirst, jlast), jhi = max(jfirst, jlast);
   const int wn = jhi - jlo + 4;
   double* Grow = a.G + ((size_t)bl * a.Nk + ik) * NQ * a.wcap;
+  double* Gcrow = a.Gc + ((size_t)bl * a.Nk + ik) * NL * apply_kp(NL);
+  // column `col` of the (l, l') = q window: compact row [l][l' * APPLY_WS + col] or, beyond APPLY_WS, the dense overflow
+  auto put = [&](int q, int col, double v) {
+    if (col < APPLY_WS) Gcrow[(q / NL) * apply_kp(NL) + (q % NL) * APPLY_WS + col] = v;
+    else Grow[q * a.wcap + col] = v;
+  };
   if (active) a.meta[(size_t)bl * a.Nk + ik] = make_int2(jlo, wn);
   // k'(mu) is monotone, so the live window is only ever moved in the direction jfirst -> jlast (a k' that dips back
   // across a knot by rounding keeps its current interval: the spline is C2, the value agrees to ~1e-14).  Every
@@ -160,10 +169,10 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
     }
     const double kp = kq * wL[0];
     while (up && j < jhi && kp >= knots[j + 1]) {
-      double* g = Grow + (j - jlo);          // B-spline j has no support beyond this knot: retire its column
+      const int col = j - jlo;               // B-spline j has no support beyond this knot: retire its column
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        if (active) g[q * a.wcap] = acc[q][0];
+        if (active) put(q, col, acc[q][0]);
         acc[q][0] = acc[q][1]; acc[q][1] = acc[q][2]; acc[q][2] = acc[q][3]; acc[q][3] = 0.0;
       }
       ++j;
@@ -172,10 +181,10 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
       knot = knots[j];
     }
     while (down && j > jlo && kp < knot) {
-      double* g = Grow + (j + 3 - jlo);
+      const int col = j + 3 - jlo;
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        if (active) g[q * a.wcap] = acc[q][3];
+        if (active) put(q, col, acc[q][3]);
         acc[q][3] = acc[q][2]; acc[q][2] = acc[q][1]; acc[q][1] = acc[q][0]; acc[q][0] = 0.0;
       }
       --j;
@@ -194,92 +203,144 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
    }
   }
   if (!active) return;
-  double* g = Grow + (j - jlo);
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) g[q * a.wcap + r] = acc[q][r];
+    for (int r = 0; r < 4; ++r) put(q, j - jlo + r, acc[q][r]);
+  // zero padding of the compact rows: columns [wn, APPLY_WS) of every (l, l') and the K padding of every l
+  for (int c = wn; c < APPLY_WS; ++c)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) put(q, c, 0.0);
+#pragma unroll
+  for (int l = 0; l < NL; ++l)
+    for (int c = NL * APPLY_WS; c < apply_kp(NL); ++c) Gcrow[l * apply_kp(NL) + c] = 0.0;
 }
-
-constexpr int APPLY_WS = 16;  // window columns of a node staged in shared memory (wider windows: rest from global)
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
 }
 
-// One CTA per cosmology.  Thread = (k group, l, term row): the B-spline coefficients of the cosmology live in shared
-// memory ([l'][term][j], point-major from the Cinv GEMM), and the banded-operator rows of the NEXT k node of each
-// group are copied global -> shared with cp.async while the current node is contracted (double buffer), so every
-// operator word is fetched once per CTA and its DRAM/L2 latency is hidden behind the previous node.
-template <int NL>
-__global__ void __launch_bounds__(APPLY_THREADS) ap_apply_kernel(ApArgs a) {
-  constexpr int NQ = NL * NL;
-  extern __shared__ __align__(16) double sm[];
-  const int nslot = NL * a.nterm, ngrp = APPLY_THREADS / nslot;
-  double* coefs = sm;                                                   // [NL][nterm][Nk]
-  double* Gs = coefs + (size_t)NL * a.Nk * a.nterm;                     // [2][ngrp][NQ][APPLY_WS]
-  int2* metas = reinterpret_cast<int2*>(Gs + (size_t)2 * ngrp * NQ * APPLY_WS);  // [Nk]
-  const int bl = blockIdx.x, b = a.b0 + bl, tid = threadIdx.x;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int APPLY_SLACK = 16;  // zeroed doubles after the coefficient block: windows may run past the last row's end
+
+// One CTA per cosmology.  Its compact banded operator (Nk x NL rows of K = NL * APPLY_WS columns, written by ap_geom) and
+// its B-spline coefficients ([l'][term][j], point-major from the Cinv GEMM) are both contiguous in global memory: two TMA
+// bulk copies (cp.async.bulk + mbarrier complete_tx) bring them to shared memory - no per-element load instructions
+// (an earlier cp.async version was bound by L1TEX request traffic).  Then one warp per k node evaluates
+//   out[l][term] = sum_{(l', c)} G[k][l][(l', c)] * coef[l'][term][jlo(k) + c]
+// as an (8 x K)(K x 8 NT) DMMA product: rows l (NL of 8 used; the FP64 pipe is not the bound here, shared-memory and
+// issue traffic are, and the fragment form needs 3x fewer of both than per-output dot products).  Zero operator columns
+// beyond a window's length make out-of-window coefficient reads harmless (they stay inside the block + slack).
+template <int NL, int NT>  // NT: 8-term tiles, nterm <= 8 NT
+__global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
+  constexpr int NQ = NL * NL, KK = NL * APPLY_WS, KP = apply_kp(NL), NKS = KP / 4;
+  constexpr int NT_MAX = NT;
+  extern __shared__ __align__(128) double sm[];
+  const int nslot = NL * a.nterm;
+  const uint32_t gbytes = (uint32_t)((size_t)a.Nk * NL * KP * sizeof(double)), cbytes = (uint32_t)((size_t)nslot * a.Nk * sizeof(double));
+  double* Gs = sm;                                                      // [Nk][NL][KP]
+  double* coefs = Gs + (size_t)a.Nk * NL * KP;                          // [NL][nterm][Nk] + slack
+  int2* metas = reinterpret_cast<int2*>(coefs + (size_t)nslot * a.Nk + APPLY_SLACK);  // [Nk]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(metas + a.Nk);
+  const int bl = blockIdx.x, b = a.b0 + bl, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t Bp = a.Bp;
-  for (int i = tid; i < a.Nk; i += APPLY_THREADS) metas[i] = a.meta[(size_t)bl * a.Nk + i];
-  {  // B-spline coefficients, point-major [b][l][term][j]: contiguous, coalesced
-    const double* cb = a.coef + (size_t)b * NL * a.Nk * a.nterm;
-#pragma unroll 8
-    for (int i = tid; i < NL * a.Nk * a.nterm; i += APPLY_THREADS) coefs[i] = cb[i];
+  const double* Gb = a.G + (size_t)bl * a.Nk * NQ * a.wcap;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(gbytes + cbytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(Gs)),
+                 "l"(a.Gc + (size_t)bl * a.Nk * NL * KP), "r"(gbytes), "r"(smem_u32(bar))
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(coefs)),
+                 "l"(a.coef + (size_t)b * nslot * a.Nk), "r"(cbytes), "r"(smem_u32(bar))
+                 : "memory");
   }
+  for (int i = tid; i < a.Nk; i += APPLY_THREADS) metas[i] = a.meta[(size_t)bl * a.Nk + i];
+  if (tid < APPLY_SLACK) coefs[(size_t)nslot * a.Nk + tid] = 0.0;
   const double qperp = a.DA[b] / a.da_fid, qpar = a.h_fid / a.H[b];
   const double norm = 1.0 / (qperp * qperp * qpar);  // pybird.py:1611
-  __syncthreads();
+  __syncthreads();  // metas, slack and the barrier initialisation are visible to every thread
+  {
+    uint32_t ok;
+    do {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+                   : "=r"(ok) : "r"(smem_u32(bar)) : "memory");
+    } while (!ok);
+  }
 
-  const int grp = tid / nslot, slot = tid - grp * nslot;
-  const bool active = grp < ngrp;
-  const int l = active ? slot / a.nterm : 0, i = active ? slot - l * a.nterm : 0;
-  const bool apply = a.ap_st || i < 21 || i >= 24;  // Pstl only with APst (pybird.py:1618-1619)
-  const double* Gb = a.G + (size_t)bl * a.Nk * NQ * a.wcap;
-  auto prefetch = [&](int ik, int buf) {
-    if (active && ik < a.Nk) {
-      const int wn = min(metas[ik].y, APPLY_WS);
-      const double* Gk = Gb + (size_t)ik * NQ * a.wcap;
-      double* dst = Gs + (size_t)((buf * ngrp + grp) * NQ) * APPLY_WS;
-      for (int e = slot; e < NQ * APPLY_WS; e += nslot) {
-        const int q = e / APPLY_WS, c = e - q * APPLY_WS;
-        if (c < wn) cp_async8(dst + e, Gk + (size_t)q * a.wcap + c);
-      }
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
-  };
-  prefetch(grp, 0);
-  asm volatile("cp.async.wait_group 0;\n" ::);
-  __syncthreads();
-  const int niter = (a.Nk + ngrp - 1) / ngrp;
-  for (int it = 0; it < niter; ++it) {
-    const int buf = it & 1, ik = grp + it * ngrp;
-    prefetch(ik + ngrp, buf ^ 1);
-    if (active && ik < a.Nk) {
-      const size_t o = ((size_t)(l * a.Nk + ik) * a.nterm + i) * Bp + b;
-      if (!apply) {
-        a.Tout[o] = a.Tin[o];
-      } else {
-        const int2 mw = metas[ik];
-        const double* gq = Gs + (size_t)((buf * ngrp + grp) * NQ + l * NL) * APPLY_WS;
-        const double* cf = coefs + (size_t)i * a.Nk + mw.x;
-        const int wn = min(mw.y, APPLY_WS);
-        double acc = 0.0;
+  // fragment roles: A[row = r][col = c4] = G row of multipole l = r; B[row = c4][col = r] = coefficient of term 8 t + r.
+  // Everything that does not depend on the node is hoisted: K-index offsets into the coefficient block, term offsets,
+  // output offsets and flags.  Padded K columns and padded term columns read valid (finite) coefficients: they meet zero
+  // operator columns or land in accumulator columns that are never stored.
+  const int r = lane >> 2, c4 = lane & 3;
+  const int lstride = a.nterm * a.Nk;
+  int boff[NKS];  // K index kappa = 4 s + c4  ->  (l', c)  ->  l' * lstride + c
 #pragma unroll
-        for (int lp = 0; lp < NL; ++lp)
-          for (int c = 0; c < wn; ++c) acc = fma(gq[lp * APPLY_WS + c], cf[(size_t)lp * a.nterm * a.Nk + c], acc);
-        if (mw.y > APPLY_WS) {  // strong AP distortion: the columns beyond the staged window straight from global
-          const double* Gk = Gb + ((size_t)ik * NQ + l * NL) * a.wcap;
+  for (int s = 0; s < NKS; ++s) {
+    const int kap = 4 * s + c4, lp = kap / APPLY_WS;
+    boff[s] = kap < KK ? lp * lstride + (kap - lp * APPLY_WS) : 0;
+  }
+  int ioff[NT_MAX];          // B operand: term 8 t + r (clamped)
+  size_t ooff[NT_MAX][2];    // C columns: term i = 8 t + 2 c4 + h  ->  i * Bp
+  unsigned store = 0, copy = 0;  // per (t, h): result stored / Pstl row passed through unchanged (no APst, pybird.py:1618-1619)
+#pragma unroll
+  for (int t = 0; t < NT_MAX; ++t) {
+    ioff[t] = min(8 * t + r, a.nterm - 1) * a.Nk;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 8 * t + 2 * c4 + h;
+      ooff[t][h] = (size_t)i * Bp;
+      const bool valid = i < a.nterm && r < NL;
+      const bool st = !a.ap_st && i >= 21 && i < 24;
+      if (valid && !st) store |= 1u << (2 * t + h);
+      if (valid && st) copy |= 1u << (2 * t + h);
+    }
+  }
+  const double* grow0 = Gs + (size_t)(r < NL ? r : 0) * KP + c4;
+  for (int ik = warp; ik < a.Nk; ik += APPLY_THREADS / 32) {
+    const int2 mw = metas[ik];
+    const double* grow = grow0 + (size_t)ik * NL * KP;
+    const double* cbase = coefs + mw.x;
+    double acc[NT_MAX][2];
+#pragma unroll
+    for (int t = 0; t < NT_MAX; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < NKS; ++s) {
+      const double af = r < NL ? grow[4 * s] : 0.0;
+#pragma unroll
+      for (int t = 0; t < NT_MAX; ++t) dmma884(acc[t][0], acc[t][1], af, cbase[ioff[t] + boff[s]]);
+    }
+    // C[row = r (multipole)][col = 2 c4 + h (term in tile)]
+    const size_t nodebase = ((size_t)(r * a.Nk + ik) * a.nterm) * Bp + b;
+    if (mw.y > APPLY_WS && r < NL) {  // strong AP distortion: the columns beyond the compact window from the dense overflow
+      const double* Gk = Gb + ((size_t)ik * NQ + r * NL) * a.wcap;
+#pragma unroll
+      for (int t = 0; t < NT_MAX; ++t)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (!((store >> (2 * t + h)) & 1u)) continue;
+          const double* cg = a.coef + ((size_t)b * nslot + 8 * t + 2 * c4 + h) * a.Nk + mw.x;
           for (int c = APPLY_WS; c < mw.y; ++c)
 #pragma unroll
-            for (int lp = 0; lp < NL; ++lp) acc = fma(__ldg(Gk + lp * a.wcap + c), cf[(size_t)lp * a.nterm * a.Nk + c], acc);
+            for (int lp = 0; lp < NL; ++lp)
+              acc[t][h] = fma(__ldg(Gk + lp * a.wcap + c), __ldg(cg + (size_t)lp * lstride + c), acc[t][h]);
         }
-        a.Tout[o] = norm * acc;
-      }
     }
-    asm volatile("cp.async.wait_group 0;\n" ::);
-    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < NT_MAX; ++t)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const size_t o = nodebase + ooff[t][h];
+        if ((store >> (2 * t + h)) & 1u) a.Tout[o] = norm * acc[t][h];
+        else if ((copy >> (2 * t + h)) & 1u) a.Tout[o] = a.Tin[o];
+      }
   }
 }
 
@@ -296,9 +357,8 @@ int run(ApArgs a, int B, cudaStream_t s, int phase) {
   const int geom_cos = (GEOM_THREADS - 2 + a.Nk) / a.Nk + 1;  // cosmologies a CTA's GEOM_THREADS consecutive (b, k) nodes can touch
   const int mu_tile = a.nmu < GEOM_MU_TILE ? a.nmu : GEOM_MU_TILE;
   const size_t smem_g = sizeof(double) * (a.nint + (size_t)a.nint * 16 + 1 + (size_t)geom_cos * mu_tile * AP_TAB);
-  const size_t smem_a = sizeof(double) * ((size_t)NL * a.Nk * a.nterm + (size_t)2 * (APPLY_THREADS / (NL * a.nterm)) * NL * NL * APPLY_WS) +
-                        sizeof(int2) * a.Nk;
-  if (NL * a.nterm > APPLY_THREADS || smem_g > 200 * 1024 || smem_a > 200 * 1024) {
+  const size_t smem_a = sizeof(double) * ((size_t)NL * a.nterm * a.Nk + APPLY_SLACK + (size_t)a.Nk * NL * apply_kp(NL)) + sizeof(int2) * a.Nk + 16;
+  if (a.nterm > 32 || (NL * a.nterm * a.Nk) % 2 || smem_g > 200 * 1024 || smem_a > 200 * 1024) {  // bulk copies move 16-byte units
     eftb_set_error("ap: unsupported sizes nmu=%d nterm=%d Nk=%d", a.nmu, a.nterm, a.Nk);
     return EFTB_ERR_ARG;
   }
@@ -308,7 +368,8 @@ int run(ApArgs a, int B, cudaStream_t s, int phase) {
     conf_g = smem_g;
   }
   if (smem_a > conf_a) {
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(ap_apply_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    EFTB_CUDA_CHECK(cudaFuncSetAttribute(ap_apply_kernel<NL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    EFTB_CUDA_CHECK(cudaFuncSetAttribute(ap_apply_kernel<NL, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
     conf_a = smem_a;
   }
   const int chunk = a.nb;  // capacity of the scratch, set by the caller
@@ -321,7 +382,8 @@ int run(ApArgs a, int B, cudaStream_t s, int phase) {
       EFTB_LAUNCH_CHECK();
     }
     if (phase & EFTB_PHASE_SECOND) {
-      ap_apply_kernel<NL><<<a.nb, APPLY_THREADS, smem_a, s>>>(a);
+      if (a.nterm <= 24) ap_apply_kernel<NL, 3><<<a.nb, APPLY_THREADS, smem_a, s>>>(a);
+      else ap_apply_kernel<NL, 4><<<a.nb, APPLY_THREADS, smem_a, s>>>(a);
       EFTB_LAUNCH_CHECK();
     }
   }
@@ -333,7 +395,8 @@ int run(ApArgs a, int B, cudaStream_t s, int phase) {
 size_t ap_scratch_doubles(const eftb_plan* p, int B) {
   const eftb_config& c = p->cfg;
   const size_t chunk = ap_chunk(c, B);
-  return chunk * c.Nk * c.Nl * c.Nl * c.Nk + chunk * c.Nk;  // G | meta (int2 = 8 bytes each)
+  // dense overflow G | meta (int2 = 8 bytes each) | pad to 16 bytes | compact operator Gc
+  return chunk * c.Nk * c.Nl * c.Nl * c.Nk + chunk * c.Nk + 1 + chunk * c.Nk * c.Nl * apply_kp(c.Nl);
 }
 
 int ap_chunk_count(const eftb_plan* p, int B) {
@@ -356,6 +419,10 @@ int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const doubl
   a.b0 = 0;
   a.G = scratch;
   a.meta = reinterpret_cast<int2*>(scratch + (size_t)a.nb * c.Nk * c.Nl * c.Nl * c.Nk);
+  {
+    const size_t off = (size_t)a.nb * c.Nk * c.Nl * c.Nl * c.Nk + (size_t)a.nb * c.Nk;
+    a.Gc = scratch + off + (off & 1);  // 16-byte aligned (the scratch base is): TMA bulk copies read it
+  }
   if (c.Nl == 3) return run<3>(a, B, s, phase);
   if (c.Nl == 2) return run<2>(a, B, s, phase);
   eftb_set_error("ap: unsupported Nl=%d", c.Nl);

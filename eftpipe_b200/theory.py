@@ -164,14 +164,47 @@ class EFTLSS:
     # ---- per batch (theory.py:557-609) ----
     def calculate(self, cosmo: dict):
         """cosmo[tracer] = dict(pkh=(B, 200) on kh = logspace(-5, 0, 200), f=, DA=, H= (B,) [, rdrag, h])."""
-        self._state = {}
+        self._state, self.derived = {}, {}
         for name, dp in self.plans.items():
             c = cosmo[name]
             pm, bm = dp.eval_terms(c["pkh"], c["f"], c.get("DA"), c.get("H"), want_bm=True, want_pm=False)
             f_bm = dp.to_batch_minor(c["f"])[0]
             self._state[name] = (bm, f_bm)
             self.B = bm.shape[-1] if not hasattr(c["pkh"], "shape") else c["pkh"].shape[0]
+            self._derive(name, c)
         return self
+
+    def _derive(self, name, c):
+        """derived parameters of theory.py:620-648: `{prefix}alperp, alpara, fz, fsigma8_z` per point"""
+        prefix = self.tracers[name].get("prefix")
+        prefix = name + "_" if prefix is None else prefix
+        apo = self.info.get(name, {}).get("ap")
+        if apo is not None and c.get("DA") is not None and c.get("H") is not None:
+            qperp, qpar = np.asarray(_host(c["DA"]), float) / apo.DA, apo.H / np.asarray(_host(c["H"]), float)  # pybird.py:1560-1562
+            if all(x is not None for x in (apo.rdrag_AP, apo.h_AP, c.get("rdrag"), c.get("h"))):
+                ratio = (apo.rdrag_AP * apo.h_AP) / (np.asarray(_host(c["rdrag"]), float) * np.asarray(_host(c["h"]), float))
+                qperp, qpar = qperp * ratio, qpar * ratio  # pybird.py:1576-1578
+            self.derived[prefix + "alperp"], self.derived[prefix + "alpara"] = qperp, qpar
+        else:
+            self.derived[prefix + "alperp"] = self.derived[prefix + "alpara"] = -1
+        self.derived[prefix + "fz"] = np.asarray(_host(c["f"]), float)
+        if c.get("fsigma8_z") is not None:
+            self.derived[prefix + "fsigma8_z"] = np.asarray(_host(c["fsigma8_z"]), float)
+
+    def get_bird_component(self, tracer, params, chained=False, binned=True):
+        """(ls, k, BirdComponent) - theory.py:265-266, :844-847"""
+        info = self.info[tracer]
+        return info["ls"], info["kout"], self.bases[tracer].reduce_Plk(self._view(tracer), params)
+
+    def get_eft_params_values_dict(self, tracer, params):
+        """the tracer's own EFT parameters out of `params` (theory.py:262-263)"""
+        basis = self.bases[tracer]
+        names = list(basis.non_gaussian_params()) + list(basis.gaussian_params())
+        return {n: params[n] for n in names if n in params}
+
+    def get_snapshots(self, tracer):
+        raise LoggedError("snapshots are taken on the stage-by-stage path (pybird.Bird.create_snapshot); the fused "
+                          "batched pipeline keeps no intermediate term arrays")
 
     def get_nonlinear_Plk_terms(self, tracer, chained=False, binned=True):
         return self._state[tracer]
@@ -245,6 +278,10 @@ class PlkInterpolator:
             raise ValueError(f"l={l} not in {self.ls}") from ex
         out = self.fn(k)
         return out[..., idx[0], :] if len(idx) == 1 else out[..., idx, :]
+
+
+def _host(x):
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else x
 
 
 def window_matrix(window: Window):

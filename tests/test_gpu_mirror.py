@@ -231,6 +231,16 @@ def test_multitracer_likelihood_against_oracle(dr16_setup, dr16):
     assert like.ndata == 142 and len(like.gaussian_names) == 14
     assert like.hartlap == pytest.approx((1000 - 142 - 2) / 999)
     th.calculate(S["cosmo"])
+    # derived parameters of theory.py:620-648 and the per-tracer parameter view (theory.py:262-263)
+    from eftpipe_b200 import synthetic as syn
+
+    bl = S["batches"]["LRG_NGC"]
+    np.testing.assert_allclose(th.derived["LRG_NGC_alperp"], bl.DA / syn.angular_distance(0.307115, 0.696), rtol=1e-12)
+    np.testing.assert_allclose(th.derived["LRG_NGC_alpara"], syn.hubble(0.307115, 0.696) / bl.H, rtol=1e-12)
+    np.testing.assert_allclose(th.derived["ELG_NGC_fz"], S["batches"]["ELG_NGC"].f)
+    assert set(th.get_eft_params_values_dict("LRG_NGC", S["params"])) == {"LRG_NGC_b1", "LRG_NGC_b2", "LRG_NGC_b4"}
+    ls, kk, comp = th.get_bird_component("LRG_NGC", {k: v for k, v in S["params"].items() if k.startswith("LRG")})
+    assert ls == [0, 2, 4] and kk.size == 18 and tuple(comp.sum().shape) == (S["B"], 3, 18)
     res = like.calculate(S["params"], want_bestfit=True)
     logp = _np(res["logp"])
     png, pg = like.PNG_PG(S["params"])
