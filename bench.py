@@ -179,7 +179,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -414,7 +414,7 @@ def run_ours(args):
                                           f"processes (host has {cores} cores); oracle/pybird_oracle.py restatement of the "
                                           "reference numpy path"}
         line["logp_check"]["max_rel_err_vs_oracle"] = float(np.max(np.abs(got - ref_logp) / np.abs(ref_logp)))
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -528,7 +528,7 @@ def run_multitracer(args):
                            "launch": "one CUDA graph replay per step" if graph is not None else "eager launches"},
                 "clocks": clocks, "setup_s": round(t_setup, 1),
                 "logp_check": {"finite": bool(torch.isfinite(logp).all()), "status_nonzero": int((status != 0).sum())}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -639,7 +639,27 @@ from eftpipe_b200 import plan as P  # noqa: E402  (host-only module; used in sta
 NCU_DRAM_BYTES_PER_POINT = {"resum": 61.0e6 / 1024, "antidiag": 113.9e6 / 1024, "spectral": 543.3e6 / 1024, "ap": 158.9e6 / 1024}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print to file descriptor 1 (NCCL's version banner, for one) goes to stderr from here on; the
+    one JSON line of the contract is written to the original stdout by `emit`."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
