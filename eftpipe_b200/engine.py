@@ -41,6 +41,101 @@ def capture_graph(fn, warmup=2):
     return graph, out
 
 
+class HostPipeline:
+    """Double-buffered host -> device -> host driver for a fixed-shape evaluation `fn(*device_inputs) -> device outputs`
+    (what an MCMC / importance-sampling loop that produces its points on the host needs to keep the GPU busy).
+
+    Per slot: ONE packed pinned input buffer (`host_in(slot)` returns the named views to fill), one device copy of it,
+    a CUDA graph of `fn` on views of that device buffer, pinned output buffers.  `submit(slot)` enqueues the slot's
+    H2D copy on a copy stream, the graph replay on the current stream and the D2H copies on a second copy stream, so
+    the copies of step i+1 / i-1 overlap the kernels of step i; `wait(slot)` blocks until the slot's outputs are on the
+    host.  Slots share the library workspaces, so replays are serialised on the compute stream by construction."""
+
+    def __init__(self, fn, shapes: dict, nslots=2, use_graph=True):
+        torch = _lib.require_cuda()
+        self.use_graph = use_graph
+        self.torch, self.names = torch, list(shapes)
+        sizes = [int(np.prod(shapes[n])) for n in self.names]
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        self.copy_in, self.copy_out = torch.cuda.Stream(), torch.cuda.Stream()
+        self.h_in, self.d_in, self.graphs, self.d_out, self.h_out = [], [], [], [], []
+        self.ev_h2d, self.ev_comp, self.ev_d2h = [], [], []
+        view = lambda buf: {n: buf[offs[i] : offs[i + 1]].view(*shapes[n]) for i, n in enumerate(self.names)}
+        for _ in range(nslots):
+            h = torch.empty(int(offs[-1]), dtype=torch.float64).pin_memory()
+            d = torch.empty(int(offs[-1]), dtype=torch.float64, device="cuda")
+            self.h_in.append((h, view(h)))
+            self.d_in.append((d, view(d)))
+        self._fn = fn
+        self._captured = False
+
+    def host_in(self, slot):
+        """dict name -> pinned host view to fill before `submit(slot)`"""
+        return self.h_in[slot][1]
+
+    def _capture(self):
+        torch = self.torch
+        for slot in range(len(self.h_in)):
+            self.d_in[slot][0].copy_(self.h_in[slot][0])
+        torch.cuda.synchronize()
+        for slot in range(len(self.h_in)):
+            dv = self.d_in[slot][1]
+            if self.use_graph:
+                graph, outs = capture_graph(lambda dv=dv: self._fn(**dv))
+            else:  # eager launches (profiling): the outputs are re-produced by every submit
+                graph, outs = None, self._fn(**dv)
+            outs = list(outs) if isinstance(outs, (tuple, list)) else [outs]
+            self.graphs.append(graph)
+            self.d_out.append(outs)
+            self.h_out.append([torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs])
+            self.ev_h2d.append(torch.cuda.Event())
+            self.ev_comp.append(torch.cuda.Event())
+            self.ev_d2h.append(torch.cuda.Event())
+        self._captured = True
+
+    def submit(self, slot):
+        torch = self.torch
+        if not self._captured:
+            self._capture()
+        compute = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_in):
+            self.copy_in.wait_event(self.ev_comp[slot])  # the previous replay of this slot has consumed its inputs
+            self.d_in[slot][0].copy_(self.h_in[slot][0], non_blocking=True)
+            self.ev_h2d[slot].record(self.copy_in)
+        compute.wait_event(self.ev_h2d[slot])
+        compute.wait_event(self.ev_d2h[slot])            # ... and its previous outputs are already on the host
+        if self.graphs[slot] is not None:
+            self.graphs[slot].replay()
+        else:
+            outs = self._fn(**self.d_in[slot][1])
+            self.d_out[slot] = list(outs) if isinstance(outs, (tuple, list)) else [outs]
+        self.ev_comp[slot].record(compute)
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(self.ev_comp[slot])
+            for h, d in zip(self.h_out[slot], self.d_out[slot]):
+                h.copy_(d, non_blocking=True)
+            self.ev_d2h[slot].record(self.copy_out)
+
+    def wait(self, slot):
+        """block until the outputs of the last `submit(slot)` are in `outputs(slot)`"""
+        self.ev_d2h[slot].synchronize()
+        return self.h_out[slot]
+
+    def join(self):
+        """make the current stream wait for every outstanding read-back (for timing with stream events)"""
+        compute = self.torch.cuda.current_stream()
+        for ev in self.ev_d2h:
+            compute.wait_event(ev)
+
+    @property
+    def h2d_bytes(self):
+        return self.h_in[0][0].numel() * 8
+
+    @property
+    def d2h_bytes(self):
+        return sum(h.numel() * h.element_size() for h in self.h_out[0])
+
+
 class DevicePlan:
     """One tracer's pipeline on the current CUDA device."""
 
