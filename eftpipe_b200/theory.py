@@ -167,6 +167,8 @@ class EFTLSS:
         self._state, self.derived = {}, {}
         for name, dp in self.plans.items():
             c = cosmo[name]
+            if not self.tracers[name].get("with_RSD", True):  # theory.py:566-567
+                c = dict(c, f=np.zeros(np.shape(_host(c["f"]))))
             pm, bm = dp.eval_terms(c["pkh"], c["f"], c.get("DA"), c.get("H"), want_bm=True, want_pm=False)
             f_bm = dp.to_batch_minor(c["f"])[0]
             self._state[name] = (bm, f_bm)
