@@ -396,7 +396,8 @@ size_t ap_scratch_doubles(const eftb_plan* p, int B) {
   const eftb_config& c = p->cfg;
   const size_t chunk = ap_chunk(c, B);
   // dense overflow G | meta (int2 = 8 bytes each) | pad to 16 bytes | compact operator Gc
-  return chunk * c.Nk * c.Nl * c.Nl * c.Nk + chunk * c.Nk + 1 + chunk * c.Nk * c.Nl * apply_kp(c.Nl);
+  const size_t n = chunk * c.Nk * c.Nl * c.Nl * c.Nk + chunk * c.Nk + 1 + chunk * c.Nk * c.Nl * apply_kp(c.Nl);
+  return (n + 1) & ~(size_t)1;  // whole 16-byte units: the buffers that follow in the workspace are TMA sources too
 }
 
 int ap_chunk_count(const eftb_plan* p, int B) {

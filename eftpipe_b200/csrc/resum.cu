@@ -196,20 +196,47 @@ __device__ __forceinline__ void resum_body(const ResumArgs& a) {
     Xs[s] = ok ? a.F[(size_t)(a.row_x + s) * Bp + b] : 0.0;
     Ys[s] = ok ? a.F[(size_t)(a.row_y + s) * Bp + b] : 0.0;
   }
-  {  // Cr is point-major [b][l][ncr][Ns]: contiguous, coalesced
-    const double* crb = a.Cr + (size_t)b * NL * a.ncr * a.Ns;
+  const double* crb = a.Cr + (size_t)b * NL * a.ncr * a.Ns;               // point-major [b][l][ncr][Ns]
+  const double* qf = a.Qf + (size_t)b * (2 * NQH) + (size_t)IA * NQH;     // Q^{ll'}(f) of this cosmology (resum_q_kernel)
+  // The rows this half contracts with are contiguous per multipole and, like the Q table, whole 16-byte units: TMA bulk
+  // copies (one thread issues NL + 1 of them, one mbarrier wait) instead of ~30 dependent load/store pairs per thread.
+  const bool bulk = a.NsP == a.Ns && ((size_t)nrow * a.Ns) % 2 == 0 && ((size_t)a.ncr * a.Ns) % 2 == 0 && (row0 * a.Ns) % 2 == 0;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Cs + (size_t)NL * nrow * a.NsP);
+  if (bulk) {
+    if (tid == 0) {
+      const uint32_t cbytes = (uint32_t)((size_t)nrow * a.Ns * sizeof(double)), qbytes = (uint32_t)(NQH * sizeof(double));
+      const uint32_t bar32 = (uint32_t)__cvta_generic_to_shared(bar);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar32));
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar32), "r"(NL * cbytes + qbytes) : "memory");
+#pragma unroll
+      for (int l = 0; l < NL; ++l)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(Cs + (size_t)l * nrow * a.NsP)),
+                     "l"(crb + ((size_t)l * a.ncr + row0) * a.Ns), "r"(cbytes), "r"(bar32)
+                     : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(Qs)),
+                   "l"(qf), "r"(qbytes), "r"(bar32)
+                   : "memory");
+    }
+  } else {
 #pragma unroll 8
     for (int i = tid; i < NL * nrow * a.NsP; i += RS_THREADS) {
       const int s = i % a.NsP, r = (i / a.NsP) % nrow, l = i / (a.NsP * nrow);
       Cs[i] = s < a.Ns ? crb[((size_t)l * a.ncr + row0 + r) * a.Ns + s] : 0.0;
     }
-  }
-  {  // Q^{ll'}(f) of this cosmology, expanded by resum_q_kernel
-    const double* qf = a.Qf + (size_t)b * (2 * NQH) + (size_t)IA * NQH;
 #pragma unroll
     for (int i = tid; i < NQH; i += RS_THREADS) Qs[i] = qf[i];
   }
-  __syncthreads();
+  __syncthreads();  // X, Y (and the fallback copies) are in place; the barrier initialisation is visible
+  if (bulk) {
+    uint32_t ok;
+    do {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+                   : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+    } while (!ok);
+  }
 
   const int ntask = NL * a.Nkr, nchunk = a.NsP / RS_C;
   const int rem = ntask % RS_THREADS;
@@ -398,7 +425,7 @@ int run(const ResumArgs& a, cudaStream_t s, int phase) {
     EFTB_LAUNCH_CHECK();
   }
   if (!(phase & EFTB_PHASE_SECOND)) return EFTB_OK;
-  size_t smem = sizeof(double) * ((size_t)NL * NL * NIR * RS_SLOTS + 2 * a.NsP + (size_t)NL * (a.ncr - 1) * a.NsP);
+  size_t smem = sizeof(double) * ((size_t)NL * NL * NIR * RS_SLOTS + 2 * a.NsP + (size_t)NL * (a.ncr - 1) * a.NsP + 2);  // + mbarrier
   const size_t smem_lin = sizeof(double) * ((size_t)NIR * rl_pitch(a.NsP) + 2 * NL * a.NsP + (size_t)a.KPAD * NIR +
                                             (size_t)a.nslots * NL * a.KPAD + (size_t)NL * NL * NIR * RS_SLOTS);
   if (smem_lin > smem) smem = smem_lin;
