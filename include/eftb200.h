@@ -10,6 +10,9 @@
  *  - plain C, no torch types; all data pointers are DEVICE pointers owned by the caller unless a
  *    parameter is documented as host memory; the library owns only the immutable plan constants.
  *  - every call enqueues work on `stream` (a cudaStream_t passed as void*) and does not synchronise.
+ *    eftb_eval_terms additionally forks part of its work onto a plan-owned side stream and joins it back into
+ *    `stream` with events before it returns (capturable into a CUDA graph): one eftb_eval_terms call at a time per
+ *    plan; the stage entry points may run concurrently on one plan with distinct workspaces.
  *  - return value: 0 on success, negative eftb_status on error (never throws, never aborts);
  *    per-point numerical failures (non positive-definite F2) are reported in the `status` array.
  *  - "batch-minor" arrays: logical shape [rows][Bp] with the cosmology index fastest and
