@@ -167,6 +167,8 @@ class EFTLSS:
         self._state, self.derived = {}, {}
         for name, dp in self.plans.items():
             c = cosmo[name]
+            if hasattr(c, "Pkh"):  # a boltzmann.BoltzmannExtractor (theory.py:559-565)
+                c = c.cosmo()
             if not self.tracers[name].get("with_RSD", True):  # theory.py:566-567
                 c = dict(c, f=np.zeros(np.shape(_host(c["f"]))))
             pm, bm = dp.eval_terms(c["pkh"], c["f"], c.get("DA"), c.get("H"), want_bm=True, want_pm=False)

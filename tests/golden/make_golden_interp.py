@@ -115,3 +115,26 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def linear_power_file_golden():
+    """reference `LinearPowerFile` (boltzmann.py:246-309) on a synthetic template that starts above k = 1e-5"""
+    import tempfile
+
+    ref = refload.load()
+    bz = importlib.import_module("eftpipe.boltzmann")
+    b = synthetic.make_batch(1, 0.7, seed=3)
+    k = np.logspace(-4, 0.3, 300)
+    pk = np.exp(np.interp(np.log(k), np.log(b.kin), np.log(b.plin[0])))
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as fh:
+        np.savetxt(fh, np.column_stack([k, pk]))
+        path = fh.name
+    ext = bz.LinearPowerFile(path, gz=0.8, prefix="t_")
+    kh = np.logspace(-5, 0, 200)
+    np.savez_compressed(os.path.join(HERE, "linear_power_file.npz"), meta=meta(), k=k, pk=pk, gz=0.8, kh=kh, pkh=ext.Pkh(kh),
+                        requirements=json.dumps(sorted(ext.get_requirements())))
+    os.unlink(path)
+
+
+if __name__ == "__main__" and os.environ.get("EFTB_GOLDEN_LPF", "1") == "1":
+    linear_power_file_golden()

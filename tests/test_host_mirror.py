@@ -114,3 +114,30 @@ def test_basis_names_and_descriptors():
     with pytest.raises(NotImplementedError):
         parambasis.EastCoastBasis(prefix="a", cross_prefix=["b", "c"])
     assert parambasis.find_param_basis("eastcoast") is parambasis.EastCoastBasis
+
+
+def test_linear_power_file_extractor_matches_reference():
+    """boltzmann.py:246-309 mirror against the live reference's `LinearPowerFile.Pkh` (tests/golden/linear_power_file.npz,
+    generated by tests/golden/make_golden_interp.py) + the batched protocol getters."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+    from eftpipe_b200 import boltzmann
+
+    g = dict(np.load(os.path.join(GOLDEN, "linear_power_file.npz")))
+    ext = boltzmann.LinearPowerFile((g["k"], g["pk"]), gz=float(g["gz"]), prefix="t_")
+    assert sorted(ext.get_requirements()) == json.loads(str(g["requirements"]))
+    ext.initialize_with_provider({"t_f": [0.7, 0.8, 0.9], "t_alperp": [1.0, 1.01, 0.99], "t_alpara": [1.0, 0.98, 1.02]})
+    pkh = ext.Pkh(g["kh"])
+    assert pkh.shape == (3, 200)
+    np.testing.assert_allclose(pkh[1], g["pkh"], rtol=1e-13)
+    assert ext.DA() == 1 and ext.H() == 1  # the first calls seed the AP fiducial (boltzmann.py:287-297)
+    np.testing.assert_allclose(ext.DA(), [1.0, 1.01, 0.99])
+    np.testing.assert_allclose(ext.H(), 1 / np.array([1.0, 0.98, 1.02]))
+    c = ext.cosmo()
+    assert set(c) >= {"pkh", "f", "DA", "H"} and c["pkh"].shape == (3, 200)
+    arr = boltzmann.ArrayExtractor(pkh, c["f"], c["DA"], c["H"])
+    assert arr.cosmo()["pkh"] is pkh and boltzmann.find_boltzmann_extractor(arr) is arr
+    with pytest.raises(NotImplementedError):
+        boltzmann.find_boltzmann_extractor("classynu")
