@@ -9,6 +9,10 @@
 // double-buffered shared memory (row pitches 20 and 132 doubles = 4 mod 16 -> conflict-free fragment
 // reads).  Used for: front operator, D -> P22/C22/C13 spectral transforms, B-spline collocation, the
 // window/binning/chained projection and the inverse-covariance product.
+#include <stdlib.h>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include "common.cuh"
 
 namespace {
@@ -175,6 +179,57 @@ int pick_mt(int M, int ncta_per_slab) {
   return best;
 }
 
+int launch_mt(int mt, const GemmArgs& g, int nz, cudaStream_t stream) {
+  switch (mt) {
+    case 11: return launch<11>(g, nz, stream);
+    case 10: return launch<10>(g, nz, stream);
+    case 9: return launch<9>(g, nz, stream);
+    case 8: return launch<8>(g, nz, stream);
+    case 7: return launch<7>(g, nz, stream);
+    case 6: return launch<6>(g, nz, stream);
+    case 5: return launch<5>(g, nz, stream);
+    default: return launch<4>(g, nz, stream);
+  }
+}
+
+// Slab height per GEMM shape: the analytic pick above ignores that several CTAs share an SM, so the first call of every
+// shape (outside stream capture: the engine warms its pipelines up before capturing them) times all slab heights once
+// and keeps the fastest.  The slab height only re-tiles the rows; the K summation order, hence every output bit, is the
+// same for all of them.  EFTB_GEMM_AUTOTUNE=0 keeps the analytic pick.
+int choose_mt(const GemmArgs& g, int nz, cudaStream_t stream) {
+  static std::map<std::tuple<int, int, int, int, int, int>, int> tuned;
+  static std::mutex mu;
+  static const bool enabled = !(getenv("EFTB_GEMM_AUTOTUNE") && atoi(getenv("EFTB_GEMM_AUTOTUNE")) == 0);
+  const int model = pick_mt(g.M, ((g.N + BN - 1) / BN) * nz);
+  if (!enabled) return model;
+  const auto key = std::make_tuple(g.Mp, g.Kp, g.N, nz, g.pm_bp > 0 ? 1 : 0, g.zdiv);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = tuned.find(key);
+  if (it != tuned.end()) return it->second;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return model;
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return model;
+  int best = model;
+  float best_ms = 1e30f;
+  for (int mt = 4; mt <= 11; ++mt) {
+    if (launch_mt(mt, g, nz, stream) != EFTB_OK) continue;  // warm-up (function attributes, caches)
+    cudaEventRecord(e0, stream);
+    for (int r = 0; r < 3; ++r) launch_mt(mt, g, nz, stream);
+    cudaEventRecord(e1, stream);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = model; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best_ms * 0.98f) { best_ms = ms; best = mt; }  // ties go to the smaller slab tried first
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  tuned[key] = best;
+  if (getenv("EFTB_GEMM_VERBOSE"))
+    fprintf(stderr, "eftb gemm autotune: M=%d K=%d N=%d nz=%d -> MT=%d (model %d), %.1f us\n", g.M, g.K, g.N, nz, best, model, best_ms / 3 * 1e3);
+  return best;
+}
+
 }  // namespace
 
 int gemm_upload(const double* host, int nbatch, int M, int K, GemmMatrix* out) {
@@ -212,14 +267,5 @@ int gemm_run(const GemmMatrix& A, const double* X, double* C, int N, int nz, int
   }
   GemmArgs g{A.d, X, C, A.M, A.K, A.Kp, A.Mp, N, A.nbatch > 1 ? 1 : 0, zdiv, xs, xs2, cs, cs2,
              pm ? pm->bp : 0, pm ? pm->ld : 0, pm ? pm->is : 0, ldx ? ldx : (size_t)N, ldc ? ldc : (size_t)N};
-  switch (pick_mt(A.M, ((N + BN - 1) / BN) * nz)) {
-    case 11: return launch<11>(g, nz, stream);
-    case 10: return launch<10>(g, nz, stream);
-    case 9: return launch<9>(g, nz, stream);
-    case 8: return launch<8>(g, nz, stream);
-    case 7: return launch<7>(g, nz, stream);
-    case 6: return launch<6>(g, nz, stream);
-    case 5: return launch<5>(g, nz, stream);
-    default: return launch<4>(g, nz, stream);
-  }
+  return launch_mt(choose_mt(g, nz, stream), g, nz, stream);
 }
