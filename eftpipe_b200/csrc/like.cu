@@ -130,17 +130,21 @@ struct FinArgs {
   int B, Bp, ndata, ngauss, jeffreys;
 };
 
-// block (32 points, ny entry-rows): every entry of the packed lower triangle of F2, of F1 and F0 is one dot product
+// block (LF_PX points, ny entry-rows): every entry of the packed lower triangle of F2, of F1 and F0 is one dot product
 // over the data index, sum_d V[d][ra] * Y[d][rb]; entry-rows are spread over threadIdx.y, loads are coalesced
-// over the 32 points and unrolled 4x (independent partial sums) to keep several loads in flight
+// over the LF_PX points and unrolled 4x (independent partial sums) to keep several loads in flight
+// LF_PX points per CTA (Bp is a multiple of 32, hence of LF_PX): 8 rather than a full warp of points, so that a batch of
+// 1024 spreads over 128 CTAs instead of 32 - the kernel is latency bound and there are 148 SMs to hide it on
+constexpr int LF_PX = 8;
+
 __global__ void like_finish_kernel(FinArgs a) {
   extern __shared__ double sm[];
   const int nG = a.ngauss, nc = nG + 1;
-  double* F2 = sm;                    // [nG][nG][32]
-  double* F1 = F2 + (size_t)nG * nG * 32;  // [nG][32]
-  double* F0 = F1 + (size_t)nG * 32;       // [32]
+  double* F2 = sm;                    // [nG][nG][LF_PX]
+  double* F1 = F2 + (size_t)nG * nG * LF_PX;  // [nG][LF_PX]
+  double* F0 = F1 + (size_t)nG * LF_PX;       // [LF_PX]
   const int lx = threadIdx.x, g = threadIdx.y;
-  const int b = blockIdx.x * 32 + lx;
+  const int b = blockIdx.x * LF_PX + lx;
   const size_t Bp = a.Bp, stride = (size_t)nc * Bp;
   const int ntri = nG * (nG + 1) / 2, nent = ntri + nG + 1;
   for (int e = threadIdx.y; e < nent; e += blockDim.y) {
@@ -167,10 +171,10 @@ __global__ void like_finish_kernel(FinArgs a) {
     const double sum = (s0 + s1) + (s2 + s3);
     if (e < ntri) {
       const double v = sum + a.sigma_inv[eg * nG + ej];  // marginal.py:167-175
-      F2[((size_t)eg * nG + ej) * 32 + lx] = v;
-      F2[((size_t)ej * nG + eg) * 32 + lx] = v;
+      F2[((size_t)eg * nG + ej) * LF_PX + lx] = v;
+      F2[((size_t)ej * nG + eg) * LF_PX + lx] = v;
     } else if (e < ntri + nG) {
-      F1[(size_t)eg * 32 + lx] = -sum + a.sigma_inv_mu[eg];  // marginal.py:177-185
+      F1[(size_t)eg * LF_PX + lx] = -sum + a.sigma_inv_mu[eg];  // marginal.py:177-185
     } else {
       F0[lx] = sum + a.mu_sigma_mu;  // marginal.py:187-196
     }
@@ -181,16 +185,16 @@ __global__ void like_finish_kernel(FinArgs a) {
   bool ok = true;
   double logdet = 0.0;
   for (int j = 0; j < nG && ok; ++j) {
-    double dj = F2[((size_t)j * nG + j) * 32 + lx];
-    for (int k = 0; k < j; ++k) { const double l = F2[((size_t)j * nG + k) * 32 + lx]; dj -= l * l; }
+    double dj = F2[((size_t)j * nG + j) * LF_PX + lx];
+    for (int k = 0; k < j; ++k) { const double l = F2[((size_t)j * nG + k) * LF_PX + lx]; dj -= l * l; }
     if (!(dj > 0.0)) { ok = false; break; }
     const double ljj = sqrt(dj);
-    F2[((size_t)j * nG + j) * 32 + lx] = ljj;
+    F2[((size_t)j * nG + j) * LF_PX + lx] = ljj;
     logdet += 2.0 * log(ljj);
     for (int i = j + 1; i < nG; ++i) {
-      double s = F2[((size_t)i * nG + j) * 32 + lx];
-      for (int k = 0; k < j; ++k) s -= F2[((size_t)i * nG + k) * 32 + lx] * F2[((size_t)j * nG + k) * 32 + lx];
-      F2[((size_t)i * nG + j) * 32 + lx] = s / ljj;
+      double s = F2[((size_t)i * nG + j) * LF_PX + lx];
+      for (int k = 0; k < j; ++k) s -= F2[((size_t)i * nG + k) * LF_PX + lx] * F2[((size_t)j * nG + k) * LF_PX + lx];
+      F2[((size_t)i * nG + j) * LF_PX + lx] = s / ljj;
     }
   }
   if (!ok) {  // reference raises RuntimeError("det of F2ij <= 0") (marginal.py:113-116); here: flag the point
@@ -202,10 +206,10 @@ __global__ void like_finish_kernel(FinArgs a) {
   // y = L^-1 F1 ;  F1^T F2^-1 F1 = |y|^2
   double quad = 0.0;
   for (int i = 0; i < nG; ++i) {
-    double s = F1[(size_t)i * 32 + lx];
-    for (int k = 0; k < i; ++k) s -= F2[((size_t)i * nG + k) * 32 + lx] * F1[(size_t)k * 32 + lx];
-    s /= F2[((size_t)i * nG + i) * 32 + lx];
-    F1[(size_t)i * 32 + lx] = s;
+    double s = F1[(size_t)i * LF_PX + lx];
+    for (int k = 0; k < i; ++k) s -= F2[((size_t)i * nG + k) * LF_PX + lx] * F1[(size_t)k * LF_PX + lx];
+    s /= F2[((size_t)i * nG + i) * LF_PX + lx];
+    F1[(size_t)i * LF_PX + lx] = s;
     quad += s * s;
   }
   logdet -= nG * log(2.0 * M_PI);  // ln det(F2 / 2 pi)
@@ -214,10 +218,10 @@ __global__ void like_finish_kernel(FinArgs a) {
   a.status[b] = 0;
   if (a.bestfit) {  // bG = L^-T y (marginal.py:117)
     for (int i = nG - 1; i >= 0; --i) {
-      double s = F1[(size_t)i * 32 + lx];
-      for (int k = i + 1; k < nG; ++k) s -= F2[((size_t)k * nG + i) * 32 + lx] * F1[(size_t)k * 32 + lx];
-      s /= F2[((size_t)i * nG + i) * 32 + lx];
-      F1[(size_t)i * 32 + lx] = s;
+      double s = F1[(size_t)i * LF_PX + lx];
+      for (int k = i + 1; k < nG; ++k) s -= F2[((size_t)k * nG + i) * LF_PX + lx] * F1[(size_t)k * LF_PX + lx];
+      s /= F2[((size_t)i * nG + i) * LF_PX + lx];
+      F1[(size_t)i * LF_PX + lx] = s;
       a.bestfit[(size_t)b * nG + i] = s;
     }
   }
@@ -319,14 +323,14 @@ int eftb_like_eval(const eftb_like* L, int B, const double* const* terms, const 
   if (rc) return rc;
   FinArgs a{V, Y, L->sigma_inv, L->sigma_inv_mu, L->mu_sigma_mu, logp, bestfit, status, B, Bp, nd, L->cfg.ngauss, L->cfg.jeffreys};
   const int nG = L->cfg.ngauss;
-  size_t smem = sizeof(double) * ((size_t)nG * nG * 32 + (size_t)nG * 32 + 32);
+  size_t smem = sizeof(double) * ((size_t)nG * nG * LF_PX + (size_t)nG * LF_PX + LF_PX);
   static size_t configured = 0;
   if (smem > configured) {
     EFTB_CUDA_CHECK(cudaFuncSetAttribute(like_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const int nent = nG * (nG + 1) / 2 + nG + 1;
-  dim3 block(32, nent < 30 ? nent : 30), grid(Bp / 32);
+  dim3 block(LF_PX, nent < 64 ? nent : 64), grid(Bp / LF_PX);
   like_finish_kernel<<<grid, block, smem, s>>>(a);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;

@@ -164,22 +164,32 @@ class EFTLSS:
     # ---- per batch (theory.py:557-609) ----
     def calculate(self, cosmo: dict):
         """cosmo[tracer] = dict(pkh=(B, 200) on kh = logspace(-5, 0, 200), f=, DA=, H= (B,) [, rdrag, h])."""
-        self._state, self.derived = {}, {}
+        self._state, self._derive_inputs, self._derived = {}, {}, None
         for name, dp in self.plans.items():
             c = cosmo[name]
             if hasattr(c, "Pkh"):  # a boltzmann.BoltzmannExtractor (theory.py:559-565)
                 c = c.cosmo()
             if not self.tracers[name].get("with_RSD", True):  # theory.py:566-567
-                c = dict(c, f=np.zeros(np.shape(_host(c["f"]))))
+                c = dict(c, f=c["f"] * 0.0)  # same container type and device as the input
             pm, bm = dp.eval_terms(c["pkh"], c["f"], c.get("DA"), c.get("H"), want_bm=True, want_pm=False)
             f_bm = dp.to_batch_minor(c["f"])[0]
             self._state[name] = (bm, f_bm)
             self.B = bm.shape[-1] if not hasattr(c["pkh"], "shape") else c["pkh"].shape[0]
-            self._derive(name, c)
+            self._derive_inputs[name] = c
         return self
 
+    @property
+    def derived(self):
+        """derived parameters of theory.py:620-648, `{prefix}alperp, alpara, fz, fsigma8_z` per point - evaluated on first
+        access (they read the inputs back to the host, which must not happen while `calculate` is being captured into a
+        CUDA graph)"""
+        if self._derived is None:
+            self._derived = {}
+            for name, c in self._derive_inputs.items():
+                self._derive(name, c)
+        return self._derived
+
     def _derive(self, name, c):
-        """derived parameters of theory.py:620-648: `{prefix}alperp, alpara, fz, fsigma8_z` per point"""
         prefix = self.tracers[name].get("prefix")
         prefix = name + "_" if prefix is None else prefix
         apo = self.info.get(name, {}).get("ap")
@@ -188,12 +198,12 @@ class EFTLSS:
             if all(x is not None for x in (apo.rdrag_AP, apo.h_AP, c.get("rdrag"), c.get("h"))):
                 ratio = (apo.rdrag_AP * apo.h_AP) / (np.asarray(_host(c["rdrag"]), float) * np.asarray(_host(c["h"]), float))
                 qperp, qpar = qperp * ratio, qpar * ratio  # pybird.py:1576-1578
-            self.derived[prefix + "alperp"], self.derived[prefix + "alpara"] = qperp, qpar
+            self._derived[prefix + "alperp"], self._derived[prefix + "alpara"] = qperp, qpar
         else:
-            self.derived[prefix + "alperp"] = self.derived[prefix + "alpara"] = -1
-        self.derived[prefix + "fz"] = np.asarray(_host(c["f"]), float)
+            self._derived[prefix + "alperp"] = self._derived[prefix + "alpara"] = -1
+        self._derived[prefix + "fz"] = np.asarray(_host(c["f"]), float)
         if c.get("fsigma8_z") is not None:
-            self.derived[prefix + "fsigma8_z"] = np.asarray(_host(c["fsigma8_z"]), float)
+            self._derived[prefix + "fsigma8_z"] = np.asarray(_host(c["fsigma8_z"]), float)
 
     def get_bird_component(self, tracer, params, chained=False, binned=True):
         """(ls, k, BirdComponent) - theory.py:265-266, :844-847"""
