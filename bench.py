@@ -277,10 +277,10 @@ def run_ours(args):
         return logp, status
 
     # kernels launched per step (counted from the call graph of csrc/api.cu + like.cu):
-    # front: transpose+tails+gemm (3) | f,DA,H transposes (3) | antidiag (1) | spectral: regroup + 2 gemms (3) | group (1)
+    # front: transpose+tails+gemm (3) | f,DA,H to batch-minor (1) | antidiag (1) | spectral: regroup + 2 gemms (3) | group (1)
     # | resum: Q(f) + sweep (2) | ap: gemm + geom + apply (3) | project gemm (1) | f, nuisance transposes (2)
     # | like: vectors+gemm+finish (3)
-    launches["n"] = 22
+    launches["n"] = 20
 
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")  # > 126 MB L2
     for _ in range(args.warmup):

@@ -351,11 +351,7 @@ int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double*
   const bool split_ap = c.has_ap && ap_chunk_count(p, B) == 1;
   cudaStream_t s2 = p->side;
   double* qf = out + z.out + z.ap;
-  if ((rc = launch_to_batch_minor(f, B, Bp, 1, scal, s))) return rc;
-  if (c.has_ap) {
-    if ((rc = launch_to_batch_minor(DA, B, Bp, 1, scal + Bp, s))) return rc;
-    if ((rc = launch_to_batch_minor(H, B, Bp, 1, scal + 2 * (size_t)Bp, s))) return rc;
-  }
+  if ((rc = launch_scalars_to_batch_minor(f, c.has_ap ? DA : nullptr, c.has_ap ? H : nullptr, B, Bp, scal, s))) return rc;
   EFTB_CUDA_CHECK(cudaEventRecord(p->ev_fork, s));
   EFTB_CUDA_CHECK(cudaStreamWaitEvent(s2, p->ev_fork, 0));
   if (c.has_resum && (rc = launch_resum(p, B, Bp, F, Cr, scal, T, qf, s2, EFTB_PHASE_FIRST))) return rc;

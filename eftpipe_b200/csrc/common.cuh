@@ -97,5 +97,6 @@ int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const doubl
 int ap_chunk_count(const eftb_plan* p, int B);  // launches the AP stage splits the batch into (phases need 1)
 size_t ap_scratch_doubles(const eftb_plan* p, int B);  // banded AP operator G + window metadata
 int launch_to_batch_minor(const double* in, int B, int Bp, int R, double* out, cudaStream_t s);
+int launch_scalars_to_batch_minor(const double* s0, const double* s1, const double* s2, int B, int Bp, double* out, cudaStream_t s);
 int launch_to_point_major(const double* in, int B, int Bp, int R, const int32_t* perm, double* out,
                           cudaStream_t s);

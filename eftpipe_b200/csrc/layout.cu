@@ -58,7 +58,24 @@ __global__ void front_tails_kernel(const double* __restrict__ plin, int B, int B
   u[(size_t)(nin + i) * Bp + b] = last * exp(slope * x);
 }
 
+// up to three per-point scalars (f, D_A, H) to their batch-minor rows in one launch: out[r][Bp], pad lanes replicate B-1
+__global__ void scalars_to_batch_minor_kernel(const double* __restrict__ s0, const double* __restrict__ s1,
+                                              const double* __restrict__ s2, int B, int Bp, double* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= Bp) return;
+  const int src = min(b, B - 1);
+  out[b] = s0[src];
+  if (s1) out[(size_t)Bp + b] = s1[src];
+  if (s2) out[2 * (size_t)Bp + b] = s2[src];
+}
+
 }  // namespace
+
+int launch_scalars_to_batch_minor(const double* s0, const double* s1, const double* s2, int B, int Bp, double* out, cudaStream_t s) {
+  scalars_to_batch_minor_kernel<<<(Bp + 255) / 256, 256, 0, s>>>(s0, s1, s2, B, Bp, out);
+  EFTB_LAUNCH_CHECK();
+  return EFTB_OK;
+}
 
 int launch_to_batch_minor(const double* in, int B, int Bp, int R, double* out, cudaStream_t s) {
   dim3 grid(Bp / 32, (R + 31) / 32), block(32, 8);
