@@ -1,5 +1,6 @@
 // C ABI of libeftb200: plan management, stage entry points, the fused per-batch pipeline.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "common.cuh"
@@ -348,14 +349,16 @@ int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double*
   // the cosmology scalars only - the Q(f) expansion of the resummation and the AP resampling geometry - runs beside the
   // front end and the loop kernels, and the D -> P22(k) GEMM runs beside the regrouping of the configuration-space
   // channels.  All of them write buffers nothing else touches until the join.
+  static const int side_mask = getenv("EFTB_SIDE") ? atoi(getenv("EFTB_SIDE")) : 3;  // tuning knob: 1 = Q(f) + AP geometry, 2 = P22 GEMM
   const bool split_ap = c.has_ap && ap_chunk_count(p, B) == 1;
   cudaStream_t s2 = p->side;
+  cudaStream_t sq = (side_mask & 1) ? s2 : s, sg = (side_mask & 2) ? s2 : s;
   double* qf = out + z.out + z.ap;
   if ((rc = launch_scalars_to_batch_minor(f, c.has_ap ? DA : nullptr, c.has_ap ? H : nullptr, B, Bp, scal, s))) return rc;
   EFTB_CUDA_CHECK(cudaEventRecord(p->ev_fork, s));
   EFTB_CUDA_CHECK(cudaStreamWaitEvent(s2, p->ev_fork, 0));
-  if (c.has_resum && (rc = launch_resum(p, B, Bp, F, Cr, scal, T, qf, s2, EFTB_PHASE_FIRST))) return rc;
-  if (split_ap && (rc = launch_ap(p, B, Bp, nullptr, nullptr, scal + Bp, scal + 2 * (size_t)Bp, out + z.out, nullptr, s2,
+  if (c.has_resum && (rc = launch_resum(p, B, Bp, F, Cr, scal, T, qf, sq, EFTB_PHASE_FIRST))) return rc;
+  if (split_ap && (rc = launch_ap(p, B, Bp, nullptr, nullptr, scal + Bp, scal + 2 * (size_t)Bp, out + z.out, nullptr, sq,
                                   EFTB_PHASE_FIRST))) return rc;
   if ((rc = eftb_front(p, B, plin, u, F, stream))) return rc;
   if ((rc = launch_antidiag(p, Bp, F, D, s))) return rc;
@@ -363,7 +366,7 @@ int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double*
   EFTB_CUDA_CHECK(cudaStreamWaitEvent(s2, p->ev_loops, 0));
   {  // D -> P22(k) on the side stream
     const size_t dch = (size_t)(c.Nmax + 1) * 2 * Bp;
-    if ((rc = gemm_run(p->Ak, D, P22, Bp, EFTB_N22, EFTB_N22, dch, 0, (size_t)c.Nk * Bp, 0, s2))) return rc;
+    if ((rc = gemm_run(p->Ak, D, P22, Bp, EFTB_N22, EFTB_N22, dch, 0, (size_t)c.Nk * Bp, 0, sg))) return rc;
   }
   EFTB_CUDA_CHECK(cudaEventRecord(p->ev_join, s2));
   if (Dcf && (rc = launch_antidiag(p, Bp, F, Dcf, s, true))) return rc;
