@@ -331,8 +331,8 @@ class APeffect:
         self.Nlmax = Nlmax if Nlmax else co.Nl
         if self.Nlmax > co.Nl:
             raise ValueError(f"request Nlmax={self.Nlmax}, while bird only compute Nl up to {co.Nl}")
-        if self.Nlmax != co.Nl:
-            raise NotImplementedError("Nlmax < Nl is not supported in this build")
+        if self.Nlmax != co.Nl:  # the reference itself cannot run this (pybird.py:1541 reads self.Nlmax before it is set)
+            raise NotImplementedError("Nlmax < Nl is not supported (nor functional in the reference)")
         co._register("ap", self)
 
     def get_AP_param(self, bird):
@@ -346,10 +346,15 @@ class APeffect:
         return bird._DA / self.DA * ratio, self.H / bird._H * ratio  # pybird.py:1576-1578
 
     def AP(self, bird: Bird, q=None):
-        if q is not None:
-            raise NotImplementedError("explicit q=(qperp, qpar) is not supported; pass DA and H through the Bird")
         dp = bird.co.device_plan()
-        bird._T = dp.ap(bird._T, bird._bm_scalar("DA"), bird._bm_scalar("H"), bird.B)
+        if q is not None:  # pybird.py:1603-1606: explicit (qperp, qpar), scalars or one pair per cosmology
+            t = bird.torch
+            dev = lambda x: (x if isinstance(x, t.Tensor) else t.as_tensor(np.asarray(x, float))).to("cuda", t.float64)
+            qperp, qpar = (dev(v).reshape(-1).expand(bird.B).contiguous() for v in q)
+            DA_bm, H_bm = dp.to_batch_minor(qperp * self.DA)[0], dp.to_batch_minor(self.H / qpar)[0]
+        else:
+            DA_bm, H_bm = bird._bm_scalar("DA"), bird._bm_scalar("H")
+        bird._T = dp.ap(bird._T, DA_bm, H_bm, bird.B)
         if self.snapshot:
             bird.create_snapshot("APeffect")
 
