@@ -18,9 +18,8 @@
 namespace {
 
 constexpr int BK = 16;
-constexpr int BN = 128;
+constexpr int BN = 128;  // columns per CTA of the default 4-warp tile (the 2-warp variant covers 64)
 constexpr int APITCH = BK + 4;
-constexpr int XPITCH = BN + 4;
 
 struct GemmArgs {
   const double* A;
@@ -50,9 +49,9 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-template <int MT>
-__global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
-  constexpr int BM = 8 * MT;
+template <int MT, int NW>
+__global__ void __launch_bounds__(32 * NW) gemm_f64_kernel(GemmArgs g) {
+  constexpr int BM = 8 * MT, BN = 32 * NW, XPITCH = BN + 4, NTHR = 32 * NW;  // XPITCH = 4 mod 16 for NW = 2, 4
   extern __shared__ __align__(16) double smem[];
   double* As = smem;                        // [2][BM][APITCH]
   double* Xs = smem + 2 * BM * APITCH;      // [2][BK][XPITCH]
@@ -74,13 +73,13 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
   auto load_stage = [&](int kt, int buf) {
     // A tile: BM rows x 16 doubles = BM*8 chunks of 16 B
     double* as = As + buf * BM * APITCH;
-    for (int c = tid; c < BM * 8; c += 128) {
+    for (int c = tid; c < BM * 8; c += NTHR) {
       int r = c >> 3, q = c & 7;
       const bool ok = m0 + r < g.Mp;  // A is padded to a multiple of 8 rows only: the last slab may be partial
       cp_async16(as + r * APITCH + q * 2, ok ? A + (size_t)r * g.Kp + kt * BK + q * 2 : g.A, ok);
     }
     double* xs = Xs + buf * BK * XPITCH;
-    for (int c = tid; c < BK * (BN / 2); c += 128) {
+    for (int c = tid; c < BK * (BN / 2); c += NTHR) {
       int r = c / (BN / 2), q = c % (BN / 2);
       int kk = kt * BK + r, col = n0 + q * 2;
       bool ok = (kk < g.K) && (col < g.N);
@@ -148,17 +147,17 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
   }
 }
 
-template <int MT>
+template <int MT, int NW>
 int launch(const GemmArgs& g, int nz, cudaStream_t s) {
-  constexpr int BM = 8 * MT;
-  size_t smem = sizeof(double) * (2 * BM * APITCH + 2 * BK * XPITCH);
+  constexpr int BM = 8 * MT, BNW = 32 * NW;
+  size_t smem = sizeof(double) * (2 * BM * APITCH + 2 * BK * (BNW + 4));
   static bool configured = false;
   if (!configured) {
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(gemm_f64_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EFTB_CUDA_CHECK(cudaFuncSetAttribute(gemm_f64_kernel<MT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((g.N + BN - 1) / BN, (g.Mp + BM - 1) / BM, nz);
-  gemm_f64_kernel<MT><<<grid, 128, smem, s>>>(g);
+  dim3 grid((g.N + BNW - 1) / BNW, (g.Mp + BM - 1) / BM, nz);
+  gemm_f64_kernel<MT, NW><<<grid, 32 * NW, smem, s>>>(g);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;
 }
@@ -179,17 +178,23 @@ int pick_mt(int M, int ncta_per_slab) {
   return best;
 }
 
-int launch_mt(int mt, const GemmArgs& g, int nz, cudaStream_t stream) {
+template <int NW>
+int launch_mt_nw(int mt, const GemmArgs& g, int nz, cudaStream_t stream) {
   switch (mt) {
-    case 11: return launch<11>(g, nz, stream);
-    case 10: return launch<10>(g, nz, stream);
-    case 9: return launch<9>(g, nz, stream);
-    case 8: return launch<8>(g, nz, stream);
-    case 7: return launch<7>(g, nz, stream);
-    case 6: return launch<6>(g, nz, stream);
-    case 5: return launch<5>(g, nz, stream);
-    default: return launch<4>(g, nz, stream);
+    case 11: return launch<11, NW>(g, nz, stream);
+    case 10: return launch<10, NW>(g, nz, stream);
+    case 9: return launch<9, NW>(g, nz, stream);
+    case 8: return launch<8, NW>(g, nz, stream);
+    case 7: return launch<7, NW>(g, nz, stream);
+    case 6: return launch<6, NW>(g, nz, stream);
+    case 5: return launch<5, NW>(g, nz, stream);
+    default: return launch<4, NW>(g, nz, stream);
   }
+}
+
+// tile = (slab height in m8 tiles) * 16 + warps per CTA (4: 128 columns, 2: 64 columns)
+int launch_mt(int tile, const GemmArgs& g, int nz, cudaStream_t stream) {
+  return (tile & 15) == 2 ? launch_mt_nw<2>(tile >> 4, g, nz, stream) : launch_mt_nw<4>(tile >> 4, g, nz, stream);
 }
 
 // Slab height per GEMM shape: the analytic pick above ignores that several CTAs share an SM, so the first call of every
@@ -200,7 +205,7 @@ int choose_mt(const GemmArgs& g, int nz, cudaStream_t stream) {
   static std::map<std::tuple<int, int, int, int, int, int>, int> tuned;
   static std::mutex mu;
   static const bool enabled = !(getenv("EFTB_GEMM_AUTOTUNE") && atoi(getenv("EFTB_GEMM_AUTOTUNE")) == 0);
-  const int model = pick_mt(g.M, ((g.N + BN - 1) / BN) * nz);
+  const int model = pick_mt(g.M, ((g.N + BN - 1) / BN) * nz) * 16 + 4;
   if (!enabled) return model;
   const auto key = std::make_tuple(g.Mp, g.Kp, g.N, nz, g.pm_bp > 0 ? 1 : 0, g.zdiv);
   std::lock_guard<std::mutex> lock(mu);
@@ -212,21 +217,24 @@ int choose_mt(const GemmArgs& g, int nz, cudaStream_t stream) {
   if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return model;
   int best = model;
   float best_ms = 1e30f;
-  for (int mt = 4; mt <= 11; ++mt) {
-    if (launch_mt(mt, g, nz, stream) != EFTB_OK) continue;  // warm-up (function attributes, caches)
-    cudaEventRecord(e0, stream);
-    for (int r = 0; r < 3; ++r) launch_mt(mt, g, nz, stream);
-    cudaEventRecord(e1, stream);
-    if (cudaEventSynchronize(e1) != cudaSuccess) { best = model; break; }
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    if (ms < best_ms * 0.98f) { best_ms = ms; best = mt; }  // ties go to the smaller slab tried first
-  }
+  for (int nw = 4; nw >= 2; nw -= 2)
+    for (int mt = 4; mt <= 11; ++mt) {
+      const int tile = mt * 16 + nw;
+      if (launch_mt(tile, g, nz, stream) != EFTB_OK) continue;  // warm-up (function attributes, caches)
+      cudaEventRecord(e0, stream);
+      for (int r = 0; r < 3; ++r) launch_mt(tile, g, nz, stream);
+      cudaEventRecord(e1, stream);
+      if (cudaEventSynchronize(e1) != cudaSuccess) { best = model; nw = 0; break; }
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (ms < best_ms * 0.98f) { best_ms = ms; best = tile; }  // ties go to the variant tried first
+    }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   tuned[key] = best;
   if (getenv("EFTB_GEMM_VERBOSE"))
-    fprintf(stderr, "eftb gemm autotune: M=%d K=%d N=%d nz=%d -> MT=%d (model %d), %.1f us\n", g.M, g.K, g.N, nz, best, model, best_ms / 3 * 1e3);
+    fprintf(stderr, "eftb gemm autotune: M=%d K=%d N=%d nz=%d -> MT=%d x %d warps (model MT=%d), %.1f us\n", g.M, g.K, g.N, nz, best >> 4,
+            best & 15, model >> 4, best_ms / 3 * 1e3);
   return best;
 }
 
