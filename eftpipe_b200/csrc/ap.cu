@@ -45,6 +45,8 @@ __device__ __forceinline__ double rsqrt_newton(double x) {
 constexpr int GEOM_THREADS = 128;
 constexpr int APPLY_WS = 10;  // window columns of a node held in the compact operator (wider windows: rest in the dense overflow)
 __host__ __device__ constexpr int apply_kp(int NL) { return (NL * APPLY_WS + 3) / 4 * 4; }  // K of the per-node product, padded to k4 steps
+// doubles between the B-spline coefficient blocks [l'][term][j] of consecutive cosmologies: whole 16-byte units (TMA source)
+__host__ __device__ inline size_t coef_stride(int NL, int nterm, int Nk) { return ((size_t)NL * nterm * Nk + 1) & ~(size_t)1; }
 constexpr int APPLY_THREADS = 256;
 
 // Everything of the resampling geometry that depends on (cosmology, mu) only - NOT on the k node:
@@ -243,10 +245,10 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
   constexpr int NT_MAX = NT;
   extern __shared__ __align__(128) double sm[];
   const int nslot = NL * a.nterm;
-  const uint32_t gbytes = (uint32_t)((size_t)a.Nk * NL * KP * sizeof(double)), cbytes = (uint32_t)((size_t)nslot * a.Nk * sizeof(double));
+  const uint32_t gbytes = (uint32_t)((size_t)a.Nk * NL * KP * sizeof(double)), cbytes = (uint32_t)(coef_stride(NL, a.nterm, a.Nk) * sizeof(double));
   double* Gs = sm;                                                      // [Nk][NL][KP]
   double* coefs = Gs + (size_t)a.Nk * NL * KP;                          // [NL][nterm][Nk] + slack
-  int2* metas = reinterpret_cast<int2*>(coefs + (size_t)nslot * a.Nk + APPLY_SLACK);  // [Nk]
+  int2* metas = reinterpret_cast<int2*>(coefs + coef_stride(NL, a.nterm, a.Nk) + APPLY_SLACK);  // [Nk]
   uint64_t* bar = reinterpret_cast<uint64_t*>(metas + a.Nk);
   const int bl = blockIdx.x, b = a.b0 + bl, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t Bp = a.Bp;
@@ -259,11 +261,12 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
                  "l"(a.Gc + (size_t)bl * a.Nk * NL * KP), "r"(gbytes), "r"(smem_u32(bar))
                  : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(coefs)),
-                 "l"(a.coef + (size_t)b * nslot * a.Nk), "r"(cbytes), "r"(smem_u32(bar))
+                 "l"(a.coef + (size_t)b * coef_stride(NL, a.nterm, a.Nk)), "r"(cbytes), "r"(smem_u32(bar))
                  : "memory");
   }
   for (int i = tid; i < a.Nk; i += APPLY_THREADS) metas[i] = a.meta[(size_t)bl * a.Nk + i];
-  if (tid < APPLY_SLACK) coefs[(size_t)nslot * a.Nk + tid] = 0.0;
+  // the slack after the block; with an odd block the copy also brings one pad word, which is never written by the GEMM: zero it
+  if (tid < APPLY_SLACK) coefs[coef_stride(NL, a.nterm, a.Nk) + tid] = 0.0;
   const double qperp = a.DA[b] / a.da_fid, qpar = a.h_fid / a.H[b];
   const double norm = 1.0 / (qperp * qperp * qpar);  // pybird.py:1611
   __syncthreads();  // metas, slack and the barrier initialisation are visible to every thread
@@ -273,6 +276,10 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
       asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
                    : "=r"(ok) : "r"(smem_u32(bar)) : "memory");
     } while (!ok);
+  }
+  if ((nslot * a.Nk) & 1) {  // odd block: the copy brought one pad word the GEMM never writes; out-of-window reads may touch it
+    if (tid == 0) coefs[(size_t)nslot * a.Nk] = 0.0;
+    __syncthreads();
   }
 
   // fragment roles: A[row = r][col = c4] = G row of multipole l = r; B[row = c4][col = r] = coefficient of term 8 t + r.
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (!((store >> (2 * t + h)) & 1u)) continue;
-          const double* cg = a.coef + ((size_t)b * nslot + 8 * t + 2 * c4 + h) * a.Nk + mw.x;
+          const double* cg = a.coef + (size_t)b * coef_stride(NL, a.nterm, a.Nk) + (size_t)(8 * t + 2 * c4 + h) * a.Nk + mw.x;
           for (int c = APPLY_WS; c < mw.y; ++c)
 #pragma unroll
             for (int lp = 0; lp < NL; ++lp)
@@ -357,8 +364,8 @@ int run(ApArgs a, int B, cudaStream_t s, int phase) {
   const int geom_cos = (GEOM_THREADS - 2 + a.Nk) / a.Nk + 1;  // cosmologies a CTA's GEOM_THREADS consecutive (b, k) nodes can touch
   const int mu_tile = a.nmu < GEOM_MU_TILE ? a.nmu : GEOM_MU_TILE;
   const size_t smem_g = sizeof(double) * (a.nint + (size_t)a.nint * 16 + 1 + (size_t)geom_cos * mu_tile * AP_TAB);
-  const size_t smem_a = sizeof(double) * ((size_t)NL * a.nterm * a.Nk + APPLY_SLACK + (size_t)a.Nk * NL * apply_kp(NL)) + sizeof(int2) * a.Nk + 16;
-  if (a.nterm > 32 || (NL * a.nterm * a.Nk) % 2 || smem_g > 200 * 1024 || smem_a > 200 * 1024) {  // bulk copies move 16-byte units
+  const size_t smem_a = sizeof(double) * (coef_stride(NL, a.nterm, a.Nk) + APPLY_SLACK + (size_t)a.Nk * NL * apply_kp(NL)) + sizeof(int2) * a.Nk + 16;
+  if (a.nterm > 32 || smem_g > 200 * 1024 || smem_a > 200 * 1024) {
     eftb_set_error("ap: unsupported sizes nmu=%d nterm=%d Nk=%d", a.nmu, a.nterm, a.Nk);
     return EFTB_ERR_ARG;
   }
@@ -399,6 +406,8 @@ size_t ap_scratch_doubles(const eftb_plan* p, int B) {
   const size_t n = chunk * c.Nk * c.Nl * c.Nl * c.Nk + chunk * c.Nk + 1 + chunk * c.Nk * c.Nl * apply_kp(c.Nl);
   return (n + 1) & ~(size_t)1;  // whole 16-byte units: the buffers that follow in the workspace are TMA sources too
 }
+
+size_t ap_coef_doubles(const eftb_plan* p, int Bp) { return coef_stride(p->cfg.Nl, p->cfg.nterm, p->cfg.Nk) * (size_t)Bp; }
 
 int ap_chunk_count(const eftb_plan* p, int B) {
   const int chunk = ap_chunk(p->cfg, B);

@@ -16,6 +16,8 @@ void eftb_set_error(const char* fmt, ...) {
 
 namespace {
 
+inline bool c_has_ap(const eftb_plan* p) { return p->cfg.has_ap != 0; }
+
 template <typename T>
 int upload(T** dst, const T* src, size_t n) {
   *dst = nullptr;
@@ -185,7 +187,8 @@ size_t eftb_workspace_bytes(const eftb_plan* p, int B) {
   if (!p || B < 1) return 0;
   Sizes z = sizes(p, eftb_padded_batch(B));
   // u | F | D (later reused for the spline coefficients and the AP output) | P22 | Dg | T | Cr | f,DA,H | out | AP operator
-  size_t dreg = z.D > 2 * z.T ? z.D : 2 * z.T;
+  const size_t apreg = c_has_ap(p) ? ap_coef_doubles(p, eftb_padded_batch(B)) + z.T : 0;  // coefficients | AP output
+  size_t dreg = z.D > apreg ? z.D : apreg;
   return (z.u + z.F + dreg + z.P22 + z.Dg + z.T + z.Cr + z.scal + z.out + z.ap + z.rs + z.Dcf) * sizeof(double);
 }
 
@@ -284,7 +287,7 @@ int eftb_resum(const eftb_plan* p, int B, const double* F, const double* Cr, con
 size_t eftb_ap_scratch_bytes(const eftb_plan* p, int B) {
   if (!p || B < 1 || !p->cfg.has_ap) return 0;
   const int Bp = eftb_padded_batch(B);
-  return ((size_t)p->cfg.Nl * p->cfg.Nk * p->cfg.nterm * Bp + ap_scratch_doubles(p, Bp)) * sizeof(double);
+  return (ap_coef_doubles(p, Bp) + ap_scratch_doubles(p, Bp)) * sizeof(double);
 }
 
 static int ap_stage(const eftb_plan* p, int B, const double* Tin, const double* DA, const double* H, double* coef,
@@ -294,7 +297,7 @@ static int ap_stage(const eftb_plan* p, int B, const double* Tin, const double* 
   const size_t per_l = (size_t)c.Nk * c.nterm * Bp;
   // B-spline coefficients of every term row: coef[l] = Cinv @ T[l]  (N = nterm*Bp columns), stored point-major
   // [b][l][term][j] for the one-CTA-per-cosmology apply kernel
-  GemmPointMajor pm{Bp, (size_t)c.Nl * c.nterm * c.Nk, (size_t)c.Nk};
+  GemmPointMajor pm{Bp, ap_coef_doubles(p, 1), (size_t)c.Nk};
   int rc = gemm_run(p->Cinv, Tin, coef, c.nterm * Bp, c.Nl, c.Nl, per_l, 0, (size_t)c.nterm * c.Nk, 0, s, &pm);
   if (rc) return rc;
   if (Bp > B) {  // pad lanes are not processed by the per-cosmology kernels: keep them finite
@@ -308,8 +311,7 @@ int eftb_ap(const eftb_plan* p, int B, const double* Tin, const double* DA, cons
   EFTB_NEED(p && Tin && DA && H && scratch && Tout && B >= 1 && Tin != Tout, "NULL/invalid argument");
   if (!p->cfg.has_ap) { eftb_set_error("eftb_ap: plan built without AP"); return EFTB_ERR_NOT_BUILT; }
   const eftb_config& c = p->cfg;
-  const size_t nT = (size_t)c.Nl * c.Nk * c.nterm * eftb_padded_batch(B);
-  return ap_stage(p, B, Tin, DA, H, scratch, scratch + nT, Tout, (cudaStream_t)stream);
+  return ap_stage(p, B, Tin, DA, H, scratch, scratch + ap_coef_doubles(p, eftb_padded_batch(B)), Tout, (cudaStream_t)stream);
 }
 
 int eftb_project(const eftb_plan* p, int B, const double* T, double* out, void* stream) {
@@ -336,7 +338,8 @@ int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double*
   double* w = (double*)workspace;
   double* u = w;            w += z.u;
   double* F = w;            w += z.F;
-  double* D = w;            w += (z.D > 2 * z.T ? z.D : 2 * z.T);
+  const size_t ncoef = c.has_ap ? ap_coef_doubles(p, Bp) : 0;
+  double* D = w;            w += (z.D > ncoef + z.T ? z.D : ncoef + z.T);
   double* P22 = w;          w += z.P22;
   double* Dg = w;           w += z.Dg;
   double* T = w;            w += z.T;
@@ -377,7 +380,7 @@ int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double*
   double* cur = T;
   if (c.has_ap) {
     double* coef = D;
-    double* T2 = D + z.T;
+    double* T2 = D + ncoef;
     if ((rc = ap_stage(p, B, T, scal + Bp, scal + 2 * (size_t)Bp, coef, out + z.out, T2, s,
                        split_ap ? EFTB_PHASE_SECOND : EFTB_PHASE_ALL))) return rc;
     cur = T2;

@@ -94,7 +94,8 @@ int launch_resum(const eftb_plan* p, int B, int Bp, const double* F, const doubl
 size_t resum_scratch_doubles(const eftb_plan* p, int B);  // expanded Q(f): [B][2 Nl Nl NIR 4]
 int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const double* Tin, const double* DA,
               const double* H, double* scratch, double* Tout, cudaStream_t s, int phase = EFTB_PHASE_ALL);  // FIRST: geometry
-int ap_chunk_count(const eftb_plan* p, int B);  // launches the AP stage splits the batch into (phases need 1)
+int ap_chunk_count(const eftb_plan* p, int B);
+size_t ap_coef_doubles(const eftb_plan* p, int Bp);  // size of the point-major B-spline coefficient buffer (even per-point stride)  // launches the AP stage splits the batch into (phases need 1)
 size_t ap_scratch_doubles(const eftb_plan* p, int B);  // banded AP operator G + window metadata
 int launch_to_batch_minor(const double* in, int B, int Bp, int R, double* out, cudaStream_t s);
 int launch_scalars_to_batch_minor(const double* s0, const double* s1, const double* s2, int B, int Bp, double* out, cudaStream_t s);

@@ -131,3 +131,25 @@ def test_large_batch_is_consistent_with_small_batches():
         small, _ = dp.eval_terms(batch.plin[sl], batch.f[sl], batch.DA[sl], batch.H[sl])
         torch.cuda.synchronize()
         np.testing.assert_array_equal(_np(small), big[sl])
+
+
+def test_odd_node_count_with_nnlo():
+    """kmax = 0.305 gives 65 k nodes; with NNLO (27 term rows) the per-cosmology coefficient block has an odd number of
+    doubles - the TMA-staged AP kernels pad the stride.  Fused pipeline against the oracle."""
+    import pybird_oracle as orc
+    from eftpipe_b200 import engine, plan, synthetic
+
+    Om_AP, z_AP = 0.307115, 0.696
+    DA0, H0 = synthetic.angular_distance(Om_AP, z_AP), synthetic.hubble(Om_AP, z_AP)
+    batch = synthetic.make_batch(3, 0.7, seed=21)
+    pl = plan.build_tracer_plan(Nl=3, kmax=0.305, with_NNLO=True, ap=dict(DA=DA0, H=H0, APst=True))
+    assert pl.grid.Nk == 65 and pl.grid.nterm == 27
+    got, _ = engine.DevicePlan(pl).eval_terms(batch.plin, batch.f, batch.DA, batch.H)
+    got = _np(got)
+    co = orc.Common(Nl=3, kmax=0.305, with_NNLO=True)
+    nl, rs, ap = orc.NonLinear(co), orc.Resum(co), orc.APeffect(co, Om_AP=Om_AP, z_AP=z_AP, APst=True)
+    for i in range(2):
+        b = orc.Bird(co, batch.kin, batch.plin[i], batch.f[i], batch.DA[i], batch.H[i], 0.7)
+        nl.PsCf(b); orc.set_PsCfl(b); rs.Ps(b); ap.AP(b)
+        ref = np.concatenate([b.P11l, b.Pctl, b.Ploopl, b.Pstl, b.PctNNLOl], axis=1)
+        assert rowmax_rel(got[i], ref) <= 1e-8
