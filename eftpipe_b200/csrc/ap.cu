@@ -433,6 +433,10 @@ int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const doubl
     const size_t off = (size_t)a.nb * c.Nk * c.Nl * c.Nl * c.Nk + (size_t)a.nb * c.Nk;
     a.Gc = scratch + off + (off & 1);  // 16-byte aligned (the scratch base is): TMA bulk copies read it
   }
+  if ((phase & EFTB_PHASE_SECOND) && ((reinterpret_cast<uintptr_t>(coef) | reinterpret_cast<uintptr_t>(a.Gc)) & 15)) {
+    eftb_set_error("ap: the scratch / coefficient buffers must be 16-byte aligned (TMA sources)");
+    return EFTB_ERR_ARG;
+  }
   if (c.Nl == 3) return run<3>(a, B, s, phase);
   if (c.Nl == 2) return run<2>(a, B, s, phase);
   eftb_set_error("ap: unsupported Nl=%d", c.Nl);

@@ -200,7 +200,8 @@ __device__ __forceinline__ void resum_body(const ResumArgs& a) {
   const double* qf = a.Qf + (size_t)b * (2 * NQH) + (size_t)IA * NQH;     // Q^{ll'}(f) of this cosmology (resum_q_kernel)
   // The rows this half contracts with are contiguous per multipole and, like the Q table, whole 16-byte units: TMA bulk
   // copies (one thread issues NL + 1 of them, one mbarrier wait) instead of ~30 dependent load/store pairs per thread.
-  const bool bulk = a.NsP == a.Ns && ((size_t)nrow * a.Ns) % 2 == 0 && ((size_t)a.ncr * a.Ns) % 2 == 0 && (row0 * a.Ns) % 2 == 0;
+  const bool bulk = a.NsP == a.Ns && ((size_t)nrow * a.Ns) % 2 == 0 && ((size_t)a.ncr * a.Ns) % 2 == 0 && (row0 * a.Ns) % 2 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(crb) | reinterpret_cast<uintptr_t>(qf)) & 15) == 0;
   uint64_t* bar = reinterpret_cast<uint64_t*>(Cs + (size_t)NL * nrow * a.NsP);
   if (bulk) {
     if (tid == 0) {

@@ -17,6 +17,8 @@
  *    per-point numerical failures (non positive-definite F2) are reported in the `status` array.
  *  - "batch-minor" arrays: logical shape [rows][Bp] with the cosmology index fastest and
  *    Bp = eftb_padded_batch(B) (B rounded up to a multiple of 32; pad lanes replicate point B-1).
+ *  - workspaces and scratch buffers must be 16-byte aligned (any cudaMalloc / torch allocation is): parts of them are
+ *    sources of TMA bulk copies.
  *  - all arithmetic is IEEE binary64.
  */
 #ifndef EFTB200_H
