@@ -306,6 +306,8 @@ def run_ours(args):
     time.sleep(0.3)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
+    if args.profile_range:  # ncu --profile-from-start off: capture the timed steps only (no plan-build / autotune launches)
+        torch.cuda.cudart().cudaProfilerStart()
     w0 = time.time()
     for i in range(args.steps):
         flush.zero_()  # evict L2 between timed iterations (not timed)
@@ -318,6 +320,8 @@ def run_ours(args):
         ev[i][1].record()
     torch.cuda.synchronize()
     w1 = time.time()
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStop()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop(w0, w1)
@@ -661,6 +665,8 @@ def main():
                     help="config2 = the bench line (single tracer); config3 = informational multi-tracer likelihood")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (use with `ncu --profile-from-start off`)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
