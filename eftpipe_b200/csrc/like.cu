@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(128) like_vectors_kernel(VecArgs a) {
 struct FinArgs {
   const double *V, *Y, *sigma_inv, *sigma_inv_mu;
   double mu_sigma_mu;
-  double *logp, *bestfit;
+  double *logp, *bestfit, *fullchi2;
   int32_t* status;
   int B, Bp, ndata, ngauss, jeffreys;
 };
@@ -143,6 +143,8 @@ __global__ void like_finish_kernel(FinArgs a) {
   double* F2 = sm;                    // [nG][nG][LF_PX]
   double* F1 = F2 + (size_t)nG * nG * LF_PX;  // [nG][LF_PX]
   double* F0 = F1 + (size_t)nG * LF_PX;       // [LF_PX]
+  double* F1o = F0 + LF_PX;                    // [nG][LF_PX]  F1 and diag(F2) before the factorisation (fullchi2 only)
+  double* F2d = F1o + (size_t)nG * LF_PX;      // [nG][LF_PX]
   const int lx = threadIdx.x, g = threadIdx.y;
   const int b = blockIdx.x * LF_PX + lx;
   const size_t Bp = a.Bp, stride = (size_t)nc * Bp;
@@ -181,6 +183,11 @@ __global__ void like_finish_kernel(FinArgs a) {
   }
   __syncthreads();
   if (g != 0 || b >= a.B) return;
+  if (a.fullchi2)
+    for (int i = 0; i < nG; ++i) {
+      F1o[(size_t)i * LF_PX + lx] = F1[(size_t)i * LF_PX + lx];
+      F2d[(size_t)i * LF_PX + lx] = F2[((size_t)i * nG + i) * LF_PX + lx];
+    }
   // in-place Cholesky F2 = L L^T on this point's column of shared memory
   bool ok = true;
   double logdet = 0.0;
@@ -201,6 +208,7 @@ __global__ void like_finish_kernel(FinArgs a) {
     a.logp[b] = -INFINITY;
     a.status[b] = 1;
     if (a.bestfit) for (int i = 0; i < nG; ++i) a.bestfit[(size_t)b * nG + i] = NAN;
+    if (a.fullchi2) a.fullchi2[b] = NAN;
     return;
   }
   // y = L^-1 F1 ;  F1^T F2^-1 F1 = |y|^2
@@ -216,14 +224,28 @@ __global__ void like_finish_kernel(FinArgs a) {
   const double chi2 = -quad + F0[lx] + (a.jeffreys ? 0.0 : logdet);  // marginal.py:118-122
   a.logp[b] = -0.5 * chi2;
   a.status[b] = 0;
-  if (a.bestfit) {  // bG = L^-T y (marginal.py:117)
+  if (a.bestfit || a.fullchi2) {  // bG = L^-T y (marginal.py:117)
     for (int i = nG - 1; i >= 0; --i) {
       double s = F1[(size_t)i * LF_PX + lx];
       for (int k = i + 1; k < nG; ++k) s -= F2[((size_t)k * nG + i) * LF_PX + lx] * F1[(size_t)k * LF_PX + lx];
       s /= F2[((size_t)i * nG + i) * LF_PX + lx];
       F1[(size_t)i * LF_PX + lx] = s;
-      a.bestfit[(size_t)b * nG + i] = s;
+      if (a.bestfit) a.bestfit[(size_t)b * nG + i] = s;
     }
+  }
+  if (a.fullchi2) {
+    // marginal.py:129-131: chi^2 of the data at the best-fit bG, r = PNG + bG.PG - d, without the prior terms:
+    //   r^T C^-1 r = F0' + 2 bG.g + bG^T F2' bG,  F2' = F2 - Sigma^-1,  g = PG C^-1 (PNG - d) = -(F1 - Sigma^-1 mu),
+    //   F0' = F0 - mu^T Sigma^-1 mu.  The strict upper triangle of F2 still holds the values from before the factorisation.
+    double full = F0[lx] - a.mu_sigma_mu;
+    for (int i = 0; i < nG; ++i) {
+      const double bi = F1[(size_t)i * LF_PX + lx];
+      full -= 2.0 * bi * (F1o[(size_t)i * LF_PX + lx] - a.sigma_inv_mu[i]);
+      full += bi * bi * (F2d[(size_t)i * LF_PX + lx] - a.sigma_inv[i * nG + i]);
+      for (int j = i + 1; j < nG; ++j)
+        full += 2.0 * bi * F1[(size_t)j * LF_PX + lx] * (F2[((size_t)i * nG + j) * LF_PX + lx] - a.sigma_inv[i * nG + j]);
+    }
+    a.fullchi2[b] = full;
   }
 }
 
@@ -308,6 +330,12 @@ size_t eftb_like_workspace_bytes(const eftb_like* L, int B) {
 
 int eftb_like_eval(const eftb_like* L, int B, const double* const* terms, const double* const* fgrowth, const double* nuis,
                    double* logp, double* bestfit, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  return eftb_like_eval_full(L, B, terms, fgrowth, nuis, logp, bestfit, nullptr, status, workspace, workspace_bytes, stream);
+}
+
+int eftb_like_eval_full(const eftb_like* L, int B, const double* const* terms, const double* const* fgrowth, const double* nuis,
+                        double* logp, double* bestfit, double* fullchi2, int32_t* status, void* workspace, size_t workspace_bytes,
+                        void* stream) {
   if (!L || !terms || !fgrowth || !nuis || !logp || !status || !workspace || B < 1) {
     eftb_set_error("eftb_like_eval: NULL/invalid argument");
     return EFTB_ERR_ARG;
@@ -321,9 +349,9 @@ int eftb_like_eval(const eftb_like* L, int B, const double* const* terms, const 
   if (rc) return rc;
   rc = gemm_run(L->invcov, V, Y, nc * Bp, 1, 1, 0, 0, 0, 0, s);
   if (rc) return rc;
-  FinArgs a{V, Y, L->sigma_inv, L->sigma_inv_mu, L->mu_sigma_mu, logp, bestfit, status, B, Bp, nd, L->cfg.ngauss, L->cfg.jeffreys};
+  FinArgs a{V, Y, L->sigma_inv, L->sigma_inv_mu, L->mu_sigma_mu, logp, bestfit, fullchi2, status, B, Bp, nd, L->cfg.ngauss, L->cfg.jeffreys};
   const int nG = L->cfg.ngauss;
-  size_t smem = sizeof(double) * ((size_t)nG * nG * LF_PX + (size_t)nG * LF_PX + LF_PX);
+  size_t smem = sizeof(double) * ((size_t)nG * nG * LF_PX + (size_t)3 * nG * LF_PX + LF_PX);
   static size_t configured = 0;
   if (smem > configured) {
     EFTB_CUDA_CHECK(cudaFuncSetAttribute(like_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -391,19 +391,21 @@ class DeviceLikelihood:
         arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
         return arr
 
-    def eval(self, B, terms_bm, f_bm, nuis_bm, want_bestfit=False):
+    def eval(self, B, terms_bm, f_bm, nuis_bm, want_bestfit=False, want_fullchi2=False):
+        """(logp, status, bestfit) or, with want_fullchi2, (logp, status, bestfit, fullchi2) - marginal.py:79-137"""
         t = self.torch
         ws, need = self._workspace(B)
         logp = t.empty(B, dtype=t.float64, device="cuda")
         status = t.empty(B, dtype=t.int32, device="cuda")
         best = t.empty((B, self.cfg.ngauss), dtype=t.float64, device="cuda") if want_bestfit else None
+        full = t.empty(B, dtype=t.float64, device="cuda") if want_fullchi2 else None
         ta, fa = self._ptr_array(terms_bm), self._ptr_array(f_bm)
         _lib.check(
-            self.lib.eftb_like_eval(self.handle, B, ta, fa, _p(nuis_bm), _p(logp), _p(best), _p(status), _p(ws), need,
-                                    _stream_ptr(t)),
+            self.lib.eftb_like_eval_full(self.handle, B, ta, fa, _p(nuis_bm), _p(logp), _p(best), _p(full), _p(status), _p(ws),
+                                         need, _stream_ptr(t)),
             "eftb_like_eval",
         )
-        return logp, status, best
+        return (logp, status, best, full) if want_fullchi2 else (logp, status, best)
 
     def vectors(self, B, terms_bm, f_bm, nuis_bm):
         t = self.torch

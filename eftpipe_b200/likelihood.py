@@ -378,8 +378,10 @@ class EFTLike(Marginalizable):
     def calculate(self, params, want_bestfit=False):
         """likelihood.py:570-594 for a batch: returns dict(logp=(B,), chi2=(B,), status=(B,) [, bestfit])."""
         B, terms, fs, nuis = self._inputs(params)
-        logp, status, best = self.device.eval(B, terms, fs, nuis, want_bestfit=want_bestfit)
+        logp, status, best, full = self.device.eval(B, terms, fs, nuis, want_bestfit=want_bestfit, want_fullchi2=True)
         out = {"logp": logp, self.likelihood_prefix + "chi2": -2.0 * logp, "status": status}
+        if self.gaussian_names:  # likelihood.py:583-590: chi^2 at the best-fit marginalised parameters
+            out[self.likelihood_prefix + "fullchi2"] = full
         if want_bestfit:
             out["bestfit"] = {self.marg_param_prefix + n: best[:, i] for i, n in enumerate(self.gaussian_names)}
         return out

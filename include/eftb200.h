@@ -222,6 +222,11 @@ size_t eftb_like_workspace_bytes(const eftb_like*, int B);
 int eftb_like_eval(const eftb_like*, int B, const double* const* terms, const double* const* fgrowth,
                    const double* nuis, double* logp, double* bestfit, int32_t* status, void* workspace,
                    size_t workspace_bytes, void* stream);
+/* the same plus fullchi2 [B] (optional): chi^2 of the data at the best-fit marginalised parameters, without the prior
+ * terms (marginal.py:129-131; EFTLike's derived `{prefix}fullchi2`, likelihood.py:583-590) */
+int eftb_like_eval_full(const eftb_like*, int B, const double* const* terms, const double* const* fgrowth,
+                        const double* nuis, double* logp, double* bestfit, double* fullchi2, int32_t* status,
+                        void* workspace, size_t workspace_bytes, void* stream);
 /* un-marginalised pieces for parity tests: vec [B][ndata][ngauss+1] (point-major) with
  * vec[.,d,0] = PNG[d] - data[d] (likelihood.py:528-549) and vec[.,d,1+g] = PG[g][d] (likelihood.py:483-525) */
 int eftb_like_vectors(const eftb_like*, int B, const double* const* terms, const double* const* fgrowth,

@@ -156,9 +156,11 @@ def test_single_tracer_marginalised_likelihood(chain, golden2, dr16):
         spec = likelihood.build_spec([tr], g["lrg_data"], g["lrg_invcov"], gaussian=names, sigma_inv=sig, jeffreys=jeff)
         dev = DeviceLikelihood(spec)
         nuis = likelihood.pack_nuisance(torch, [basis], sampled, [binned._f_bm], binned.B, binned._T.shape[-1])
-        logp, status, best = dev.eval(binned.B, [binned._T.contiguous()], [binned._f_bm], nuis, want_bestfit=True)
+        logp, status, best, full = dev.eval(binned.B, [binned._T.contiguous()], [binned._f_bm], nuis, want_bestfit=True,
+                                            want_fullchi2=True)
         ref = g["marg_out"]
         np.testing.assert_allclose(_np(logp), ref[:, col], rtol=1e-6)  # north star: chi^2 to 1e-6
+        np.testing.assert_allclose(_np(full), ref[:, col + 1], rtol=1e-6)  # marginal.py:129-131 fullchi2
         np.testing.assert_allclose(_np(best), ref[:, col + 2 : col + 8], rtol=1e-5, atol=1e-8)
         assert not _np(status).any()
         vec = _np(dev.vectors(binned.B, [binned._T.contiguous()], [binned._f_bm], nuis))
