@@ -535,7 +535,7 @@ def build_tracer_plan(Nl=3, kmax=0.3, NFFT=256, with_NNLO=False, kin=None, windo
 
 
 def compose_projection(g: GridConfig, window=None, icc=None, binning=None, chained=False, window_st=True, fiber=None,
-                       fiber_st=False):
+                       fiber_st=False, window_stoch=None, window_picc=None):
     """Compose window (+ICC), fibre collisions, binning and chained mixing into one matrix on the Nl*Nk nodes, in the
     reference's order (theory.py:582-604).
 
@@ -543,6 +543,8 @@ def compose_projection(g: GridConfig, window=None, icc=None, binning=None, chain
     icc    : None or dict(matrix=(Na,Nk,Nl,Nk), PSN_times_Pshot=(Na,Nk))    (window.py:393-405)
     fiber  : None or (Nl, Nk, Nl, Nk) matrix F of `fiber_matrix`: P <- P + F.P  (pybird.py:1760-1806; not Picc)
     binning: None or (nbin, Nk) matrix (`binning_matrix`)
+    window_stoch / window_picc: a probed custom window stage (plugins.probe_linear_stage) brings its own operator for the
+             stochastic terms and its own constant on Picc
     Returns dict(matrix=(Nout, Nl*Nk), picc=(Nout,), shape=(Nl_out, nk_out), st=True, matrix_st=None or (Nout, Nl*Nk)).
     `matrix_st` is the operator of the stochastic terms when it differs from `matrix`: the window leaves them alone
     with window_st=False (window.py:401-403), the fibre correction unless fiberst (pybird.py:1798-1806)."""
@@ -555,10 +557,14 @@ def compose_projection(g: GridConfig, window=None, icc=None, binning=None, chain
         if icc is not None:
             op = op - icc["matrix"]
             picc = picc - icc["PSN_times_Pshot"]
-        if window_st:
+        if window_stoch is not None:
+            op_st = np.array(window_stoch, dtype=float)
+        elif window_st:
             op_st = op
         elif op.shape != eye.shape:
             raise ValueError("window_st=False needs a window that preserves the node grid")
+        if window_picc is not None:
+            picc = picc + np.asarray(window_picc, float)
     if fiber is not None:
         if op.shape[0] != Nl:
             raise ValueError("fibre-collision correction needs Na == Nl window output")

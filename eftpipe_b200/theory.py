@@ -17,6 +17,7 @@ from .engine import DevicePlan
 from .icc import IntegralConstraint
 from .marginal import LoggedError
 from .parambasis import find_param_basis
+from .plugins import find_window_constructor, probe_linear_stage
 from .pybird import APeffect, Common, DAfunc, FiberCollision, Hubble
 from .window import Window
 
@@ -116,12 +117,19 @@ class EFTLSS:
                 apo = APeffect(co=Common(Nl=Nl), **apc)
                 ap = dict(DA=apo.DA, H=apo.H, nbinsmu=apc.get("nbinsmu", 200), accboost=apc.get("accboost", 1), APst=apo.APst)
                 self.info.setdefault(name, {})["ap"] = apo
-            window = icc = None
-            if cfg.get("with_window"):
+            window = icc = custom = None
+            ww = cfg.get("with_window")
+            if ww:
                 wc = dict(cfg.get("window") or {})
                 if cfg.get("icc"):
                     icc = IntegralConstraint(co=co, **cfg["icc"])
-                window = Window(co=co, icc=icc, **wc)
+                if isinstance(ww, str) and ww not in ("auto", "default"):
+                    # theory.py:62-72, :370-377: a class by dotted path with an in-place `.Window(bird)`; probed once
+                    # into a fixed operator (plugins.probe_linear_stage) - ICC and the Picc constant included
+                    plugin = find_window_constructor(ww)(**wc, co=co, icc=icc, name=f"{name}.window")
+                    custom = probe_linear_stage(plugin.Window, co)
+                else:
+                    window = Window(co=co, icc=icc, **wc)
             fiber = None
             if cfg.get("with_fiber"):  # theory.py:378-385, :482-485
                 fiber = FiberCollision(co=co, **dict(cfg.get("fiber") or {}))
@@ -137,7 +145,13 @@ class EFTLSS:
                 binm = np.vstack(P.interp_matrices(co.k, keff))
             g = P.GridConfig(Nl=Nl, kmax=cfg.get("kmax", 0.3), with_NNLO=co.with_NNLO, optiresum=co.optiresum)
             proj = None
-            if window is not None or binm is not None or req["chained"] or fiber is not None:
+            if custom is not None:
+                proj = P.compose_projection(g, window=custom["matrix"], icc=None, binning=binm, chained=req["chained"],
+                                            fiber=None if fiber is None else fiber.matrix(),
+                                            fiber_st=False if fiber is None else fiber.fiberst,
+                                            window_stoch=custom["matrix_st"], window_picc=custom["picc"])
+                proj["kout"] = keff
+            elif window is not None or binm is not None or req["chained"] or fiber is not None:
                 proj = P.compose_projection(
                     g, window=None if window is None else window_matrix(window),
                     icc=None if icc is None else dict(matrix=icc.effective_matrix(), PSN_times_Pshot=icc.PSN),

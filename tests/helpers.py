@@ -39,3 +39,28 @@ def option_plan(common, resum):
     return P.build_tracer_plan(Nl=common.get("Nl", 3), optiresum=common.get("optiresum", False),
                                ircutoff=common.get("IRcutoff", False), kIR=common.get("kIR"),
                                lambda_ir=resum.get("LambdaIR", 0.2))
+
+
+class MatrixWindow:
+    """A reference-style custom window plugin (theory.py:62-72): numpy code with an in-place `.Window(bird)`, applying a
+    given (Na, Nk, Nl, Nk) operator to every term array except - optionally - the stochastic ones, and a constant to Picc."""
+
+    def __init__(self, matrix, picc=None, window_st=True, co=None, icc=None, name=None):
+        self.matrix, self.picc, self.window_st, self.co, self.icc, self.name = np.asarray(matrix, float), picc, window_st, co, icc, name
+
+    def Window(self, bird):
+        f = lambda T: np.einsum("akln,lin->aik", self.matrix, T)
+        bird.P11l, bird.Pctl, bird.Ploopl = f(bird.P11l), f(bird.Pctl), f(bird.Ploopl)
+        if bird.co.with_NNLO:
+            bird.PctNNLOl = f(bird.PctNNLOl)
+        if self.window_st:
+            bird.Pstl = f(bird.Pstl)
+        if self.picc is not None:
+            bird.Picc = bird.Picc + self.picc
+
+
+class SquaringWindow(MatrixWindow):
+    """not linear: must be refused at plan build"""
+
+    def Window(self, bird):
+        bird.Ploopl = bird.Ploopl**2

@@ -330,3 +330,26 @@ def test_theory_and_likelihood_are_graph_capturable(dr16_setup):
     torch.cuda.synchronize()
     assert np.array_equal(_np(g_logp), eager) and not _np(g_status).any()
     assert "LRG_NGC_alperp" in th.derived  # evaluated on demand, after the capture
+
+
+def test_custom_window_plugin_through_eftlss(golden2):
+    """`with_window: "helpers.MatrixWindow"` (theory.py:62-72, :370-377): the plugin's operator - here the reference's
+    window + integral-constraint operator of config 2 - is probed at plan build and composed with the binning; the
+    batched terms reproduce the reference's binned goldens."""
+    import helpers
+    from eftpipe_b200 import theory
+
+    g = golden2
+    ap = json.loads(str(g["ap"]))
+    tracers = {"LRG": dict(prefix="", z=float(g["z"]), nd=4.5e-5, km=0.7, kr=0.25, with_IRresum=True, with_APeffect=True,
+                           APeffect=dict(rdrag_AP=147.66, h_AP=0.6777, **ap), with_window="helpers.MatrixWindow",
+                           window=dict(matrix=0.95 * g["Weff_LRG"], picc=-g["PSN"] * float(g["Pshot"])))}
+    th = theory.EFTLSS(tracers).must_provide(
+        {"nonlinear_Plk_grid": {"LRG": {"ls": [0, 2, 4], "binned": True, "binning": {"kout": g["kout"]}}}}).initialize()
+    th.calculate({"LRG": dict(pkh=g["plin"], f=g["f"], DA=g["DA"], H=g["H"])})
+    bm, _ = th.get_nonlinear_Plk_terms("LRG")
+    nk = g["kout"].size
+    T = helpers.split_terms(_np(bm).reshape(3, nk, 24, -1)[..., : len(g["f"])].transpose(3, 0, 2, 1))
+    for name, arr in T.items():
+        assert rowmax_rel(arr, g["bin_" + name]) <= TOL, name
+    assert rowmax_rel(th.info["LRG"]["picc"].reshape(3, nk), g["bin_Picc"][0]) <= TOL

@@ -141,3 +141,41 @@ def test_linear_power_file_extractor_matches_reference():
     assert arr.cosmo()["pkh"] is pkh and boltzmann.find_boltzmann_extractor(arr) is arr
     with pytest.raises(NotImplementedError):
         boltzmann.find_boltzmann_extractor("classynu")
+
+
+def test_custom_window_plugins_are_probed_into_operators(golden2):
+    """theory.py:62-72 seam: a class found by dotted path with an in-place `.Window(bird)` becomes a fixed operator."""
+    import helpers
+    from eftpipe_b200 import plugins, pybird
+
+    co = pybird.Common(Nl=3)
+    Weff = golden2["Weff_LRG"]
+    picc = -golden2["PSN"] * float(golden2["Pshot"])
+    cls = plugins.find_window_constructor("helpers.MatrixWindow")
+    assert cls is helpers.MatrixWindow and plugins.find_window_constructor("auto").__name__ == "Window"
+    op = plugins.probe_linear_stage(cls(0.95 * Weff, picc=picc, co=co).Window, co)
+    assert np.array_equal(op["matrix"], 0.95 * Weff) and op["matrix_st"] is None
+    assert np.array_equal(op["picc"], picc)
+    op = plugins.probe_linear_stage(cls(Weff, window_st=False, co=co).Window, co)  # stochastic terms left alone
+    assert np.array_equal(op["matrix_st"].reshape(150, 150), np.eye(150))
+    with pytest.raises(ValueError):
+        plugins.probe_linear_stage(helpers.SquaringWindow(Weff, co=co).Window, co)
+
+
+def test_reference_window_class_as_a_plugin(golden2):
+    """The live reference's own Window class, driven as a plugin: probing reproduces the effective operator the
+    reference applies (golden Weff_LRG).  Needs /root/reference (build container only)."""
+    import os
+
+    import refload
+    from eftpipe_b200 import plugins
+
+    if not refload.available():
+        pytest.skip("reference tree not mounted")
+    ref = refload.load()
+    co = ref.pybird.Common(Nl=3, No=3, kmax=0.3, kmA=0.7, krA=0.25, ndA=4.5e-5)
+    win = ref.window.Window(window_configspace_file=os.path.join(refload.REFERENCE_ROOT, "data", "DR16_noric", "win_NGC_LRG.txt"),
+                            co=co, accboost=4, windowk=0.1, load=False, save=False)
+    op = plugins.probe_linear_stage(win.Window, co)
+    assert rowmax_rel(op["matrix"].reshape(150, 150), golden2["Weff_LRG"].reshape(150, 150)) <= 1e-12
+    assert op["matrix_st"] is None and not op["picc"].any()
