@@ -26,6 +26,24 @@ _KNOWN = {"prefix", "z", "nd", "km", "kr", "cross", "provider", "use_cb", "with_
           "binning", "basis", "chained", "ls", "Nl", "optiresum", "IRcutoff", "kIR"}
 
 
+def _construct(cls, cfg, **fixed):
+    """`tools.Initializer` (tools.py:176-205): validate a plugin's yaml sub-dict against the constructor signature before
+    building it - unknown keyword / missing positional argument -> LoggedError, as in the reference."""
+    import inspect
+
+    params = inspect.signature(cls).parameters
+    has_var_kw = any(p.kind is p.VAR_KEYWORD for p in params.values())
+    for k in cfg:
+        if k not in params and not has_var_kw:
+            raise LoggedError(f"{cls!r} does not have keyword {k}")
+    for k, p in params.items():
+        if p.kind in (p.VAR_KEYWORD, p.VAR_POSITIONAL) or k == "self":
+            continue
+        if p.default is p.empty and k not in cfg and k not in fixed:
+            raise LoggedError(f"missing positional argument {k}")
+    return cls(**{**cfg, **fixed})
+
+
 def _merge(default, cfg):
     out = deepcopy(default)
     for k, v in cfg.items():
@@ -114,7 +132,7 @@ class EFTLSS:
             if cfg.get("with_APeffect"):
                 apc = dict(cfg.get("APeffect") or {})
                 apc.setdefault("z_AP", cfg["z"])  # theory.py:458: z_AP defaults to the tracer's z
-                apo = APeffect(co=Common(Nl=Nl), **apc)
+                apo = _construct(APeffect, apc, co=Common(Nl=Nl))
                 ap = dict(DA=apo.DA, H=apo.H, nbinsmu=apc.get("nbinsmu", 200), accboost=apc.get("accboost", 1), APst=apo.APst)
                 self.info.setdefault(name, {})["ap"] = apo
             window = icc = custom = None
@@ -122,17 +140,17 @@ class EFTLSS:
             if ww:
                 wc = dict(cfg.get("window") or {})
                 if cfg.get("icc"):
-                    icc = IntegralConstraint(co=co, **cfg["icc"])
+                    icc = _construct(IntegralConstraint, dict(cfg["icc"]), co=co)
                 if isinstance(ww, str) and ww not in ("auto", "default"):
                     # theory.py:62-72, :370-377: a class by dotted path with an in-place `.Window(bird)`; probed once
                     # into a fixed operator (plugins.probe_linear_stage) - ICC and the Picc constant included
-                    plugin = find_window_constructor(ww)(**wc, co=co, icc=icc, name=f"{name}.window")
+                    plugin = _construct(find_window_constructor(ww), wc, co=co, icc=icc, name=f"{name}.window")
                     custom = probe_linear_stage(plugin.Window, co)
                 else:
-                    window = Window(co=co, icc=icc, **wc)
+                    window = _construct(Window, wc, co=co, icc=icc)
             fiber = None
             if cfg.get("with_fiber"):  # theory.py:378-385, :482-485
-                fiber = FiberCollision(co=co, **dict(cfg.get("fiber") or {}))
+                fiber = _construct(FiberCollision, dict(cfg.get("fiber") or {}), co=co)
             binm = None
             keff = co.k
             if req["binned"]:

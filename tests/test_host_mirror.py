@@ -179,3 +179,17 @@ def test_reference_window_class_as_a_plugin(golden2):
     op = plugins.probe_linear_stage(win.Window, co)
     assert rowmax_rel(op["matrix"].reshape(150, 150), golden2["Weff_LRG"].reshape(150, 150)) <= 1e-12
     assert op["matrix_st"] is None and not op["picc"].any()
+
+
+def test_plugin_configuration_is_validated_like_the_reference_initializer():
+    """tools.py:176-205: unknown keyword / missing positional argument in a plugin's yaml sub-dict -> LoggedError"""
+    from eftpipe_b200 import pybird, theory
+    from eftpipe_b200.marginal import LoggedError
+
+    co = pybird.Common(Nl=2)
+    with pytest.raises(LoggedError, match="does not have keyword"):
+        theory._construct(pybird.APeffect, dict(Om_AP=0.3, z_AP=0.5, nbins_mu=100), co=co)
+    with pytest.raises(LoggedError, match="missing positional argument"):
+        theory._construct(pybird.FiberCollision, dict(fs=0.6), co=co)
+    ap = theory._construct(pybird.APeffect, dict(Om_AP=0.3, z_AP=0.5), co=co)
+    assert ap.nbinsmu == 200
