@@ -78,6 +78,63 @@ def flatten_rows(ls, nk, mask=None):
     return np.array(rows, dtype=np.int32)
 
 
+def extract_multipole_info(names):
+    """likelihood.py:48-62: ("P0", "P2", "k", ...) -> ("P", [0, 2])"""
+    import re
+
+    pattern = re.compile(r"^([A-Za-z]+)(\d+)$")
+    symbols, ells = set(), []
+    for x in names:
+        if match := pattern.match(x):
+            s, e = match.groups()
+            symbols.add(s)
+            ells.append(int(e))
+    if len(symbols) == 0:
+        raise ValueError("no valid multipole name found")
+    if len(symbols) != 1:
+        raise ValueError(f"ambiguous multipole names: {symbols}")
+    return symbols.pop(), sorted(ells)
+
+
+def find_reader_else_default(name, default, **kwargs):
+    """reader.py:43-62: "default" / None, or a dotted path to `fn(path, **kwargs)`"""
+    if (name or "default") == "default":
+        return default
+    import importlib
+
+    module_name, callable_name = name.rsplit(".", 1)
+    fn = getattr(importlib.import_module(module_name), callable_name)
+    return lambda path: fn(path, **kwargs)
+
+
+def read_pkl(path, **kwargs):
+    """reader.py:29-40: a commented-header text table ("# k P0 P2 P4"); without a header the names are inferred.
+    Returns (column names, 2-d array); column 0 is k."""
+    names = None
+    with open(path) as fh:
+        for line in fh:
+            if not line.startswith("#"):
+                break
+            toks = line.lstrip("#").split()
+            if names is None and len(toks) >= 2 and all("=" not in t for t in toks):
+                names = toks
+    arr = np.atleast_2d(np.loadtxt(path, **kwargs))
+    if names is None or len(names) != arr.shape[1]:
+        names = ["k"] + [f"P{2 * i}" for i in range(arr.shape[1] - 1)]
+    return names, arr
+
+
+def _as_table(obj):
+    """(names, array) from what a data reader returns: that pair, a pandas DataFrame (reader.py convention: first column
+    is k), or a bare array"""
+    if isinstance(obj, tuple):
+        return list(obj[0]), np.asarray(obj[1], float)
+    if hasattr(obj, "columns") and hasattr(obj, "to_numpy"):
+        return [str(c) for c in obj.columns], obj.to_numpy(dtype=float)
+    arr = np.asarray(obj, float)
+    return ["k"] + [f"P{2 * i}" for i in range(arr.shape[1] - 1)], arr
+
+
 @dataclass
 class MultipoleInfo:
     """likelihood.py:225-272 for an in-memory table (k, then one column per multipole in `ls_tot`)."""
@@ -94,8 +151,18 @@ class MultipoleInfo:
     data_vector: np.ndarray = field(repr=False, default=None)
 
     @classmethod
-    def load(cls, table, ls, ls_tot=None, kmin=None, kmax=None, symbol="P"):
-        table = np.loadtxt(table) if isinstance(table, (str, bytes)) else np.asarray(table, float)
+    def load(cls, table=None, ls=None, ls_tot=None, kmin=None, kmax=None, symbol=None, path=None, reader="default",
+             reader_kwargs=None):
+        """`path` / `reader` / `reader_kwargs` are the reference's yaml keys (likelihood.py:241-252): the multipole symbol
+        and the available ells come from the column names; `table` takes an in-memory (k, multipoles...) array."""
+        if path is not None or isinstance(table, (str, bytes)):
+            names, table = _as_table(find_reader_else_default(reader, read_pkl, **(reader_kwargs or {}))(path or table))
+            fsym, ftot = extract_multipole_info(names)
+            cols = [names.index(f"{fsym}{ell}") for ell in ftot]
+            table = np.column_stack([table[:, 0]] + [table[:, c] for c in cols])
+            symbol, ls_tot = symbol or fsym, ls_tot or ftot
+        table = np.asarray(table, float)
+        symbol = symbol or "P"
         ls = [ls] if isinstance(ls, int) else list(ls)
         ls_tot = list(ls_tot) if ls_tot is not None else [2 * i for i in range(table.shape[1] - 1)]
         if missing := set(ls).difference(ls_tot):
@@ -246,7 +313,7 @@ class EFTLike(Marginalizable):
         self.chained, self.with_binning = as_dict(chained), as_dict(with_binning)
         self.with_interp = as_dict(with_interp)
         self.binning = as_dict(binning or {})
-        self.cov = cov if isinstance(cov, dict) else {"matrix": cov}
+        self.cov = cov if isinstance(cov, dict) else ({"path": cov} if isinstance(cov, (str, bytes, list)) else {"matrix": cov})
         self.marg, self.jeffreys = marg or {}, jeffreys
         self.likelihood_prefix = likelihood_prefix or "eftlike_"
         self.marg_param_prefix = marg_param_prefix
@@ -259,8 +326,16 @@ class EFTLike(Marginalizable):
         self.ndata = self.data_vector.size
         for t, m in self.minfodict.items():
             self.binning[t] = dict(self.binning.get(t) or {}, kout=m.kout)
-        mat = self.cov["matrix"]
-        cov = np.loadtxt(mat) if isinstance(mat, (str, bytes)) else np.array(mat, float)
+        if "path" in self.cov:  # likelihood.py:337-347: reader by dotted path, a list of paths is block-diagonal
+            import scipy.linalg
+
+            rd = find_reader_else_default(self.cov.get("reader"), lambda q: np.loadtxt(q, **self.cov.get("reader_kwargs", {})),
+                                          **self.cov.get("reader_kwargs", {}))
+            path = self.cov["path"]
+            cov = scipy.linalg.block_diag(*[np.asarray(rd(q), float) for q in path]) if isinstance(path, list) else np.array(rd(path), float)
+        else:
+            mat = self.cov["matrix"]
+            cov = np.loadtxt(mat) if isinstance(mat, (str, bytes)) else np.array(mat, float)
         cov = cov / self.cov.get("rescale", 1)
         self.hartlap = None
         if (Nreal := self.cov.get("Nreal")) is not None:

@@ -193,3 +193,38 @@ def test_plugin_configuration_is_validated_like_the_reference_initializer():
         theory._construct(pybird.FiberCollision, dict(fs=0.6), co=co)
     ap = theory._construct(pybird.APeffect, dict(Om_AP=0.3, z_AP=0.5), co=co)
     assert ap.nbinsmu == 200
+
+
+def test_likelihood_data_and_covariance_readers(tmp_path):
+    """likelihood.py:26-62, :241-252, :337-347: yaml-style `path` / `reader` / `reader_kwargs`, multipole symbol and ells
+    from the header, block-diagonal covariance from a list of paths."""
+    import os
+
+    from eftpipe_b200 import likelihood as lk
+
+    d = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "eftpipe_b200", "data", "dr16_ngc.npz")))
+    pq = tmp_path / "NGC_ELG_Q.txt"
+    np.savetxt(pq, d["NGC_ELG_Q"], header="k Q0 Q2\nPshot=123.4", comments="# ")
+    m = lk.MultipoleInfo.load(path=str(pq), ls=[0, 2], kmin=0.03, kmax=0.20)
+    ref = lk.MultipoleInfo.load(table=d["NGC_ELG_Q"], ls=[0, 2], kmin=0.03, kmax=0.20, symbol="Q")
+    assert m.symbol == "Q" and m.ls_tot == [0, 2] and np.array_equal(m.data_vector, ref.data_vector)
+    assert lk.extract_multipole_info(["k", "P0", "P4", "P2"]) == ("P", [0, 2, 4])
+    with pytest.raises(ValueError):
+        lk.extract_multipole_info(["k", "P0", "Q2"])
+    nohdr = tmp_path / "plain.txt"
+    np.savetxt(nohdr, d["NGC_LRG_P"])
+    assert lk.MultipoleInfo.load(path=str(nohdr), ls=[0, 2, 4], kmin=0.02, kmax=0.2).ls_tot == [0, 2, 4]
+    # covariance: list of paths -> block diagonal; custom reader by dotted path
+    c = d["cov_NGC_L024_P"]
+    n = c.shape[0]
+    pa, pb = tmp_path / "a.txt", tmp_path / "b.txt"
+    np.savetxt(pa, c)
+    np.savetxt(pb, 2.0 * c)
+    like = lk.EFTLike(tracers=["LRG"], data=dict(path=str(nohdr), ls=[0, 2, 4], kmin=0.02, kmax=0.20, reader="numpy.loadtxt"),
+                      cov=dict(path=str(pa), reader="numpy.loadtxt", Nreal=1000))
+    like2 = lk.EFTLike(tracers=["LRG"], data=dict(table=d["NGC_LRG_P"], ls=[0, 2, 4], kmin=0.02, kmax=0.20), cov=dict(matrix=c, Nreal=1000))
+    assert np.array_equal(like.invcov, like2.invcov) and np.array_equal(like.data_vector, like2.data_vector)
+    two = lk.EFTLike(tracers=["A", "B"], data={t: dict(table=d["NGC_LRG_P"], ls=[0, 2, 4], kmin=0.02, kmax=0.20) for t in ("A", "B")},
+                     cov=dict(path=[str(pa), str(pb)], Nreal=1000))
+    nd = like2.ndata
+    assert two.ndata == 2 * nd and np.allclose(two.invcov[nd:, nd:] * 2.0, two.invcov[:nd, :nd]) and not two.invcov[:nd, nd:].any()
