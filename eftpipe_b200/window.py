@@ -204,14 +204,20 @@ class Window:
         import os
 
         final = self.window_fourier_file
-        tmp = final.with_name(f".{final.stem}.{os.getpid()}.tmp.npy")
-        np.save(tmp, self.Wal)
-        os.replace(tmp, final)
-        if self._create_meta:
-            mtmp = final.with_name(f".{final.stem}.{os.getpid()}.tmp.json")
-            with mtmp.open("w") as fh:
-                json.dump(self.meta, fh, indent=2)
-            os.replace(mtmp, final.with_suffix(".json"))
+        try:  # cache IO failures are not fatal (the reference swallows them with a warning, pybird.py:954-956)
+            final.parent.mkdir(parents=True, exist_ok=True)
+            tmp = final.with_name(f".{final.stem}.{os.getpid()}.tmp.npy")
+            np.save(tmp, self.Wal)
+            os.replace(tmp, final)
+            if self._create_meta:
+                mtmp = final.with_name(f".{final.stem}.{os.getpid()}.tmp.json")
+                with mtmp.open("w") as fh:
+                    json.dump(self.meta, fh, indent=2)
+                os.replace(mtmp, final.with_suffix(".json"))
+        except OSError as exc:
+            import warnings
+
+            warnings.warn(f"could not cache the window matrix at {final}: {exc}")
 
     # ---- operators ----
     @property
