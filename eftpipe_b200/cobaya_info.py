@@ -59,3 +59,37 @@ def load_info(info, root=None, cache_dir=None):
     for like in likes.values():
         like.initialize_with_provider(th)
     return th, likes
+
+
+def resolve_params(info, sampled):
+    """Evaluate the `params:` block of a Cobaya input for a batch of sampled points: fixed `value: <number>` entries and
+    derived-input entries `value: 'lambda a, b: ...'` (e.g. b2, b4 from c2, c4) are computed from `sampled` (dict name ->
+    scalar or (B,) array), the way Cobaya feeds them to the theory.  Returns a dict with everything that could be resolved;
+    output-only `derived:` lambdas are ignored."""
+    import inspect
+
+    import numpy as np
+
+    out = {k: np.asarray(v, float) for k, v in sampled.items()}
+    pending = {}
+    for name, spec in (info.get("params") or {}).items():
+        if name in out:
+            continue
+        if isinstance(spec, (int, float)):
+            out[name] = np.asarray(float(spec))
+        elif isinstance(spec, dict) and "value" in spec:
+            v = spec["value"]
+            if isinstance(v, (int, float)):
+                out[name] = np.asarray(float(v))
+            elif isinstance(v, str) and v.strip().startswith("lambda"):
+                pending[name] = eval(v, {"np": np, "numpy": np})  # noqa: S307 - the user's own input file, as Cobaya does
+    progress = True
+    while pending and progress:
+        progress = False
+        for name, fn in list(pending.items()):
+            args = list(inspect.signature(fn).parameters)
+            if all(a in out for a in args):
+                out[name] = np.asarray(fn(*[out[a] for a in args]), float)
+                del pending[name]
+                progress = True
+    return out

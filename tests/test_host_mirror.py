@@ -228,3 +228,25 @@ def test_likelihood_data_and_covariance_readers(tmp_path):
                      cov=dict(path=[str(pa), str(pb)], Nreal=1000))
     nd = like2.ndata
     assert two.ndata == 2 * nd and np.allclose(two.invcov[nd:, nd:] * 2.0, two.invcov[:nd, :nd]) and not two.invcov[:nd, nd:].any()
+
+
+def test_cobaya_params_block_is_resolved_for_a_batch():
+    """the yaml's `params:` block: fixed values and `value: 'lambda ...'` inputs (b2, b4 from c2, c4) for (B,) arrays"""
+    import yaml
+
+    from eftpipe_b200 import cobaya_info
+
+    info = yaml.safe_load("""
+params:
+  LRG_NGC_b1: {prior: {min: 0, max: 4}, ref: 2.1}
+  LRG_NGC_c2: {prior: {min: -100, max: 100}, drop: true}
+  LRG_NGC_c4: {value: 0, drop: true}
+  LRG_NGC_b2: {value: 'lambda LRG_NGC_c2, LRG_NGC_c4: (LRG_NGC_c2 + LRG_NGC_c4) / np.sqrt(2.)'}
+  LRG_NGC_b4: {value: 'lambda LRG_NGC_c2, LRG_NGC_c4: (LRG_NGC_c2 - LRG_NGC_c4) / np.sqrt(2.)'}
+  S8: {derived: 'lambda omegam, sigma8: sigma8*np.sqrt(omegam/0.3)'}
+""")
+    c2 = np.array([0.3, 0.5, -0.2])
+    p = cobaya_info.resolve_params(info, {"LRG_NGC_b1": [2.0, 2.1, 2.2], "LRG_NGC_c2": c2})
+    np.testing.assert_allclose(p["LRG_NGC_b2"], c2 / np.sqrt(2.0))
+    np.testing.assert_allclose(p["LRG_NGC_b4"], c2 / np.sqrt(2.0))
+    assert float(p["LRG_NGC_c4"]) == 0.0 and "S8" not in p
