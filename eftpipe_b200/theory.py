@@ -197,7 +197,23 @@ class EFTLSS:
     def calculate(self, cosmo: dict):
         """cosmo[tracer] = dict(pkh=(B, 200) on kh = logspace(-5, 0, 200), f=, DA=, H= (B,) [, rdrag, h])."""
         self._state, self._derive_inputs, self._derived = {}, {}, None
+        import os
+
+        import torch
+
+        # tracers are independent pipelines: each runs on its own stream, forked from and joined back into the caller's
+        # stream (capturable); the tails and latency-bound kernels of one tracer fill with the work of the others
+        concurrent = len(self.plans) > 1 and os.environ.get("EFTB_TRACER_STREAMS", "1") != "0"
+        main = torch.cuda.current_stream()
+        if concurrent:
+            if getattr(self, "_streams", None) is None:
+                self._streams = {name: torch.cuda.Stream() for name in self.plans}
+            fork = torch.cuda.Event()
+            fork.record(main)
         for name, dp in self.plans.items():
+          with torch.cuda.stream(self._streams[name]) if concurrent else _nullcontext():
+            if concurrent:
+                self._streams[name].wait_event(fork)
             c = cosmo[name]
             if hasattr(c, "Pkh"):  # a boltzmann.BoltzmannExtractor (theory.py:559-565)
                 c = c.cosmo()
@@ -208,6 +224,12 @@ class EFTLSS:
             self._state[name] = (bm, f_bm)
             self.B = bm.shape[-1] if not hasattr(c["pkh"], "shape") else c["pkh"].shape[0]
             self._derive_inputs[name] = c
+            if concurrent:
+                done = torch.cuda.Event()
+                done.record(self._streams[name])
+                main.wait_event(done)
+                for ten in (bm, f_bm):
+                    ten.record_stream(main)  # allocated on the tracer's stream, consumed on the caller's
         return self
 
     @property
@@ -324,6 +346,14 @@ class PlkInterpolator:
             raise ValueError(f"l={l} not in {self.ls}") from ex
         out = self.fn(k)
         return out[..., idx[0], :] if len(idx) == 1 else out[..., idx, :]
+
+
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
 
 
 def _host(x):
