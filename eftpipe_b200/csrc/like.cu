@@ -3,6 +3,7 @@
 // and the analytic marginalisation  -2 ln P = -F1^T F2^-1 F1 + F0 + ln det(F2 / 2 pi)  (marginal.py:79-196)
 // by a per-point Cholesky factorisation in shared memory.
 #include <math.h>
+#include <vector>
 #include "common.cuh"
 
 #define EFTB_MAX_TRACERS 8
@@ -13,6 +14,7 @@ struct eftb_like {
   int32_t h_nout[EFTB_MAX_TRACERS], h_nterm[EFTB_MAX_TRACERS];
   double* scales = nullptr;
   int32_t *d_tracer = nullptr, *d_row = nullptr, *d_row_g = nullptr;
+  int32_t* res_perm = nullptr;  // rows d * (ngauss + 1) of the vector block: the residual PNG - data of data point d
   double *data = nullptr, *picc = nullptr;
   GemmMatrix invcov;
   int32_t *g_count = nullptr, *g_tracer = nullptr, *g_term = nullptr, *g_var = nullptr;
@@ -297,6 +299,11 @@ int eftb_like_create(const eftb_like_config* cfg, const eftb_like_constants* h, 
   rc |= upload(&L->d_tracer, h->d_tracer, nd);
   rc |= upload(&L->d_row, h->d_row, nd);
   rc |= upload(&L->d_row_g, h->d_row_g ? h->d_row_g : h->d_row, nd);
+  {
+    std::vector<int32_t> perm(nd);
+    for (int d = 0; d < nd; ++d) perm[d] = d * (ng + 1);
+    rc |= upload(&L->res_perm, perm.data(), nd);
+  }
   rc |= upload(&L->data, h->data, nd);
   rc |= upload(&L->picc, h->picc, nd);
   rc |= gemm_upload(h->invcov, 1, nd, nd, &L->invcov);
@@ -315,7 +322,7 @@ int eftb_like_create(const eftb_like_config* cfg, const eftb_like_constants* h, 
 
 void eftb_like_destroy(eftb_like* L) {
   if (!L) return;
-  void* ptrs[] = {L->nout, L->nterm, L->scales, L->par_index, L->eastcoast, L->d_tracer, L->d_row, L->d_row_g, L->data, L->picc,
+  void* ptrs[] = {L->nout, L->nterm, L->scales, L->par_index, L->eastcoast, L->d_tracer, L->d_row, L->d_row_g, L->res_perm, L->data, L->picc,
                   L->g_count, L->g_tracer, L->g_term, L->g_var, L->g_coef, L->sigma_inv, L->sigma_inv_mu};
   for (void* p : ptrs) if (p) cudaFree(p);
   gemm_free(&L->invcov);
@@ -374,6 +381,11 @@ int eftb_like_vectors(const eftb_like* L, int B, const double* const* terms, con
   int rc = fill_vectors(L, Bp, terms, fgrowth, nuis, V, s);
   if (rc) return rc;
   return launch_to_point_major(V, B, Bp, nd * nc, nullptr, vec, s);
+}
+
+int eftb_like_residuals(const eftb_like* L, int B, const void* workspace, double* out, void* stream) {
+  if (!L || !workspace || !out || B < 1) { eftb_set_error("eftb_like_residuals: NULL/invalid argument"); return EFTB_ERR_ARG; }
+  return launch_to_point_major((const double*)workspace, B, eftb_padded_batch(B), L->cfg.ndata, L->res_perm, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -407,6 +407,13 @@ class DeviceLikelihood:
         )
         return (logp, status, best, full) if want_fullchi2 else (logp, status, best)
 
+    def residuals(self, B):
+        """(B, ndata): model minus data, PNG - d, of the last `eval` (read from its workspace, nothing recomputed)"""
+        t = self.torch
+        out = t.empty((B, self.cfg.ndata), dtype=t.float64, device="cuda")
+        _lib.check(self.lib.eftb_like_residuals(self.handle, B, _p(self._ws), _p(out), _stream_ptr(t)), "eftb_like_residuals")
+        return out
+
     def vectors(self, B, terms_bm, f_bm, nuis_bm):
         t = self.torch
         ws, need = self._workspace(B)

@@ -227,6 +227,9 @@ int eftb_like_eval(const eftb_like*, int B, const double* const* terms, const do
 int eftb_like_eval_full(const eftb_like*, int B, const double* const* terms, const double* const* fgrowth,
                         const double* nuis, double* logp, double* bestfit, double* fullchi2, int32_t* status,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* out [B][ndata] (point-major) = PNG - data of the LAST eftb_like_eval / eval_full call that used `workspace`
+ * (likelihood.py:528-549): read back from the vectors that call left there, nothing is recomputed */
+int eftb_like_residuals(const eftb_like*, int B, const void* workspace, double* out, void* stream);
 /* un-marginalised pieces for parity tests: vec [B][ndata][ngauss+1] (point-major) with
  * vec[.,d,0] = PNG[d] - data[d] (likelihood.py:528-549) and vec[.,d,1+g] = PG[g][d] (likelihood.py:483-525) */
 int eftb_like_vectors(const eftb_like*, int B, const double* const* terms, const double* const* fgrowth,

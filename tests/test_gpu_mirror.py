@@ -163,8 +163,10 @@ def test_single_tracer_marginalised_likelihood(chain, golden2, dr16):
         np.testing.assert_allclose(_np(full), ref[:, col + 1], rtol=1e-6)  # marginal.py:129-131 fullchi2
         np.testing.assert_allclose(_np(best), ref[:, col + 2 : col + 8], rtol=1e-5, atol=1e-8)
         assert not _np(status).any()
+        res = _np(dev.residuals(binned.B))  # left in the workspace by eval
         vec = _np(dev.vectors(binned.B, [binned._T.contiguous()], [binned._f_bm], nuis))
         assert rowmax_rel(vec[:, :, 0] + g["lrg_data"], g["marg_PNG"]) <= TOL
+        assert np.array_equal(res, vec[:, :, 0])
 
 
 def test_non_positive_definite_is_flagged_not_fatal(chain, golden2):
