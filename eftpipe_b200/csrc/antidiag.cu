@@ -16,7 +16,7 @@
 // The 4 warps of a CTA share the FFTLog coefficients of their 32 cosmologies in shared memory and each
 // works through its own list of anti-diagonals (host-balanced by pair count, longest-first).  The table is
 // stored in fragment order (1280 B per k-step, compact complex) and streamed through a per-warp ring of
-// shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), two stages ahead.
+// shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), one stage (4 k-steps, 5 KB) ahead.
 #include <algorithm>
 #include <map>
 #include <mutex>
@@ -29,8 +29,8 @@ constexpr int AD_WARPS = 4;
 constexpr int AD_MT = 10;                    // m-tiles: 80 rows >= 2 * 38
 constexpr int AD_NT = 4;                     // n-tiles per warp: 32 cosmologies
 constexpr int AD_KSTEP_BYTES = AD_MT * 8 * 16;  // 10 m-tiles x (2 pairs x 4 channels) complex = 1280 B
-constexpr int AD_S = 2;                      // k-steps per stage
-constexpr int AD_NST = 3;                    // stages in the ring
+constexpr int AD_S = 4;                      // k-steps per stage
+constexpr int AD_NST = 2;                    // stages in the ring
 
 struct AdArgs {
   const double* cre;      // F rows: Re c_n, n = 0..Nmax/2, batch-minor [.][Bp]
