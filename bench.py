@@ -50,7 +50,7 @@ def window_cache_path():
     return os.path.join(d, "win_NGC_LRG_acc4.npy")
 
 
-def host_setup(B, seed=20261018 + 2):
+def host_setup(B, seed=20261018 + 2, device=None):
     """Everything cosmology independent + the synthetic inputs (excluded from all timings)."""
     from eftpipe_b200 import likelihood, pybird, synthetic, window
 
@@ -58,7 +58,7 @@ def host_setup(B, seed=20261018 + 2):
     co = pybird.Common(Nl=3, No=3, kmax=0.3, kmA=0.7, krA=0.25, ndA=4.5e-5)
     t0 = time.time()
     win = window.Window(window_fourier_file=window_cache_path(), window_configspace_array=fx["win_LRG"], co=co,
-                        accboost=4, windowk=0.1)
+                        accboost=4, windowk=0.1, device=device)  # device=False: the reference arm never touches the GPU
     t_window = time.time() - t0
     Pshot = 1.0 / 4.5e-5
     PSN = 1e-3 / co.k[None, :] * np.array([1.0, 0.3, 0.1])[:, None]  # synthetic ICC
@@ -161,7 +161,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    S = host_setup(args.batch)
+    S = host_setup(args.batch, device=False)
     cores = os.cpu_count() or 1
     nproc = max(1, min(cores, 96))
     per_step = nproc * 2
