@@ -25,6 +25,7 @@
 // - per slot a (Nkr x Ns)(Ns x NIR) product with a FIXED left operand: DMMA m8n8k4 with the B fragments built on the
 // fly as base_slot[s] * X(s)^p from two small shared-memory tables (resum_linear_body).
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 #include "common.cuh"
 
@@ -40,10 +41,12 @@ struct ResumArgs {
   int B, Bp, Nk, Ns, NsP, nterm, ncr, Nkr, Nklow, qdeg, row_x, row_y, NQ, KPAD;
   int nslot[3];     // canonical slots of l': 0 = (X, v = l'), 1 + v = (Y, v); nslot = 1 + number of Y orders used
   int nslots;       // every non-zero polynomial as (l', canonical slot)
+  int mma;          // 1: row contraction of the a = 1 half on DMMA (resum_body_mma), 0: scalar sweep (resum_body)
   signed char slot_lp[12], slot_s[12];
 };
 
 constexpr int RL_MCH = 3;  // m8 tiles (k rows) per warp task of the linear-term GEMM
+constexpr int RS_PASS = 16; // s points per warp pass of the DMMA form (4 quads of the m8n8k4 K dimension); NsP is a multiple
 
 __host__ __device__ inline int rl_pitch(int NsP) { return NsP + ((4 - NsP % 16) + 16) % 16; }  // = 4 mod 16: conflict-free B fragments
 
@@ -104,8 +107,8 @@ __device__ __forceinline__ double dot4(const double (&T)[RS_C], const double* ro
 
 // Cs holds the rows this IA contracts with: IA = 0: [NL][1][NsP] (C11); IA = 1: [NL][ncr-1][NsP] (Cct, Cloopl x12[, CctNNLO])
 template <int NL, int NIR, bool NNLO, int IA>
-__device__ __forceinline__ void sweep_chunk(const ResumArgs& a, const double* Qs, const double* Xs, const double* Ys,
-                                            const double* Cs, int l, int ik, double k2, int s0, Accum<NL, NNLO, IA>& A) {
+__device__ __forceinline__ void sweep_chunk(const ResumArgs& a, const double* Ql, const double* Xs, const double* Ys,
+                                            const double* Cs, int cp, int ik, double k2, int s0, Accum<NL, NNLO, IA>& A) {
   // R[v,k,s] of this chunk, shared by every l' (Rt is [v][s][k]: lanes = k read contiguously).  Issued first and
   // consumed only after the first Horner sweep, which hides the L1/L2 latency.
   double Rv[NL][RS_C];
@@ -126,16 +129,16 @@ __device__ __forceinline__ void sweep_chunk(const ResumArgs& a, const double* Qs
   const int nrow = IA ? a.ncr - 1 : 1;
 #pragma unroll
   for (int lp = 0; lp < NL; ++lp) {
-    const double* q = Qs + (size_t)((l * NL + lp) * NIR) * RS_SLOTS;
+    const double* q = Ql + (size_t)(lp * NIR) * RS_SLOTS;
     double T[RS_C];
     if (a.nslot[lp] > 3) horner<NIR, 4, NL>(q, z, yk, Rv, lp, T);
     else horner<NIR, 3, NL>(q, z, yk, Rv, lp, T);
-    const double* crow = Cs + (size_t)lp * nrow * a.NsP + s0;
+    const double* crow = Cs + (size_t)lp * nrow * cp + s0;  // cp: row pitch of Cs
     A.lin[lp] = dot4(T, crow, A.lin[lp]);  // IA = 0: C11, IA = 1: Cct
     if (IA) {
 #pragma unroll
-      for (int i = 0; i < 12; ++i) A.loop[i] = dot4(T, crow + (size_t)(1 + i) * a.NsP, A.loop[i]);
-      if (NNLO) A.nnlo[lp] = dot4(T, crow + (size_t)13 * a.NsP, A.nnlo[lp]);
+      for (int i = 0; i < 12; ++i) A.loop[i] = dot4(T, crow + (size_t)(1 + i) * cp, A.loop[i]);
+      if (NNLO) A.nnlo[lp] = dot4(T, crow + (size_t)13 * cp, A.nnlo[lp]);
     }
   }
 }
@@ -183,6 +186,7 @@ template <int NL, int NIR, bool NNLO, int IA>
 __device__ __forceinline__ void resum_body(const ResumArgs& a) {
   extern __shared__ __align__(16) double sm[];
   constexpr int NQH = NL * NL * NIR * RS_SLOTS;  // this a's half of the expanded Q table
+  constexpr int qls = NL * NIR * RS_SLOTS;  // Q table of one l
   double* Qs = sm;                       // [NL][NL][NIR][4]
   double* Xs = Qs + NQH;                 // [NsP]
   double* Ys = Xs + a.NsP;               // [NsP]
@@ -248,7 +252,7 @@ __device__ __forceinline__ void resum_body(const ResumArgs& a) {
     const int l = task / a.Nkr, ik = task - l * a.Nkr;
     const double k2 = a.kr2[ik];
     A.zero();
-    for (int ch = 0; ch < nchunk; ++ch) sweep_chunk<NL, NIR, NNLO, IA>(a, Qs, Xs, Ys, Cs, l, ik, k2, ch * RS_C, A);
+    for (int ch = 0; ch < nchunk; ++ch) sweep_chunk<NL, NIR, NNLO, IA>(a, Qs + (size_t)l * qls, Xs, Ys, Cs, a.NsP, ik, k2, ch * RS_C, A);
     write_out<NL, NNLO, IA>(a, b, l, ik, A);
   }
   const int warp = tid >> 5, lane = tid & 31;
@@ -257,7 +261,7 @@ __device__ __forceinline__ void resum_body(const ResumArgs& a) {
     const int l = task / a.Nkr, ik = task - l * a.Nkr;
     const double k2 = a.kr2[ik];
     A.zero();
-    for (int ch = lane; ch < nchunk; ch += 32) sweep_chunk<NL, NIR, NNLO, IA>(a, Qs, Xs, Ys, Cs, l, ik, k2, ch * RS_C, A);
+    for (int ch = lane; ch < nchunk; ch += 32) sweep_chunk<NL, NIR, NNLO, IA>(a, Qs + (size_t)l * qls, Xs, Ys, Cs, a.NsP, ik, k2, ch * RS_C, A);
 #pragma unroll
     for (int i = 0; i < NL; ++i) A.lin[i] = warp_sum(A.lin[i]);
     if (IA) {
@@ -274,6 +278,160 @@ __device__ __forceinline__ void resum_body(const ResumArgs& a) {
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+
+// a = 1 half with the row contraction on the tensor pipe.  A warp owns 8 output columns (l,k) at a time
+// and sweeps s in passes of 16: lane = (column r = lane>>2, s offset c4 = lane&3) runs its Horner chains at the 4 points
+// s0 + 4c + c4 (c = 0..3) - which is the A fragment (8 columns x 4 s) of mma.m8n8k4.f64 for "quad" c - so the contraction
+// over s with the 13 (14) rows C[l',i,s] is, per l' and quad, one DMMA per n8 tile of rows; the B fragment is one 8-byte
+// shared load (row pitch = 4 mod 16 doubles: conflict-free) instead of 26 broadcast 16-byte loads per thread and l'.
+// n columns: 0..11 the loop rows, 12 + l' the Cct row of l' (zero for the other l', so the Cct sums stay separate per l'),
+// 16 + l' CctNNLO.  The columns left over by the groups of 8 (129 = 16 x 8 + 1) take the scalar sweep, one warp each.
+template <int NL, int NIR, bool NNLO>
+__device__ __forceinline__ void resum_body_mma(const ResumArgs& a) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int NQL = NL * NIR * RS_SLOTS, qls = NQL;  // Q table of one l
+  constexpr int NT = NNLO ? 3 : 2;
+  const int NsP = a.NsP, CP = NsP + 4, nrow = a.ncr - 1;
+  double* Qs = sm;                 // [NL][NL][NIR][4]
+  double* Xs = Qs + NL * NQL;      // [NsP]
+  double* Ys = Xs + NsP;           // [NsP]
+  double* Cs = Ys + NsP;           // [NL][nrow][CP]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Cs + (size_t)NL * nrow * CP);
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const size_t Bp = a.Bp;
+  for (int s = tid; s < NsP; s += RS_THREADS) {
+    const bool ok = s < a.Ns;
+    Xs[s] = ok ? a.F[(size_t)(a.row_x + s) * Bp + b] : 0.0;
+    Ys[s] = ok ? a.F[(size_t)(a.row_y + s) * Bp + b] : 0.0;
+  }
+  const int npad = NsP - a.Ns;  // the bulk copies bring Ns doubles per row: zero the rest (disjoint from what they write)
+  for (int i = tid; i < NL * nrow * npad; i += RS_THREADS) Cs[(size_t)(i / npad) * CP + a.Ns + i % npad] = 0.0;
+  const double* crb = a.Cr + (size_t)b * NL * a.ncr * a.Ns;             // point-major [b][l][ncr][Ns]
+  const double* qf = a.Qf + (size_t)b * (2 * NL * NQL) + (size_t)NL * NQL;  // a = 1 half of Q^{ll'}(f)
+  if (tid == 0) {
+    const uint32_t rbytes = (uint32_t)(a.Ns * sizeof(double)), qbytes = (uint32_t)(NL * NQL * sizeof(double));
+    const uint32_t bar32 = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar32));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar32), "r"(NL * nrow * rbytes + qbytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(Qs)),
+                 "l"(qf), "r"(qbytes), "r"(bar32)
+                 : "memory");
+    for (int l = 0; l < NL; ++l) {
+      for (int r = 0; r < nrow; ++r)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(Cs + ((size_t)l * nrow + r) * CP)),
+                     "l"(crb + ((size_t)l * a.ncr + 1 + r) * a.Ns), "r"(rbytes), "r"(bar32)
+                     : "memory");
+    }
+  }
+  __syncthreads();  // X, Y are in place; the barrier initialisation is visible
+  {
+    uint32_t ok;
+    do {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+                   : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+    } while (!ok);
+  }
+
+  const int warp = tid >> 5, lane = tid & 31, r = lane >> 2, c4 = lane & 3;
+  const int ntask = NL * a.Nkr, nrg = ntask / 8, rem = ntask - 8 * nrg;
+  // B-fragment rows of this lane (n = 8 t + r): tile 0 -> loop row r; tile 1 -> loop row 8 + r (r < 4) or Cct of l' = r - 4;
+  // tile 2 -> CctNNLO of l' = r.  Offsets are relative to the block of l' and include the lane's s offset.
+  const int off0 = (1 + r) * CP + c4, off1 = (r < 4 ? 9 + r : 0) * CP + c4, off2 = 13 * CP + c4;
+  for (int g = warp; g < nrg; g += RS_THREADS / 32) {
+    const int task = 8 * g + r;
+    const int l = task / a.Nkr, ik = task - l * a.Nkr;
+    const double k2 = a.kr2[ik];
+    const double* Ql = Qs + (size_t)l * qls;
+    double acc[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+    for (int s0 = 0; s0 < NsP; s0 += RS_PASS) {
+      double Rv[NL][RS_C], z[RS_C], yk[RS_C];
+      const double* rbase = a.Rt + (size_t)(s0 + c4) * a.Nkr + ik;
+#pragma unroll
+      for (int v = 0; v < NL; ++v)
+#pragma unroll
+        for (int c = 0; c < RS_C; ++c) Rv[v][c] = __ldg(rbase + ((size_t)v * NsP + 4 * c) * a.Nkr);
+#pragma unroll
+      for (int c = 0; c < RS_C; ++c) {
+        z[c] = k2 * Xs[s0 + 4 * c + c4];
+        yk[c] = k2 * Ys[s0 + 4 * c + c4];
+      }
+#pragma unroll
+      for (int lp = 0; lp < NL; ++lp) {
+        const double* q = Ql + (size_t)(lp * NIR) * RS_SLOTS;
+        double T[RS_C];
+        if (a.nslot[lp] > 3) horner<NIR, 4, NL>(q, z, yk, Rv, lp, T);
+        else horner<NIR, 3, NL>(q, z, yk, Rv, lp, T);
+        const double* cb = Cs + (size_t)lp * nrow * CP + s0;
+        const bool v1 = r < 4 || r - 4 == lp, v2 = r == lp;
+#pragma unroll
+        for (int c = 0; c < RS_C; ++c) {
+          const double b0 = cb[off0 + 4 * c];
+          const double b1 = v1 ? cb[off1 + 4 * c] : 0.0;
+          dmma884(acc[0][0], acc[0][1], T[c], b0);
+          dmma884(acc[1][0], acc[1][1], T[c], b1);
+          if (NNLO) {
+            const double b2 = v2 ? cb[off2 + 4 * c] : 0.0;
+            dmma884(acc[NT - 1][0], acc[NT - 1][1], T[c], b2);
+          }
+        }
+      }
+    }
+    // C fragment: row r (this lane's column (l,k)), n = 8 t + 2 c4 + {0, 1}
+    double* out = a.T + ((size_t)(l * a.Nk + a.Nklow + ik) * a.nterm) * Bp + b;
+    atomicAdd(out + (size_t)(9 + 2 * c4) * Bp, acc[0][0]);      // pybird.py:1444, :1462
+    atomicAdd(out + (size_t)(10 + 2 * c4) * Bp, acc[0][1]);
+    const double lin2 = __shfl_sync(0xffffffffu, acc[1][0], (lane & ~3) | 3);  // n = 14: Cct sum of l' = 2
+    if (c4 < 2) {
+      atomicAdd(out + (size_t)(17 + 2 * c4) * Bp, acc[1][0]);
+      atomicAdd(out + (size_t)(18 + 2 * c4) * Bp, acc[1][1]);
+    } else if (c4 == 2) {
+      const double lin[3] = {acc[1][0], acc[1][1], lin2};
+      for (int i = 0; i < 6; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int lp = 0; lp < NL; ++lp) v = fma(a.lct[lp * 6 + i], lin[lp], v);
+        atomicAdd(out + (size_t)(3 + i) * Bp, v);  // pybird.py:1443, :1446
+      }
+    }
+    if (NNLO) {
+      const double nn2 = __shfl_sync(0xffffffffu, acc[NT - 1][0], (lane & ~3) | 1);  // n = 18
+      if (c4 == 0) {
+        const double nn[3] = {acc[NT - 1][0], acc[NT - 1][1], nn2};
+        for (int i = 0; i < 3; ++i) {
+          double v = 0.0;
+#pragma unroll
+          for (int lp = 0; lp < NL; ++lp) v = fma(a.lctnnlo[lp * 3 + i], nn[lp], v);
+          atomicAdd(out + (size_t)(24 + i) * Bp, v);  // pybird.py:1455-1458
+        }
+      }
+    }
+  }
+  // left-over columns: the scalar sweep with the s-chunks spread over the lanes of one warp
+  const int nchunk = NsP / RS_C;
+  for (int t = warp; t < rem; t += RS_THREADS / 32) {
+    const int task = 8 * nrg + t;
+    const int l = task / a.Nkr, ik = task - l * a.Nkr;
+    const double k2 = a.kr2[ik];
+    Accum<NL, NNLO, 1> A;
+    A.zero();
+    for (int ch = lane; ch < nchunk; ch += 32) sweep_chunk<NL, NIR, NNLO, 1>(a, Qs + (size_t)l * qls, Xs, Ys, Cs, CP, ik, k2, ch * RS_C, A);
+#pragma unroll
+    for (int i = 0; i < NL; ++i) A.lin[i] = warp_sum(A.lin[i]);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) A.loop[i] = warp_sum(A.loop[i]);
+    if (NNLO) {
+#pragma unroll
+      for (int i = 0; i < NL; ++i) A.nnlo[i] = warp_sum(A.nnlo[i]);
+    }
+    if (lane == 0) write_out<NL, NNLO, 1>(a, b, l, ik, A);
+  }
 }
 
 // a = 0 half on the tensor pipe: one CTA = one cosmology; a warp task = (slot, chunk of RL_MCH m8-tiles of k) with all
@@ -398,8 +556,12 @@ __device__ __forceinline__ void resum_linear_body(const ResumArgs& a) {
 // grid (B, 2): blockIdx.y = 0 runs the heavier a = 1 half (issued first), blockIdx.y = 1 the a = 0 half that fills the tail
 template <int NL, int NIR, bool NNLO, int MINB>
 __global__ void __launch_bounds__(RS_THREADS, MINB) resum_kernel(ResumArgs a) {
-  if (blockIdx.y == 0) resum_body<NL, NIR, NNLO, 1>(a);
-  else resum_linear_body<NL, NIR>(a);
+  if (blockIdx.y == 0) {
+    if (a.mma) resum_body_mma<NL, NIR, NNLO>(a);
+    else resum_body<NL, NIR, NNLO, 1>(a);
+  } else {
+    resum_linear_body<NL, NIR>(a);
+  }
 }
 
 // Q^{ll'}_u(f) = sum_d q[u][d] f^d for every cosmology (pybird.py:1367-1380 evaluates the reference's lambdas);
@@ -419,27 +581,32 @@ __global__ void __launch_bounds__(256) resum_q_kernel(const double* __restrict__
 }
 
 template <int NL, int NIR, bool NNLO>
-int run(const ResumArgs& a, cudaStream_t s, int phase) {
+int run(ResumArgs a, cudaStream_t s, int phase) {
   if (phase & EFTB_PHASE_FIRST) {
     dim3 qgrid((a.NQ + 255) / 256, a.B);
     resum_q_kernel<<<qgrid, 256, 0, s>>>(a.qpack, a.f, a.NQ, a.qdeg, a.B, a.Qf);
     EFTB_LAUNCH_CHECK();
   }
   if (!(phase & EFTB_PHASE_SECOND)) return EFTB_OK;
-  size_t smem = sizeof(double) * ((size_t)NL * NL * NIR * RS_SLOTS + 2 * a.NsP + (size_t)NL * (a.ncr - 1) * a.NsP + 2);  // + mbarrier
+  // tuning knob (A/B runs): EFTB_RESUM_DOTS=scalar keeps the row contraction of the a = 1 half on the DFMA pipe
+  static const bool scalar_dots = getenv("EFTB_RESUM_DOTS") && !strcmp(getenv("EFTB_RESUM_DOTS"), "scalar");
+  // the DMMA form sweeps s in passes of RS_PASS and stages its rows by TMA bulk copies (16-byte units)
+  a.mma = !scalar_dots && a.NsP % RS_PASS == 0 && a.Ns % 2 == 0 &&
+          ((reinterpret_cast<uintptr_t>(a.Cr) | reinterpret_cast<uintptr_t>(a.Qf)) & 15) == 0;
+  size_t smem = sizeof(double) * ((size_t)NL * NL * NIR * RS_SLOTS + 2 * a.NsP + (size_t)NL * (a.ncr - 1) * (a.NsP + 4) + 2);  // + mbarrier
   const size_t smem_lin = sizeof(double) * ((size_t)NIR * rl_pitch(a.NsP) + 2 * NL * a.NsP + (size_t)a.KPAD * NIR +
                                             (size_t)a.nslots * NL * a.KPAD + (size_t)NL * NL * NIR * RS_SLOTS);
   if (smem_lin > smem) smem = smem_lin;
   if (smem > 200 * 1024) { eftb_set_error("resum: %zu bytes of shared memory needed", smem); return EFTB_ERR_ARG; }
   static size_t configured = 0;
-  static const int minb = getenv("EFTB_RESUM_MINB") ? atoi(getenv("EFTB_RESUM_MINB")) : 3;  // tuning knob: CTAs per SM
+  static const int minb = getenv("EFTB_RESUM_MINB") ? atoi(getenv("EFTB_RESUM_MINB")) : 4;  // tuning knob: CTAs per SM
   if (smem > configured) {
     EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NNLO, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NNLO, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  if (minb == 4) resum_kernel<NL, NIR, NNLO, 4><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
-  else resum_kernel<NL, NIR, NNLO, 3><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
+  if (minb == 3) resum_kernel<NL, NIR, NNLO, 3><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
+  else resum_kernel<NL, NIR, NNLO, 4><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;
 }
@@ -451,7 +618,7 @@ int run(const ResumArgs& a, cudaStream_t s, int phase) {
 // table qpack[d][a][l][l'][p][slot].
 int resum_pack(eftb_plan* p, const double* R, const double* q) {
   const eftb_config& c = p->cfg;
-  const int Nl = c.Nl, NIR = c.NIR, Na = c.Na, Nn = 2 * NIR * Na, NsP = eftb_round_up(c.Ns, RS_C);
+  const int Nl = c.Nl, NIR = c.NIR, Na = c.Na, Nn = 2 * NIR * Na, NsP = eftb_round_up(c.Ns, RS_PASS);
   if (Nl > 3 || Na != Nl || Na + 1 > RS_SLOTS || c.qdeg > 16) {
     eftb_set_error("resum: unsupported sizes Nl=%d Na=%d qdeg=%d", Nl, Na, c.qdeg);
     return EFTB_ERR_ARG;
