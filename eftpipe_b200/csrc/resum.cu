@@ -77,12 +77,19 @@ template <int NIR, int NS, int NL>
 __device__ __forceinline__ void horner(const double* __restrict__ q, const double (&z)[RS_C], const double (&yk)[RS_C],
                                        const double (&Rv)[NL][RS_C], int lp, double (&T)[RS_C]) {
   double P[NS][RS_C];
+  {  // the two leading coefficients in one step: P = q[NIR-1] z + q[NIR-2] (no multiply-add onto a zero accumulator)
+    const double2 t01 = *reinterpret_cast<const double2*>(q + (NIR - 1) * RS_SLOTS);
+    const double2 t23 = *reinterpret_cast<const double2*>(q + (NIR - 1) * RS_SLOTS + 2);
+    const double2 a01 = *reinterpret_cast<const double2*>(q + (NIR - 2) * RS_SLOTS);
+    const double2 a23 = *reinterpret_cast<const double2*>(q + (NIR - 2) * RS_SLOTS + 2);
+    const double qt[4] = {t01.x, t01.y, t23.x, t23.y}, qa[4] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
-  for (int s = 0; s < NS; ++s)
+    for (int s = 0; s < NS; ++s)
 #pragma unroll
-    for (int c = 0; c < RS_C; ++c) P[s][c] = 0.0;
+      for (int c = 0; c < RS_C; ++c) P[s][c] = fma(qt[s], z[c], qa[s]);
+  }
 #pragma unroll
-  for (int p = NIR - 1; p >= 0; --p) {
+  for (int p = NIR - 3; p >= 0; --p) {
     const double2 a01 = *reinterpret_cast<const double2*>(q + p * RS_SLOTS);
     const double2 a23 = *reinterpret_cast<const double2*>(q + p * RS_SLOTS + 2);
     const double qa[4] = {a01.x, a01.y, a23.x, a23.y};
