@@ -11,12 +11,14 @@
 //
 // Most of those polynomials vanish identically (the X^{p+1} terms of Q^{ll'} couple to a single Bessel order
 // v, the Y X^p terms to 2-3): plan creation keeps, per l', the <= 4 non-zero (kind, v) "slots" (11 of 18
-// polynomials at Nl=3).  One CTA (128 threads) per cosmology: Q(f) is expanded once into shared memory, then
-// each thread owns one (l, k) output column for BOTH a = 0 (linear) and a = 1 (counterterm + loop) and sweeps
-// s in chunks of 4: 2 x 4 slots x 4 points = 32 independent Horner chains fed by broadcast 16-byte shared
-// loads (1 load per 4 DFMA).  A task count that is not a multiple of 128 (3 x 43 = 129) leaves <= 4 tasks
-// over; each is swept by one warp with the s-chunks spread over its lanes and a shuffle reduction.
-// FP64-FMA bound: ~2.4e6 DFMA per cosmology at Nl=3 for the a = 1 half.
+// polynomials at Nl=3).  One CTA (128 threads) per cosmology and a: Q(f) is expanded once (resum_q_kernel) and staged
+// in shared memory with the rows C[l',i,s] by TMA bulk copies.  a = 1 (counterterm + loop rows), default form
+// (resum_body_mma): a warp owns 8 output columns (l,k) and sweeps s in passes of 16; every lane runs 3-4 slots x
+// 4 points of Horner chains fed by broadcast 16-byte shared loads, and its 4 results are the A fragment of
+// mma.m8n8k4.f64, so the contraction with the 13 (14) rows runs on DMMA.  The scalar form (resum_body: thread = one
+// (l,k) column, s in chunks of 4, 13 + 3 accumulators per thread) remains as the fallback for unaligned / odd row
+// sizes and sweeps the columns left over by the groups of 8 (3 x 43 = 129 = 16 x 8 + 1), one warp per column with the
+// s-chunks spread over its lanes and a shuffle reduction.  FP64 bound: ~2.3e6 DFMA per cosmology at Nl=3 for a = 1.
 //
 // The a = 0 half (linear terms) contracts with ONE row per l' (C11), so there the separable form of the reference
 // itself (pybird.py:1409-1441) is 3x cheaper than the sweep:  z^p = k^{2p} X(s)^p, hence
