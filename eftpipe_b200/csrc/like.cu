@@ -163,16 +163,19 @@ __global__ void like_finish_kernel(FinArgs a) {
     }
     const double* pv = a.V + (size_t)ra * Bp + b;
     const double* py = a.Y + (size_t)rb * Bp + b;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    // 8 independent partial sums: 16 loads in flight per thread (the loop is a chain of L2 round trips otherwise)
+    double sp[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     int d = 0;
-    for (; d + 4 <= a.ndata; d += 4) {
-      s0 = fma(pv[(size_t)d * stride], py[(size_t)d * stride], s0);
-      s1 = fma(pv[(size_t)(d + 1) * stride], py[(size_t)(d + 1) * stride], s1);
-      s2 = fma(pv[(size_t)(d + 2) * stride], py[(size_t)(d + 2) * stride], s2);
-      s3 = fma(pv[(size_t)(d + 3) * stride], py[(size_t)(d + 3) * stride], s3);
+    for (; d + 8 <= a.ndata; d += 8) {
+      double v[8], y[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { v[u] = pv[(size_t)(d + u) * stride]; y[u] = py[(size_t)(d + u) * stride]; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sp[u] = fma(v[u], y[u], sp[u]);
     }
-    for (; d < a.ndata; ++d) s0 = fma(pv[(size_t)d * stride], py[(size_t)d * stride], s0);
-    const double sum = (s0 + s1) + (s2 + s3);
+    double st = 0.0;
+    for (; d < a.ndata; ++d) st = fma(pv[(size_t)d * stride], py[(size_t)d * stride], st);
+    const double sum = (((sp[0] + sp[1]) + (sp[2] + sp[3])) + ((sp[4] + sp[5]) + (sp[6] + sp[7]))) + st;
     if (e < ntri) {
       const double v = sum + a.sigma_inv[eg * nG + ej];  // marginal.py:167-175
       F2[((size_t)eg * nG + ej) * LF_PX + lx] = v;
@@ -197,13 +200,13 @@ __global__ void like_finish_kernel(FinArgs a) {
     double dj = F2[((size_t)j * nG + j) * LF_PX + lx];
     for (int k = 0; k < j; ++k) { const double l = F2[((size_t)j * nG + k) * LF_PX + lx]; dj -= l * l; }
     if (!(dj > 0.0)) { ok = false; break; }
-    const double ljj = sqrt(dj);
-    F2[((size_t)j * nG + j) * LF_PX + lx] = ljj;
-    logdet += 2.0 * log(ljj);
+    const double ljj = sqrt(dj), rjj = 1.0 / ljj;
+    F2[((size_t)j * nG + j) * LF_PX + lx] = rjj;  // the diagonal holds 1 / L_jj: the solves below multiply instead of dividing
+    if (!a.jeffreys) logdet += log(dj);           // 2 ln L_jj; not needed without the ln det term (marginal.py:119-120)
     for (int i = j + 1; i < nG; ++i) {
       double s = F2[((size_t)i * nG + j) * LF_PX + lx];
       for (int k = 0; k < j; ++k) s -= F2[((size_t)i * nG + k) * LF_PX + lx] * F2[((size_t)j * nG + k) * LF_PX + lx];
-      F2[((size_t)i * nG + j) * LF_PX + lx] = s / ljj;
+      F2[((size_t)i * nG + j) * LF_PX + lx] = s * rjj;
     }
   }
   if (!ok) {  // reference raises RuntimeError("det of F2ij <= 0") (marginal.py:113-116); here: flag the point
@@ -218,7 +221,7 @@ __global__ void like_finish_kernel(FinArgs a) {
   for (int i = 0; i < nG; ++i) {
     double s = F1[(size_t)i * LF_PX + lx];
     for (int k = 0; k < i; ++k) s -= F2[((size_t)i * nG + k) * LF_PX + lx] * F1[(size_t)k * LF_PX + lx];
-    s /= F2[((size_t)i * nG + i) * LF_PX + lx];
+    s *= F2[((size_t)i * nG + i) * LF_PX + lx];
     F1[(size_t)i * LF_PX + lx] = s;
     quad += s * s;
   }
@@ -230,7 +233,7 @@ __global__ void like_finish_kernel(FinArgs a) {
     for (int i = nG - 1; i >= 0; --i) {
       double s = F1[(size_t)i * LF_PX + lx];
       for (int k = i + 1; k < nG; ++k) s -= F2[((size_t)k * nG + i) * LF_PX + lx] * F1[(size_t)k * LF_PX + lx];
-      s /= F2[((size_t)i * nG + i) * LF_PX + lx];
+      s *= F2[((size_t)i * nG + i) * LF_PX + lx];
       F1[(size_t)i * LF_PX + lx] = s;
       if (a.bestfit) a.bestfit[(size_t)b * nG + i] = s;
     }
