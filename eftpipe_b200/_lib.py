@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("EFTB200_LIB", os.path.join(_HERE, "libeftb200.so"))  # override: A/B testing of kernel variants
+LIB_PATH = os.environ.get("EFTB200_LIB") or os.path.join(_HERE, "libeftb200.so")  # override: A/B testing of kernel variants
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

@@ -33,7 +33,10 @@
 
 namespace {
 
-constexpr int RS_THREADS = 128;
+#ifndef EFTB_RS_THREADS
+#define EFTB_RS_THREADS 128
+#endif
+constexpr int RS_THREADS = EFTB_RS_THREADS;
 constexpr int RS_C = 4;      // s points per chunk
 constexpr int RS_SLOTS = 4;  // polynomial slots per l'
 
@@ -564,7 +567,7 @@ __device__ __forceinline__ void resum_linear_body(const ResumArgs& a) {
 
 // grid (B, 2): blockIdx.y = 0 runs the heavier a = 1 half (issued first), blockIdx.y = 1 the a = 0 half that fills the tail
 template <int NL, int NIR, bool NNLO, int MINB>
-__global__ void __launch_bounds__(RS_THREADS, MINB) resum_kernel(ResumArgs a) {
+__global__ void __launch_bounds__(RS_THREADS, MINB * 128 / RS_THREADS) resum_kernel(ResumArgs a) {
   if (blockIdx.y == 0) {
     if (a.mma) resum_body_mma<NL, NIR, NNLO>(a);
     else resum_body<NL, NIR, NNLO, 1>(a);
