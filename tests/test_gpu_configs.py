@@ -153,3 +153,44 @@ def test_odd_node_count_with_nnlo():
         nl.PsCf(b); orc.set_PsCfl(b); rs.Ps(b); ap.AP(b)
         ref = np.concatenate([b.P11l, b.Pctl, b.Ploopl, b.Pstl, b.PctNNLOl], axis=1)
         assert rowmax_rel(got[i], ref) <= 1e-8
+
+
+_SCALAR_SCRIPT = r"""
+import sys
+import numpy as np
+from eftpipe_b200 import engine, plan, synthetic
+out = sys.argv[1]
+batch = synthetic.make_batch(5, 0.7, seed=77)
+res = {}
+for name, kw in (("nl3", dict(Nl=3)), ("nl2", dict(Nl=2)), ("nnlo", dict(Nl=3, with_NNLO=True)), ("opti", dict(Nl=3, optiresum=True))):
+    got, _ = engine.DevicePlan(plan.build_tracer_plan(**kw)).eval_terms(batch.plin, batch.f)
+    res[name] = got.detach().cpu().numpy()
+np.savez(out, **res)
+"""
+
+
+def test_resum_scalar_fallback_agrees_with_dmma_form(tmp_path):
+    """The a = 1 half of the resummation kernel has two forms: the DMMA row contraction (default) and the scalar sweep
+    that remains as the fallback for unaligned / odd row sizes (and sweeps the left-over columns).  Same inputs through
+    both (the fallback forced by EFTB_RESUM_DOTS=scalar in a fresh process, the knob is read once per process):
+    Nl = 3, Nl = 2, NNLO (third n-tile) and optiresum (52 s nodes padded to 64)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "run.py"
+    script.write_text(_SCALAR_SCRIPT)
+    outs = {}
+    for mode in ("dmma", "scalar"):
+        env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        env.pop("EFTB_RESUM_DOTS", None)
+        if mode == "scalar":
+            env["EFTB_RESUM_DOTS"] = "scalar"
+        out = tmp_path / f"{mode}.npz"
+        subprocess.run([sys.executable, str(script), str(out)], check=True, env=env, cwd=root, timeout=600)
+        outs[mode] = np.load(out)
+    for name in outs["dmma"].files:
+        a, b = outs["dmma"][name], outs["scalar"][name]
+        assert np.isfinite(a).all() and a.shape == b.shape
+        assert rowmax_rel(a, b) <= 1e-11, name  # same algebra, different summation order
