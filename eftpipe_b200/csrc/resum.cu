@@ -568,6 +568,9 @@ __device__ __forceinline__ void resum_linear_body(const ResumArgs& a) {
 // grid (B, 2): blockIdx.y = 0 runs the heavier a = 1 half (issued first), blockIdx.y = 1 the a = 0 half that fills the tail
 template <int NL, int NIR, bool NNLO, int MINB>
 __global__ void __launch_bounds__(RS_THREADS, MINB * 128 / RS_THREADS) resum_kernel(ResumArgs a) {
+#ifdef EFTB_TIMING_ONLY_HALF  // timing builds only (-DEFTB_TIMING_ONLY_HALF=0|1, wrong results): one half alone, same launch
+  if ((int)blockIdx.y != EFTB_TIMING_ONLY_HALF) return;
+#endif
   if (blockIdx.y == 0) {
     if (a.mma) resum_body_mma<NL, NIR, NNLO>(a);
     else resum_body<NL, NIR, NNLO, 1>(a);
