@@ -614,7 +614,7 @@ def stage_profile(dp, like, lib, S, d_plin, d_f, d_DA, d_H, d_cols, terms_bm, B,
     achieved = flops[top] * B / (ms[top] * 1e-3) / 1e12
     roof = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the committed
-            # `ncu --set full` capture at B = 1024 (profiles/r1_top_kernels_v6.txt), scaled to this batch
+            # `ncu --set full` capture at B = 1024 (profiles/r1_resum_kernel_v9.txt, r1_top_kernels_v8.txt), scaled to this batch
             "traffic": NCU_DRAM_BYTES_PER_POINT.get(top, 0.0) * B or None,
             "peak_source": "FP64 measured live on this GPU: max(DFMA probe %.1f, cuBLAS DGEMM 8192^3 %.1f TFLOP/s); "
                            "MEASURED_PEAKS.json has no FP64 entry" % (tf.value, dgemm_tf),
@@ -626,7 +626,8 @@ def stage_profile(dp, like, lib, S, d_plin, d_f, d_DA, d_H, d_cols, terms_bm, B,
 
 from eftpipe_b200 import plan as P  # noqa: E402  (host-only module; used in stage_profile)
 
-# DRAM bytes (read + write) per evaluation point of each stage's kernels, from profiles/r1_top_kernels_v6.txt
+# DRAM bytes (read + write) per evaluation point of each stage's kernels, from profiles/r1_top_kernels_v6.txt and, for the
+# final resum_kernel, r1_resum_kernel_v9.txt (same traffic: 60.74 + 0.14 MB)
 # (ncu --set full --clock-control none, B = 1024, config 2): resum_kernel 60.75 + 0.10 MB; antidiag_kernel 12.9 + 100.1 MB;
 # spectral = regroup 160.0 + 99.8, P22 GEMM 118.2 + 4.7, C(s) GEMM 152.6 + 3.9 MB; ap = Cinv GEMM 29.6, geom 1.2 + 1.3 (its
 # operator stays in L2), apply 70.0 + 4.5 MB
