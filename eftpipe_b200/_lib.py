@@ -90,6 +90,7 @@ SIGNATURES = {
     "eftb_like_workspace_bytes": (_SZ, [_VP, _I]),
     "eftb_like_eval": (C.c_int, [_VP, _I, C.POINTER(_VP), C.POINTER(_VP), _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "eftb_like_eval_full": (C.c_int, [_VP, _I, C.POINTER(_VP), C.POINTER(_VP), _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "eftb_like_eval_priors": (C.c_int, [_VP, _I, C.POINTER(_VP), C.POINTER(_VP), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "eftb_like_residuals": (C.c_int, [_VP, _I, _VP, _VP, _VP]),
     "eftb_like_vectors": (C.c_int, [_VP, _I, C.POINTER(_VP), C.POINTER(_VP), _VP, _VP, _VP, _SZ, _VP]),
 }

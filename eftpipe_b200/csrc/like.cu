@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(128) like_vectors_kernel(VecArgs a) {
 
 struct FinArgs {
   const double *V, *Y, *sigma_inv, *sigma_inv_mu;
+  const double *pp_loc, *pp_sinv;  // per-point Gaussian prior (callable loc / scale, marginal.py:13-20, :60-77): [B][nG] or NULL
   double mu_sigma_mu;
   double *logp, *bestfit, *fullchi2;
   int32_t* status;
@@ -151,6 +152,18 @@ __global__ void like_finish_kernel(FinArgs a) {
   const int b = blockIdx.x * LF_PX + lx;
   const size_t Bp = a.Bp, stride = (size_t)nc * Bp;
   const int ntri = nG * (nG + 1) / 2, nent = ntri + nG + 1;
+  // prior terms: plan constants, or this point's own location / inverse variance (diagonal Sigma^-1; padding lanes: none)
+  const bool pp = a.pp_sinv != nullptr;
+  const double* ps = pp ? a.pp_sinv + (size_t)(b < a.B ? b : 0) * nG : nullptr;
+  const double* pl = pp ? a.pp_loc + (size_t)(b < a.B ? b : 0) * nG : nullptr;
+  auto sinv = [&](int i, int j) { return pp ? (i == j ? ps[i] : 0.0) : a.sigma_inv[i * nG + j]; };
+  auto sinv_mu = [&](int i) { return pp ? ps[i] * pl[i] : a.sigma_inv_mu[i]; };
+  auto mu_s_mu = [&]() {
+    if (!pp) return a.mu_sigma_mu;
+    double s = 0.0;
+    for (int i = 0; i < nG; ++i) s = fma(ps[i] * pl[i], pl[i], s);
+    return s;
+  };
   for (int e = threadIdx.y; e < nent; e += blockDim.y) {
     int eg = 0, ej = 0, ra = 0, rb = 0;
     if (e < ntri) {
@@ -177,13 +190,13 @@ __global__ void like_finish_kernel(FinArgs a) {
     for (; d < a.ndata; ++d) st = fma(pv[(size_t)d * stride], py[(size_t)d * stride], st);
     const double sum = (((sp[0] + sp[1]) + (sp[2] + sp[3])) + ((sp[4] + sp[5]) + (sp[6] + sp[7]))) + st;
     if (e < ntri) {
-      const double v = sum + a.sigma_inv[eg * nG + ej];  // marginal.py:167-175
+      const double v = sum + sinv(eg, ej);  // marginal.py:167-175
       F2[((size_t)eg * nG + ej) * LF_PX + lx] = v;
       F2[((size_t)ej * nG + eg) * LF_PX + lx] = v;
     } else if (e < ntri + nG) {
-      F1[(size_t)eg * LF_PX + lx] = -sum + a.sigma_inv_mu[eg];  // marginal.py:177-185
+      F1[(size_t)eg * LF_PX + lx] = -sum + sinv_mu(eg);  // marginal.py:177-185
     } else {
-      F0[lx] = sum + a.mu_sigma_mu;  // marginal.py:187-196
+      F0[lx] = sum + mu_s_mu();  // marginal.py:187-196
     }
   }
   __syncthreads();
@@ -242,13 +255,13 @@ __global__ void like_finish_kernel(FinArgs a) {
     // marginal.py:129-131: chi^2 of the data at the best-fit bG, r = PNG + bG.PG - d, without the prior terms:
     //   r^T C^-1 r = F0' + 2 bG.g + bG^T F2' bG,  F2' = F2 - Sigma^-1,  g = PG C^-1 (PNG - d) = -(F1 - Sigma^-1 mu),
     //   F0' = F0 - mu^T Sigma^-1 mu.  The strict upper triangle of F2 still holds the values from before the factorisation.
-    double full = F0[lx] - a.mu_sigma_mu;
+    double full = F0[lx] - mu_s_mu();
     for (int i = 0; i < nG; ++i) {
       const double bi = F1[(size_t)i * LF_PX + lx];
-      full -= 2.0 * bi * (F1o[(size_t)i * LF_PX + lx] - a.sigma_inv_mu[i]);
-      full += bi * bi * (F2d[(size_t)i * LF_PX + lx] - a.sigma_inv[i * nG + i]);
+      full -= 2.0 * bi * (F1o[(size_t)i * LF_PX + lx] - sinv_mu(i));
+      full += bi * bi * (F2d[(size_t)i * LF_PX + lx] - sinv(i, i));
       for (int j = i + 1; j < nG; ++j)
-        full += 2.0 * bi * F1[(size_t)j * LF_PX + lx] * (F2[((size_t)i * nG + j) * LF_PX + lx] - a.sigma_inv[i * nG + j]);
+        full += 2.0 * bi * F1[(size_t)j * LF_PX + lx] * (F2[((size_t)i * nG + j) * LF_PX + lx] - sinv(i, j));
     }
     a.fullchi2[b] = full;
   }
@@ -346,6 +359,17 @@ int eftb_like_eval(const eftb_like* L, int B, const double* const* terms, const 
 int eftb_like_eval_full(const eftb_like* L, int B, const double* const* terms, const double* const* fgrowth, const double* nuis,
                         double* logp, double* bestfit, double* fullchi2, int32_t* status, void* workspace, size_t workspace_bytes,
                         void* stream) {
+  return eftb_like_eval_priors(L, B, terms, fgrowth, nuis, nullptr, nullptr, logp, bestfit, fullchi2, status, workspace,
+                               workspace_bytes, stream);
+}
+
+int eftb_like_eval_priors(const eftb_like* L, int B, const double* const* terms, const double* const* fgrowth, const double* nuis,
+                          const double* prior_loc, const double* prior_sigma_inv, double* logp, double* bestfit, double* fullchi2,
+                          int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  if ((prior_loc == nullptr) != (prior_sigma_inv == nullptr)) {
+    eftb_set_error("eftb_like_eval_priors: prior_loc and prior_sigma_inv go together");
+    return EFTB_ERR_ARG;
+  }
   if (!L || !terms || !fgrowth || !nuis || !logp || !status || !workspace || B < 1) {
     eftb_set_error("eftb_like_eval: NULL/invalid argument");
     return EFTB_ERR_ARG;
@@ -359,7 +383,8 @@ int eftb_like_eval_full(const eftb_like* L, int B, const double* const* terms, c
   if (rc) return rc;
   rc = gemm_run(L->invcov, V, Y, nc * Bp, 1, 1, 0, 0, 0, 0, s);
   if (rc) return rc;
-  FinArgs a{V, Y, L->sigma_inv, L->sigma_inv_mu, L->mu_sigma_mu, logp, bestfit, fullchi2, status, B, Bp, nd, L->cfg.ngauss, L->cfg.jeffreys};
+  FinArgs a{V, Y, L->sigma_inv, L->sigma_inv_mu, prior_loc, prior_sigma_inv, L->mu_sigma_mu, logp, bestfit, fullchi2, status, B, Bp, nd,
+            L->cfg.ngauss, L->cfg.jeffreys};
   const int nG = L->cfg.ngauss;
   size_t smem = sizeof(double) * ((size_t)nG * nG * LF_PX + (size_t)3 * nG * LF_PX + LF_PX);
   static size_t configured = 0;

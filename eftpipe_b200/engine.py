@@ -391,9 +391,17 @@ class DeviceLikelihood:
         arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
         return arr
 
-    def eval(self, B, terms_bm, f_bm, nuis_bm, want_bestfit=False, want_fullchi2=False):
-        """(logp, status, bestfit) or, with want_fullchi2, (logp, status, bestfit, fullchi2) - marginal.py:79-137"""
+    def eval(self, B, terms_bm, f_bm, nuis_bm, want_bestfit=False, want_fullchi2=False, prior_loc=None, prior_sigma_inv=None):
+        """(logp, status, bestfit) or, with want_fullchi2, (logp, status, bestfit, fullchi2) - marginal.py:79-137.
+        prior_loc / prior_sigma_inv: (B, nG) device tensors, the per-point Gaussian prior of callable `loc` / `scale`
+        (marginal.py:60-77; diagonal of Sigma^-1) in place of the plan constants."""
         t = self.torch
+        if (prior_loc is None) != (prior_sigma_inv is None):
+            raise ValueError("prior_loc and prior_sigma_inv go together")
+        if prior_loc is not None:
+            for p in (prior_loc, prior_sigma_inv):
+                if tuple(p.shape) != (B, self.cfg.ngauss) or p.dtype != t.float64 or not p.is_cuda or not p.is_contiguous():
+                    raise ValueError(f"per-point priors must be contiguous float64 CUDA tensors of shape ({B}, {self.cfg.ngauss})")
         ws, need = self._workspace(B)
         logp = t.empty(B, dtype=t.float64, device="cuda")
         status = t.empty(B, dtype=t.int32, device="cuda")
@@ -401,8 +409,8 @@ class DeviceLikelihood:
         full = t.empty(B, dtype=t.float64, device="cuda") if want_fullchi2 else None
         ta, fa = self._ptr_array(terms_bm), self._ptr_array(f_bm)
         _lib.check(
-            self.lib.eftb_like_eval_full(self.handle, B, ta, fa, _p(nuis_bm), _p(logp), _p(best), _p(full), _p(status), _p(ws),
-                                         need, _stream_ptr(t)),
+            self.lib.eftb_like_eval_priors(self.handle, B, ta, fa, _p(nuis_bm), _p(prior_loc), _p(prior_sigma_inv), _p(logp),
+                                           _p(best), _p(full), _p(status), _p(ws), need, _stream_ptr(t)),
             "eftb_like_eval",
         )
         return (logp, status, best, full) if want_fullchi2 else (logp, status, best)

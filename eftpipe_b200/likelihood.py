@@ -419,8 +419,10 @@ class EFTLike(Marginalizable):
             if rows_g is not None:
                 spec["rows_g"] = rows_g
             specs.append(spec)
-        sig = self.sigma_inv if gaussian else None
-        mu = self.mu_G if gaussian else None
+        # callable loc / scale (marginal.py:13-20): the prior is per point, evaluated in `calculate`; the plan holds none
+        self.callable_prior = bool(gaussian) and self.has_callable_prior()
+        sig = self.sigma_inv if gaussian and not self.callable_prior else None
+        mu = self.mu_G if gaussian and not self.callable_prior else None
         self.spec = build_spec(specs, self.data_vector, self.invcov, gaussian=gaussian, sigma_inv=sig, mu=mu,
                                jeffreys=self.jeffreys)
         self.device = DeviceLikelihood(self.spec)
@@ -450,10 +452,24 @@ class EFTLike(Marginalizable):
         png = vec[:, :, 0] + torch.as_tensor(self.data_vector, device="cuda")
         return png, vec[:, :, 1:].permute(0, 2, 1)
 
+    def env(self, params):
+        """likelihood.py:560-564: numpy plus every tracer's EFT parameters - here arrays over the batch"""
+        out = {"np": np}
+        for t in self.tracers:
+            for name, val in self.provider.get_eft_params_values_dict(t, params).items():
+                out[name] = val.detach().cpu().numpy() if hasattr(val, "detach") else np.asarray(val, dtype=np.float64)
+        return out
+
     def calculate(self, params, want_bestfit=False):
         """likelihood.py:570-594 for a batch: returns dict(logp=(B,), chi2=(B,), status=(B,) [, bestfit])."""
         B, terms, fs, nuis = self._inputs(params)
-        logp, status, best, full = self.device.eval(B, terms, fs, nuis, want_bestfit=want_bestfit, want_fullchi2=True)
+        loc = sinv = None
+        if self.callable_prior:
+            import torch
+
+            loc, sinv = (torch.as_tensor(a, device="cuda") for a in self.point_priors(self.env(params), B))
+        logp, status, best, full = self.device.eval(B, terms, fs, nuis, want_bestfit=want_bestfit, want_fullchi2=True,
+                                                    prior_loc=loc, prior_sigma_inv=sinv)
         out = {"logp": logp, self.likelihood_prefix + "chi2": -2.0 * logp, "status": status}
         if self.gaussian_names:  # likelihood.py:583-590: chi^2 at the best-fit marginalised parameters
             out[self.likelihood_prefix + "fullchi2"] = full

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define EFTB_ABI_VERSION 2
+#define EFTB_ABI_VERSION 3
 
 typedef enum {
   EFTB_OK = 0,
@@ -227,6 +227,14 @@ int eftb_like_eval(const eftb_like*, int B, const double* const* terms, const do
 int eftb_like_eval_full(const eftb_like*, int B, const double* const* terms, const double* const* fgrowth,
                         const double* nuis, double* logp, double* bestfit, double* fullchi2, int32_t* status,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* the same with a per-point Gaussian prior: prior_loc [B][ngauss] and prior_sigma_inv [B][ngauss] (the diagonal of
+ * Sigma^-1 = 1 / scale^2, all zeros for a point whose scales are infinite) replace the plan constants.  This is the
+ * reference's callable `loc` / `scale` (strings eval'ed against the sampled EFT parameters at every evaluation,
+ * marginal.py:13-20, :60-77, likelihood.py:560-564); both NULL = eftb_like_eval_full */
+int eftb_like_eval_priors(const eftb_like*, int B, const double* const* terms, const double* const* fgrowth,
+                          const double* nuis, const double* prior_loc, const double* prior_sigma_inv, double* logp,
+                          double* bestfit, double* fullchi2, int32_t* status, void* workspace, size_t workspace_bytes,
+                          void* stream);
 /* out [B][ndata] (point-major) = PNG - data of the LAST eftb_like_eval / eval_full call that used `workspace`
  * (likelihood.py:528-549): read back from the vectors that call left there, nothing is recomputed */
 int eftb_like_residuals(const eftb_like*, int B, const void* workspace, double* out, void* stream);

@@ -18,6 +18,7 @@ loggamma).  File:line citations are relative to /root/reference/eftpipe/.
 """
 from __future__ import annotations
 
+import inspect
 import os
 from dataclasses import dataclass, field
 
@@ -742,6 +743,22 @@ def marginalized_logp(PNG, PG, data, invcov, mu_G=None, sigma_inv=None, jeffreys
         return -0.5 * chi2
     r = best @ PG + PNG - data
     return -0.5 * chi2, r @ invcov @ r, best
+
+
+def eval_callable(s, env):
+    """marginal.py:13-20"""
+    fn = eval(s, env)
+    return fn(*(env[p] for p in inspect.getfullargspec(fn).args))
+
+
+def prior_mu_sigma_inv(valid_prior, env):
+    """marginal.py:60-77 `mu_G`, `sigma_inv` for one point: loc / scale may be strings eval'ed against `env`"""
+    loc = [eval_callable(d["loc"], env) if isinstance(d["loc"], str) else d["loc"] for d in valid_prior.values()]
+    std = [eval_callable(d["scale"], env) if isinstance(d["scale"], str) else d["scale"] for d in valid_prior.values()]
+    n = len(std)
+    if np.inf in std:
+        return np.array(loc, dtype=np.float64), np.zeros((n, n))  # :74-75
+    return np.array(loc, dtype=np.float64), np.diag(1 / np.array(std, dtype=np.float64) ** 2)
 
 
 def hartlap(Nreal, ndata):

@@ -169,6 +169,69 @@ def test_single_tracer_marginalised_likelihood(chain, golden2, dr16):
         assert np.array_equal(res, vec[:, :, 0])
 
 
+def test_callable_priors_on_device(chain, golden2):
+    """Callable `loc` / `scale` (marginal.py:13-20, :60-77): the prior of every point is evaluated from its own sampled
+    parameters (`Marginalizable.point_priors`) and enters the kernel as per-point location / inverse variance
+    (eftb_like_eval_priors); against the oracle's marginalisation point by point."""
+    import pybird_oracle as orc
+    import torch
+    from eftpipe_b200 import likelihood, marginal, parambasis
+    from eftpipe_b200.engine import DeviceLikelihood
+
+    g = golden2
+    basis = parambasis.WestCoastBasis(prefix="")
+    binned = chain["binned"]
+    B, nk = binned.B, g["kout"].size
+    names = ["b3", "cct", "cr1", "cr2", "ce0", "cequad"]
+    prior = {
+        "b3": {"loc": "lambda b1: 0.5 * b1", "scale": 4.0},
+        "cct": {"loc": 0.0, "scale": "lambda b1, b2: 2.0 + np.abs(b2)"},
+        "cr1": {"loc": "lambda b2, b4: b2 - b4", "scale": "lambda b4: np.exp(0.1 * b4) * 4"},
+        "cr2": {"loc": 1.5, "scale": 4.0},
+        "ce0": {"loc": 0, "scale": 2.0},
+        "cequad": {"scale": 2.0},
+    }
+
+    class M(marginal.Marginalizable):
+        def marginalizable_params(self):
+            return names
+
+    m = M()
+    m.setup_prior(prior)
+    params = _params(g["nuisance"])
+    sampled = {k: params[k] for k in ("b1", "b2", "b4")}
+    env = {k: np.asarray(v, float) for k, v in sampled.items()}
+    loc, sinv = m.point_priors(env, B)
+    tr = dict(basis=basis, co=chain["co"], nout=3 * nk, nterm=24, rows=np.arange(3 * nk, dtype=np.int32), picc=binned._picc.reshape(-1))
+    spec = likelihood.build_spec([tr], g["lrg_data"], g["lrg_invcov"], gaussian=names, jeffreys=False)
+    dev = DeviceLikelihood(spec)
+    nuis = likelihood.pack_nuisance(torch, [basis], sampled, [binned._f_bm], B, binned._T.shape[-1])
+    args = (B, [binned._T.contiguous()], [binned._f_bm], nuis)
+    logp, status, best, full = dev.eval(*args, want_bestfit=True, want_fullchi2=True,
+                                        prior_loc=torch.as_tensor(loc, device="cuda"), prior_sigma_inv=torch.as_tensor(sinv, device="cuda"))
+    assert not _np(status).any()
+    vec = _np(dev.vectors(*args))
+    for i in range(B):
+        point = {"np": np, **{k: float(v[i]) for k, v in env.items()}}
+        mu, sig = orc.prior_mu_sigma_inv(m.valid_prior, point)
+        ref = orc.marginalized_logp(vec[i, :, 0] + g["lrg_data"], vec[i, :, 1:].T, g["lrg_data"], g["lrg_invcov"], mu_G=mu,
+                                    sigma_inv=sig, jeffreys=False, return_bestfit=True)
+        assert abs(_np(logp)[i] - ref[0]) <= 1e-6 * abs(ref[0])
+        assert abs(_np(full)[i] - ref[1]) <= 1e-6 * abs(ref[1])
+        np.testing.assert_allclose(_np(best)[i], ref[2], rtol=1e-5, atol=1e-8)
+    # constant priors through the per-point entry = the plan-constant path
+    scales = np.array([4, 2, 4, 4, 2, 2], float)
+    mu_c = np.array([0.3, 0, -0.2, 0, 0.1, 0])
+    spec_c = likelihood.build_spec([tr], g["lrg_data"], g["lrg_invcov"], gaussian=names, sigma_inv=np.diag(1 / scales**2), mu=mu_c)
+    a = DeviceLikelihood(spec_c).eval(*args, want_bestfit=True, want_fullchi2=True)
+    tile = lambda v: torch.as_tensor(np.ascontiguousarray(np.tile(v, (B, 1))), device="cuda")
+    b = dev.eval(*args, want_bestfit=True, want_fullchi2=True, prior_loc=tile(mu_c), prior_sigma_inv=tile(1 / scales**2))
+    for x, y in zip((a[0], a[2], a[3]), (b[0], b[2], b[3])):
+        np.testing.assert_allclose(_np(x), _np(y), rtol=1e-12, atol=1e-12)
+    with pytest.raises(ValueError):
+        dev.eval(*args, prior_loc=tile(mu_c))
+
+
 def test_non_positive_definite_is_flagged_not_fatal(chain, golden2):
     """marginal.py:113-116 raises; the batch path flags the point and keeps going."""
     import torch
@@ -306,6 +369,43 @@ def test_multitracer_likelihood_against_oracle(dr16_setup, dr16):
         best = np.array([_np(res["bestfit"]["marg_" + n])[i] for n in names])
         np.testing.assert_allclose(best, ref_best, rtol=1e-4, atol=1e-6)
     assert worst_png <= TOL and worst_pg <= TOL
+
+
+def test_eftlike_with_callable_priors(dr16_setup, dr16):
+    """EFTLike with string `loc` / `scale` entries in `marg` (likelihood.py:560-564 `env` = every tracer's EFT parameters):
+    three tracers, 14 marginalised parameters, Gaussian priors whose location / width follow the sampled b1."""
+    import pybird_oracle as orc
+    from eftpipe_b200 import likelihood
+
+    S = dr16_setup
+    th = S["th"]
+    west = lambda: {n: {"scale": 4.0} for n in ("b3", "cct", "cr1", "cr2", "ce0", "cequad")}
+    lrg, elg = west(), west()
+    lrg["b3"] = {"loc": "lambda LRG_NGC_b1: 0.5 * LRG_NGC_b1", "scale": 2.0}
+    elg["cct"] = {"loc": 0.0, "scale": "lambda ELG_NGC_b1, LRG_NGC_b2: 1.0 + np.abs(ELG_NGC_b1 * LRG_NGC_b2)"}
+    marg = {"LRG_NGC_": lrg, "ELG_NGC_": elg, "X_NGC_ce0": {"scale": 2.0}, "X_NGC_cequad": {"loc": "lambda ELG_NGC_b4: -ELG_NGC_b4", "scale": 2.0}}
+    like = likelihood.EFTLike(
+        tracers=["LRG_NGC", "ELG_NGC", "X_NGC"], chained=[False, True, False],
+        data={"LRG_NGC": dict(table=dr16["NGC_LRG_P"], ls=[0, 2, 4], kmin=0.02, kmax=0.20),
+              "ELG_NGC": dict(table=dr16["NGC_ELG_Q"], ls=[0, 2], kmin=0.03, kmax=0.20, symbol="Q"),
+              "X_NGC": dict(table=dr16["NGC_X_P"], ls=[0, 2, 4], kmin=0.02, kmax=0.20)},
+        cov=dict(matrix=dr16["cov_NGC_L024E02X024_PQP"], Nreal=1000), with_binning=True, jeffreys=False, marg=marg)
+    like.initialize_with_provider(th)
+    assert like.callable_prior and len(like.gaussian_names) == 14
+    th.calculate(S["cosmo"])
+    res = like.calculate(S["params"], want_bestfit=True)
+    png, pg = like.PNG_PG(S["params"])
+    png, pg = _np(png), _np(pg)
+    assert not _np(res["status"]).any()
+    for i in range(S["B"]):
+        point = {"np": np, **{k: float(v[i]) for k, v in S["params"].items()}}
+        mu, sig = orc.prior_mu_sigma_inv(like.valid_prior, point)
+        ref_logp, ref_full, ref_best = orc.marginalized_logp(png[i], pg[i], like.data_vector, like.invcov, mu_G=mu, sigma_inv=sig,
+                                                             jeffreys=False, return_bestfit=True)
+        assert _np(res["logp"])[i] == pytest.approx(ref_logp, rel=1e-6), i
+        assert _np(res[like.likelihood_prefix + "fullchi2"])[i] == pytest.approx(ref_full, rel=1e-6), i
+        best = np.array([_np(res["bestfit"][like.marg_param_prefix + n])[i] for n in like.gaussian_names])
+        np.testing.assert_allclose(best, ref_best, rtol=1e-4, atol=1e-6)
 
 
 def test_theory_and_likelihood_are_graph_capturable(dr16_setup):

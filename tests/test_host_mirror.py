@@ -250,3 +250,69 @@ params:
     np.testing.assert_allclose(p["LRG_NGC_b2"], c2 / np.sqrt(2.0))
     np.testing.assert_allclose(p["LRG_NGC_b4"], c2 / np.sqrt(2.0))
     assert float(p["LRG_NGC_c4"]) == 0.0 and "S8" not in p
+
+
+CALLABLE_PRIOR = {
+    "b3": {"loc": "lambda b1: 0.5 * b1", "scale": 4.0},
+    "cct": {"loc": 0.0, "scale": "lambda b1, b2: 2.0 + np.abs(b2)"},
+    "cr1": {"loc": "lambda b2, b4: b2 - b4", "scale": "lambda b4: np.exp(0.1 * b4) * 4"},
+    "cr2": {"loc": 1.5, "scale": 4.0},
+    "ce0": {"loc": 0, "scale": 2.0},
+    "cequad": {"scale": 2.0},
+}
+
+
+def test_callable_priors_per_point_match_the_reference_evaluation():
+    """marginal.py:13-20, :60-77: string `loc` / `scale` are eval'ed against the sampled EFT parameters at every
+    evaluation.  The mirror evaluates them once per batch with arrays (`point_priors`); row by row this must equal the
+    oracle's per-point restatement and, where the reference tree is mounted, the reference's own `mu_G` / `sigma_inv`."""
+    import pybird_oracle as orc
+    import refload
+    from eftpipe_b200 import marginal
+
+    names = list(CALLABLE_PRIOR)
+
+    class M(marginal.Marginalizable):
+        def marginalizable_params(self):
+            return names
+
+    m = M()
+    m.setup_prior(CALLABLE_PRIOR)
+    assert m.has_callable_prior()
+    with pytest.raises(TypeError):
+        m.mu_G
+    rng = np.random.default_rng(5)
+    B = 7
+    env = {"b1": rng.normal(2.0, 0.3, B), "b2": rng.normal(0.5, 0.5, B), "b4": rng.normal(0.0, 0.5, B)}
+    loc, sinv = m.point_priors(env, B)
+    assert loc.shape == sinv.shape == (B, len(names))
+    ref_cls = None
+    if refload.available():
+        ref = refload.load()
+
+        class R(ref.marginal.Marginalizable):
+            def marginalizable_params(self):
+                return names
+
+            def env(self):
+                return self._env
+
+        ref_cls = R()
+        ref_cls.valid_prior = ref.marginal.Marginalizable.update_prior(ref_cls, CALLABLE_PRIOR)
+        ref_cls._sigma_inv = np.zeros((len(names), len(names)))
+    for i in range(B):
+        point = {"np": np, **{k: float(v[i]) for k, v in env.items()}}
+        mu_o, sig_o = orc.prior_mu_sigma_inv(m.valid_prior, point)
+        np.testing.assert_allclose(loc[i], mu_o, rtol=1e-15)
+        np.testing.assert_allclose(np.diag(sinv[i]), sig_o, rtol=1e-15)
+        if ref_cls is not None:
+            ref_cls._env = point
+            np.testing.assert_allclose(loc[i], ref_cls.mu_G, rtol=1e-15)
+            np.testing.assert_allclose(np.diag(sinv[i]), ref_cls.sigma_inv, rtol=1e-15)
+    # one infinite scale at a point switches the whole prior off there (marginal.py:74-75)
+    m2 = M()
+    m2.valid_prior = {"b3": {"loc": 0, "scale": "lambda b1: np.where(b1 > 2.0, np.inf, 3.0)"}, "cct": {"loc": 1.0, "scale": 2.0}}
+    _, s2 = m2.point_priors(env, B)
+    off = env["b1"] > 2.0
+    assert off.any() and (~off).any()
+    assert not s2[off].any() and np.allclose(s2[~off], [1 / 9.0, 0.25])
