@@ -282,17 +282,10 @@ int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cuda
   const size_t smem = (size_t)2 * (c.Nmax / 2 + 1) * 32 * sizeof(double) + (size_t)AD_WARPS * AD_NST * AD_S * AD_KSTEP_BYTES +
                       AD_WARPS * AD_NST * sizeof(uint64_t);
   if (smem > 227 * 1024) { eftb_set_error("antidiag: Nmax=%d needs %zu bytes of shared memory", c.Nmax, smem); return EFTB_ERR_ARG; }
-  static size_t configured = 0;
-  static int sms = 0;
-  if (smem > configured) {
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(antidiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  if (!sms) {
-    int dev = 0;
-    EFTB_CUDA_CHECK(cudaGetDevice(&dev));
-    EFTB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  static DeviceSmem configured;
+  EFTB_SET_SMEM(configured, antidiag_kernel, smem);
+  const int sms = eftb_sm_count();
+  if (!sms) return EFTB_ERR_CUDA;
   // one wave: CTAs per SM limited by shared memory (and 2 by registers)
   const int per_sm = std::max(1, std::min(2, (int)((227 * 1024) / (smem + 1024))));
   int ctas_per_group = std::max(1, (sms * per_sm) / ngroups);

@@ -369,16 +369,10 @@ int run(ApArgs a, int B, cudaStream_t s, int phase) {
     eftb_set_error("ap: unsupported sizes nmu=%d nterm=%d Nk=%d", a.nmu, a.nterm, a.Nk);
     return EFTB_ERR_ARG;
   }
-  static size_t conf_g = 0, conf_a = 0;
-  if (smem_g > conf_g) {
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(ap_geom_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-    conf_g = smem_g;
-  }
-  if (smem_a > conf_a) {
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(ap_apply_kernel<NL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(ap_apply_kernel<NL, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-    conf_a = smem_a;
-  }
+  static DeviceSmem conf_g, conf_a3, conf_a4;
+  EFTB_SET_SMEM(conf_g, ap_geom_kernel<NL>, smem_g);
+  EFTB_SET_SMEM(conf_a3, (ap_apply_kernel<NL, 3>), smem_a);
+  EFTB_SET_SMEM(conf_a4, (ap_apply_kernel<NL, 4>), smem_a);
   const int chunk = a.nb;  // capacity of the scratch, set by the caller
   for (int b0 = 0; b0 < B; b0 += chunk) {
     a.b0 = b0;

@@ -67,6 +67,25 @@ __global__ void probe_fp64_kernel(double* sink, int iters) {
 
 }  // namespace
 
+int eftb_current_device() {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { eftb_set_error("cudaGetDevice -> %s", cudaGetErrorString(e)); return -1; }
+  return dev;
+}
+
+int eftb_sm_count() {
+  static int sms[EFTB_MAX_DEVICES] = {};
+  const int dev = eftb_current_device();
+  if (dev < 0) return 0;
+  if (dev < EFTB_MAX_DEVICES && __atomic_load_n(&sms[dev], __ATOMIC_ACQUIRE)) return sms[dev];
+  int n = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) { eftb_set_error("cudaDeviceGetAttribute -> %s", cudaGetErrorString(e)); return 0; }
+  if (dev < EFTB_MAX_DEVICES) __atomic_store_n(&sms[dev], n, __ATOMIC_RELEASE);
+  return n;
+}
+
 extern "C" {
 
 int eftb_abi_version(void) { return EFTB_ABI_VERSION; }
@@ -76,9 +95,8 @@ int eftb_padded_batch(int B) { return B < 1 ? 0 : eftb_round_up(B, 32); }
 int eftb_probe_fp64(int iters, double* tflops, void* stream) {
   if (!tflops || iters < 1) { eftb_set_error("eftb_probe_fp64: bad argument"); return EFTB_ERR_ARG; }
   cudaStream_t s = (cudaStream_t)stream;
-  int dev = 0, sms = 0;
-  EFTB_CUDA_CHECK(cudaGetDevice(&dev));
-  EFTB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int sms = eftb_sm_count();
+  if (!sms) return EFTB_ERR_CUDA;
   double* sink = nullptr;
   EFTB_CUDA_CHECK(cudaMalloc(&sink, sizeof(double)));
   cudaEvent_t e0, e1;

@@ -31,6 +31,30 @@ void eftb_set_error(const char* fmt, ...);
 
 static inline int eftb_round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// ---- per-device launch configuration -------------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to a device, not to the process: a process
+// that drives several GPUs must configure every kernel on each of them.  One DeviceSmem per kernel (family) remembers
+// the largest size configured per device; `needs(dev, bytes)` says whether the attribute has to be set (again) on that
+// device.
+#define EFTB_MAX_DEVICES 64
+int eftb_current_device();  // cudaGetDevice, -1 on error (error text set)
+int eftb_sm_count();        // SMs of the current device (cached per device), 0 on error
+struct DeviceSmem {
+  size_t configured[EFTB_MAX_DEVICES] = {};
+  // true: `bytes` exceeds what this device was configured for - the caller sets the attribute and then calls done()
+  bool needs(int dev, size_t bytes) const { return dev < 0 || dev >= EFTB_MAX_DEVICES || bytes > __atomic_load_n(&configured[dev], __ATOMIC_ACQUIRE); }
+  void done(int dev, size_t bytes) { if (dev >= 0 && dev < EFTB_MAX_DEVICES) __atomic_store_n(&configured[dev], bytes, __ATOMIC_RELEASE); }
+};
+#define EFTB_SET_SMEM(state, kernel, bytes)                                                                         \
+  do {                                                                                                              \
+    const int _dev = eftb_current_device();                                                                         \
+    if (_dev < 0) return EFTB_ERR_CUDA;                                                                             \
+    if ((state).needs(_dev, (bytes))) {                                                                             \
+      EFTB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));     \
+      (state).done(_dev, (bytes));                                                                                  \
+    }                                                                                                               \
+  } while (0)
+
 // ---- fixed-operator GEMM:  C[M][N] = A[M][K] X[K][N], A zero-padded to [Mp][Kp] on upload -------
 struct GemmMatrix {       // device copy of a fixed operator, padded for the kernel's tiles
   double* d = nullptr;    // [nbatch][Mp][Kp]

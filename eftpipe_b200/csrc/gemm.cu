@@ -151,18 +151,15 @@ template <int MT, int NW>
 int launch(const GemmArgs& g, int nz, cudaStream_t s) {
   constexpr int BM = 8 * MT, BNW = 32 * NW;
   size_t smem = sizeof(double) * (2 * BM * APITCH + 2 * BK * (BNW + 4));
-  static bool configured = false;
-  if (!configured) {
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(gemm_f64_kernel<MT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static DeviceSmem configured;
+  EFTB_SET_SMEM(configured, (gemm_f64_kernel<MT, NW>), smem);
   dim3 grid((g.N + BNW - 1) / BNW, (g.Mp + BM - 1) / BM, nz);
   gemm_f64_kernel<MT, NW><<<grid, 32 * NW, smem, s>>>(g);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;
 }
 
-int g_sms = 0;
+int g_sms = 0;  // SMs of the device the current gemm_run call targets (refreshed per call from the per-device cache)
 
 // slab height (in m8 tiles) for one launch: CTAs are dealt round-robin to the SMs, so the makespan is about
 // ceil(nCTA / SMs) slabs of (8 MT + fixed per-slab overhead) rows; pick the MT that minimises it
@@ -273,11 +270,8 @@ void gemm_free(GemmMatrix* m) {
 int gemm_run(const GemmMatrix& A, const double* X, double* C, int N, int nz, int zdiv, size_t xs, size_t xs2,
              size_t cs, size_t cs2, cudaStream_t stream, const GemmPointMajor* pm, size_t ldx, size_t ldc) {
   if (!A.d || !X || !C || N % 2 || ldx % 2 || ldc % 2 || (pm && (pm->bp < 2 || pm->bp % 2))) { eftb_set_error("gemm_run: bad arguments"); return EFTB_ERR_ARG; }
-  if (!g_sms) {
-    int dev = 0;
-    EFTB_CUDA_CHECK(cudaGetDevice(&dev));
-    EFTB_CUDA_CHECK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  g_sms = eftb_sm_count();
+  if (!g_sms) return EFTB_ERR_CUDA;
   GemmArgs g{A.d, X, C, A.M, A.K, A.Kp, A.Mp, N, A.nbatch > 1 ? 1 : 0, zdiv, xs, xs2, cs, cs2,
              pm ? pm->bp : 0, pm ? pm->ld : 0, pm ? pm->is : 0, ldx ? ldx : (size_t)N, ldc ? ldc : (size_t)N};
   return launch_mt(choose_mt(g, nz, stream), g, nz, stream);

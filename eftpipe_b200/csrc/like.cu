@@ -46,15 +46,16 @@ __global__ void __launch_bounds__(128) like_vectors_kernel(VecArgs a) {
   const double* term = a.tp.terms[tr] + ((size_t)a.d_row[d] * nt) * Bp + b;
   const double* termg = a.tp.terms[tr] + ((size_t)a.d_row_g[d] * nt) * Bp + b;  // rows of the marginalised derivatives
   const double f = a.tp.fg[tr][b];
-  double par[17];
+  double par[EFTB_NPAR];
 #pragma unroll
-  for (int i = 0; i < 17; ++i) {
-    const int ix = a.par_index[tr * 17 + i];
+  for (int i = 0; i < EFTB_NPAR; ++i) {
+    const int ix = a.par_index[tr * EFTB_NPAR + i];
     par[i] = ix < 0 ? 0.0 : a.nuis[(size_t)ix * Bp + b];
   }
   const double b1A = par[0], b2A = par[1], b3A = par[2], b4A = par[3], cctA = par[4], cr1A = par[5], cr2A = par[6];
   const double b1B = par[7], b2B = par[8], b3B = par[9], b4B = par[10], cctB = par[11], cr1B = par[12], cr2B = par[13];
   const double ce0 = par[14], cemono = par[15], cequad = par[16];
+  const double cn0 = par[17], cn1 = par[18];  // west: cr4, cr6; east: ctilde, - (parambasis.py:96-107)
   const double* sc = a.scales + tr * 6;
   const double kmA = sc[0], krA = sc[1], ndA = sc[2], kmB = sc[3], krB = sc[4], ndB = sc[5];
   double bias[24];
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(128) like_vectors_kernel(VecArgs a) {
   double tv[24];
 #pragma unroll
   for (int i = 0; i < 24; ++i) tv[i] = term[(size_t)i * Bp];
+  const double f2 = f * f, f4 = f2 * f2;
   // same summation grouping as the reference: Plin + Ploop + Pct + Pst + Picc (parambasis.py:38-39)
   double plin = 0.0, ploop = 0.0, pct = 0.0, pst = 0.0;
 #pragma unroll
@@ -105,10 +107,27 @@ __global__ void __launch_bounds__(128) like_vectors_kernel(VecArgs a) {
   for (int i = 9; i < 21; ++i) ploop += bias[i] * tv[i];
 #pragma unroll
   for (int i = 21; i < 24; ++i) pst += bias[i] * tv[i];
+  if (nt > 24) {  // with_NNLO: Pct += bctNNLOAB . PctNNLOl (parambasis.py:96-107, :132-134)
+    double bn0, bn1, bn2;
+    if (!a.eastcoast[tr]) {
+      const double kr4 = (krA * krA) * (krA * krA);
+      bn0 = 0.25 * (b1A * b1A) / kr4 * cn0;
+      bn1 = 0.25 * b1A / kr4 * cn1;
+      bn2 = 0.0;
+    } else {
+      bn0 = cn0 * (-(b1A * b1A) * f4);
+      bn1 = cn0 * (-2.0 * b1A * (f4 * f));
+      bn2 = cn0 * (-(f4 * f2));
+    }
+    pct += (bn0 * term[(size_t)24 * Bp] + bn1 * term[(size_t)25 * Bp]) + bn2 * term[(size_t)26 * Bp];
+  }
   const int nc = a.ngauss + 1;
   double* out = a.V + ((size_t)d * nc) * Bp + b;
   out[0] = (plin + ploop + pct + pst + a.picc[d]) - a.data[d];
-  const double vars[5] = {1.0, b1A, b1B, f, f * f};
+  // dP/dg factors b1A^pa b1B^pb f^pf, code = pa | pb << 2 | pf << 4 (eftb200.h g_var)
+  const double pw_a[4] = {1.0, b1A, b1A * b1A, b1A * b1A * b1A};
+  const double pw_b[4] = {1.0, b1B, b1B * b1B, b1B * b1B * b1B};
+  const double pw_f[8] = {1.0, f, f2, f2 * f, f4, f4 * f, f4 * f2, f4 * f2 * f};
   for (int g = 0; g < a.ngauss; ++g) {
     double v = 0.0;
     for (int e = 0; e < a.g_count[g]; ++e) {
@@ -117,7 +136,10 @@ __global__ void __launch_bounds__(128) like_vectors_kernel(VecArgs a) {
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const double c = a.g_coef[base + q];
-        if (c != 0.0) v += c * vars[a.g_var[base + q]] * termg[(size_t)a.g_term[base + q] * Bp];
+        if (c != 0.0) {
+          const int code = a.g_var[base + q];
+          v += c * (pw_a[code & 3] * pw_b[(code >> 2) & 3] * pw_f[(code >> 4) & 7]) * termg[(size_t)a.g_term[base + q] * Bp];
+        }
       }
     }
     out[(size_t)(1 + g) * Bp] = v;
@@ -310,7 +332,7 @@ int eftb_like_create(const eftb_like_config* cfg, const eftb_like_constants* h, 
   rc |= upload(&L->nout, h->nout, nt);
   rc |= upload(&L->nterm, h->nterm, nt);
   rc |= upload(&L->scales, h->scales, (size_t)nt * 6);
-  rc |= upload(&L->par_index, h->par_index, (size_t)nt * 17);
+  rc |= upload(&L->par_index, h->par_index, (size_t)nt * EFTB_NPAR);
   rc |= upload(&L->eastcoast, h->eastcoast, nt);
   rc |= upload(&L->d_tracer, h->d_tracer, nd);
   rc |= upload(&L->d_row, h->d_row, nd);
@@ -387,11 +409,8 @@ int eftb_like_eval_priors(const eftb_like* L, int B, const double* const* terms,
             L->cfg.ngauss, L->cfg.jeffreys};
   const int nG = L->cfg.ngauss;
   size_t smem = sizeof(double) * ((size_t)nG * nG * LF_PX + (size_t)3 * nG * LF_PX + LF_PX);
-  static size_t configured = 0;
-  if (smem > configured) {
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(like_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static DeviceSmem configured;
+  EFTB_SET_SMEM(configured, like_finish_kernel, smem);
   const int nent = nG * (nG + 1) / 2 + nG + 1;
   dim3 block(LF_PX, nent < 64 ? nent : 64), grid(Bp / LF_PX);
   like_finish_kernel<<<grid, block, smem, s>>>(a);

@@ -613,13 +613,10 @@ int run(ResumArgs a, cudaStream_t s, int phase) {
                                             (size_t)a.nslots * NL * a.KPAD + (size_t)NL * NL * NIR * RS_SLOTS);
   if (smem_lin > smem) smem = smem_lin;
   if (smem > 200 * 1024) { eftb_set_error("resum: %zu bytes of shared memory needed", smem); return EFTB_ERR_ARG; }
-  static size_t configured = 0;
+  static DeviceSmem conf3, conf4;
   static const int minb = getenv("EFTB_RESUM_MINB") ? atoi(getenv("EFTB_RESUM_MINB")) : 4;  // tuning knob: CTAs per SM
-  if (smem > configured) {
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NNLO, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EFTB_CUDA_CHECK(cudaFuncSetAttribute(resum_kernel<NL, NIR, NNLO, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  EFTB_SET_SMEM(conf3, (resum_kernel<NL, NIR, NNLO, 3>), smem);
+  EFTB_SET_SMEM(conf4, (resum_kernel<NL, NIR, NNLO, 4>), smem);
   if (minb == 3) resum_kernel<NL, NIR, NNLO, 3><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
   else resum_kernel<NL, NIR, NNLO, 4><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
   EFTB_LAUNCH_CHECK();

@@ -11,7 +11,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from .marginal import LoggedError, Marginalizable, valid_prior_config
-from .parambasis import BirdComponent, TCT, TLOOP, TST, T11
+from .parambasis import NPAR, BirdComponent, TCT, TLOOP, TST, T11
 from .transformer import f_batch_minor
 
 
@@ -219,10 +219,10 @@ def build_spec(tracers, data, invcov, gaussian=(), sigma_inv=None, mu=None, jeff
     mu = np.zeros(ng) if mu is None else np.asarray(mu, float)
     scales = np.array([[t["co"].kmA, t["co"].krA, t["co"].ndA, t["co"].kmB, t["co"].krB, t["co"].ndB] for t in tracers])
     return dict(
-        ntracer=nt, ndata=ndata, ngauss=ng, npar=17 * nt, jeffreys=bool(jeffreys),
+        ntracer=nt, ndata=ndata, ngauss=ng, npar=NPAR * nt, jeffreys=bool(jeffreys),
         nout=np.array([t["nout"] for t in tracers], dtype=np.int32),
         nterm=np.array([t["nterm"] for t in tracers], dtype=np.int32), scales=scales,
-        par_index=np.arange(17 * nt, dtype=np.int32).reshape(nt, 17),
+        par_index=np.arange(NPAR * nt, dtype=np.int32).reshape(nt, NPAR),
         eastcoast=np.array([int(t["basis"].counterform() == "eastcoast") for t in tracers], dtype=np.int32),
         d_tracer=d_tracer, d_row=d_row, d_row_g=d_row_g, data=data, picc=picc, invcov=np.ascontiguousarray(invcov, float),
         g_count=g_count, g_tracer=g_tracer, g_term=g_term, g_var=g_var, g_coef=g_coef,
@@ -231,9 +231,9 @@ def build_spec(tracers, data, invcov, gaussian=(), sigma_inv=None, mu=None, jeff
 
 
 def pack_nuisance(torch, bases, params, f_list, B, Bp):
-    """(17*ntracer, Bp) batch-minor nuisance array from a parameter dictionary (scalars or (B,) arrays).
+    """(NPAR*ntracer, Bp) batch-minor nuisance array from a parameter dictionary (scalars or (B,) arrays).
     Parameters missing from `params` are 0, as in the reference (`basis.default()`, parambasis.py:234-236)."""
-    nuis = torch.zeros((17 * len(bases), Bp), dtype=torch.float64, device="cuda")
+    nuis = torch.zeros((NPAR * len(bases), Bp), dtype=torch.float64, device="cuda")
     conv = {}
 
     def dev(v):
@@ -251,11 +251,11 @@ def pack_nuisance(torch, bases, params, f_list, B, Bp):
         for i, v in enumerate(cols):
             if isinstance(v, float):
                 if v != 0.0:
-                    nuis[17 * it + i].fill_(v)
+                    nuis[NPAR * it + i].fill_(v)
             else:
-                nuis[17 * it + i, :B] = v
+                nuis[NPAR * it + i, :B] = v
                 if Bp > B:
-                    nuis[17 * it + i, B:] = v[-1]
+                    nuis[NPAR * it + i, B:] = v[-1]
     return nuis
 
 

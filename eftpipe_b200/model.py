@@ -72,6 +72,7 @@ class EFTModel:
 
     def set_icc(self, Pshot, icc_fourier_file=None, **kwargs):
         d = self.tracers["x"]
+        d["with_icc"] = True  # model.py:332
         d["icc"] = dict(Pshot=Pshot, icc_fourier_file=icc_fourier_file, **kwargs)
         return self
 

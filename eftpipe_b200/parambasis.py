@@ -2,10 +2,11 @@
 `reduce_Plk`, `WestCoastBasis`, `EastCoastBasis`, `find_param_basis`, batched on the device.
 
 A basis answers two questions for the CUDA bias-reduction kernel (`like_vectors_kernel`):
-  * `kernel_columns(params, f)`: the 17 west-coast-form inputs b1A..cr2A, b1B..cr2B, ce0, cemono, cequad
-    (parambasis.py:76-83) as per-point tensors / floats / None (= 0);
+  * `kernel_columns(params, f)`: the NPAR = 19 west-coast-form inputs b1A..cr2A, b1B..cr2B, ce0, cemono, cequad
+    (parambasis.py:76-83) and the two NNLO counterterm coefficients (cr4, cr6 west / ctilde, 0 east; :96-107) as
+    per-point tensors / floats (0 = absent);
   * `gaussian_descriptors(co)`: for every Gaussian (analytically marginalisable) parameter the derivative
-    dP/dg as  sum_q coef_q * var_q * term[i_q]  with var in {1, b1A, b1B, f, f^2}
+    dP/dg as  sum_q coef_q * var_q * term[i_q]  with var = b1A^pa b1B^pb f^pf (`var_code`)
     (parambasis.py:249-316 west, :403-454 east).
 """
 from __future__ import annotations
@@ -15,8 +16,18 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-VAR_ONE, VAR_B1A, VAR_B1B, VAR_F, VAR_F2 = 0, 1, 2, 3, 4
-T11, TCT, TLOOP, TST = 0, 3, 9, 21  # offsets of P11l, Pctl, Ploopl, Pstl rows on the term axis
+NPAR = 19  # EFTB_NPAR of include/eftb200.h
+
+
+def var_code(pa=0, pb=0, pf=0):
+    """b1A^pa * b1B^pb * f^pf as the integer the kernel decodes (eftb200.h `g_var`)"""
+    if not (0 <= pa <= 3 and 0 <= pb <= 3 and 0 <= pf <= 7):
+        raise ValueError("derivative factor outside b1^<=3 f^<=7")
+    return pa | pb << 2 | pf << 4
+
+
+VAR_ONE, VAR_B1A, VAR_B1B, VAR_F, VAR_F2 = var_code(), var_code(pa=1), var_code(pb=1), var_code(pf=1), var_code(pf=2)
+T11, TCT, TLOOP, TST, TNNLO = 0, 3, 9, 21, 24  # offsets of P11l, Pctl, Ploopl, Pstl, PctNNLOl rows on the term axis
 
 
 @dataclass
@@ -90,7 +101,8 @@ class WestCoastBasis:
         get = lambda n: params.get(n, 0.0)
         A = [get(n) for n in self.bsA()]
         Bv = [get(n) for n in self.bsB()] if self.is_cross() else A
-        return A + Bv + [get(n) for n in self.es()]
+        # the NNLO coefficients carry the tracer's own prefix, also for a cross (parambasis.py:192-193, :242)
+        return A + Bv + [get(n) for n in self.es()] + [get(n) for n in self.cnnloA()]
 
     def gaussian_descriptors(self, co):
         x1, x2 = _stoch_factors(co)
@@ -108,6 +120,9 @@ class WestCoastBasis:
             out[pre + "cct"] = [(TCT + 0, VAR_B1A, 2.0 / km**2), (TCT + 3, VAR_F, 2.0 / km**2)]
             out[pre + "cr1"] = [(TCT + 1, VAR_B1A, 2.0 / kr**2), (TCT + 4, VAR_F, 2.0 / kr**2)]
             out[pre + "cr2"] = [(TCT + 2, VAR_B1A, 2.0 / kr**2), (TCT + 5, VAR_F, 2.0 / kr**2)]
+            if co.with_NNLO:  # parambasis.py:303-307 (auto spectra only, like the reference)
+                out[pre + "cr4"] = [(TNNLO + 0, var_code(pa=2), 0.25 / kr**4)]
+                out[pre + "cr6"] = [(TNNLO + 1, VAR_B1A, 0.25 / kr**4)]
         out[self.prefix + "ce0"] = [(TST + 0, VAR_ONE, x1)]
         out[self.prefix + "cemono"] = [(TST + 1, VAR_ONE, x2)]
         out[self.prefix + "cequad"] = [(TST + 2, VAR_ONE, x2)]
@@ -172,11 +187,15 @@ class EastCoastBasis:
         A = [b1, b1 + 7 / 2 * bG2, b1 + 15 * bG2 + 6 * bGamma3, 1 / 2 * b2 - 7 / 2 * bG2,
              c0 - f / 3 * c2 + 3 / 35 * f**2 * c4, c2 - 6 / 7 * f * c4, c4]  # parambasis.py:384-392
         Pshot, a0, a2 = get("Pshot"), get("a0"), get("a2")
-        return A + A + [Pshot, a0 + 1 / 3 * a2, 2 / 3 * a2]
+        return A + A + [Pshot, a0 + 1 / 3 * a2, 2 / 3 * a2, get("ctilde"), 0.0]  # :395-398
 
     def gaussian_descriptors(self, co):
         x1, x2 = _stoch_factors(co)
         pre = self.prefix
+        nnlo = {}
+        if co.with_NNLO:  # parambasis.py:439-445
+            nnlo[pre + "ctilde"] = [(TNNLO + 0, var_code(pa=2, pf=4), -1.0), (TNNLO + 1, var_code(pa=1, pf=5), -2.0),
+                                    (TNNLO + 2, var_code(pf=6), -1.0)]
         return {
             pre + "bGamma3": [(TLOOP + 3, VAR_ONE, 6.0), (TLOOP + 7, VAR_B1A, 6.0)],
             pre + "c0": [(TCT + 0, VAR_ONE, -2.0)],
@@ -185,6 +204,7 @@ class EastCoastBasis:
             pre + "Pshot": [(TST + 0, VAR_ONE, x1)],
             pre + "a0": [(TST + 1, VAR_ONE, x2)],
             pre + "a2": [(TST + 1, VAR_ONE, x2 / 3.0), (TST + 2, VAR_ONE, 2.0 * x2 / 3.0)],
+            **nnlo,
         }
 
     def reduce_Plk(self, bird, params_values_dict):
@@ -211,6 +231,11 @@ def reduce_Plk(bird, bsA, bsB=None, es=(0.0, 0.0, 0.0), cnnloA=(0.0, 0.0), cnnlo
         basis = WestCoastBasis(prefix="X_", cross_prefix=["A_", "B_"])
         params = {**{"A_" + n: v for n, v in zip(names, bsA)}, **{"B_" + n: v for n, v in zip(names, bsB)}}
     params.update({basis.prefix + n: v for n, v in zip(("ce0", "cemono", "cequad"), es)})
+    if bird.co.with_NNLO:
+        if bird.co.counterform == "eastcoast":
+            # the function form reads ctilde = cnnloA[0] and takes bsA as already-converted west-form values (:102-105)
+            raise NotImplementedError("function-form reduce_Plk with counterform='eastcoast' and NNLO: use EastCoastBasis.reduce_Plk")
+        params.update({basis.prefix + n: v for n, v in zip(("cr4", "cr6"), cnnloA)})
     return reduce_on_device(basis, bird, params)[0]
 
 

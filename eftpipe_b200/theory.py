@@ -21,9 +21,21 @@ from .plugins import find_window_constructor, probe_linear_stage
 from .pybird import APeffect, Common, DAfunc, FiberCollision, Hubble
 from .window import Window
 
-_KNOWN = {"prefix", "z", "nd", "km", "kr", "cross", "provider", "use_cb", "with_IRresum", "with_APeffect",
-          "with_window", "with_fiber", "with_NNLO", "with_RSD", "kmax", "IRresum", "APeffect", "window", "icc", "fiber",
-          "binning", "basis", "chained", "ls", "Nl", "optiresum", "IRcutoff", "kIR"}
+_KNOWN = {"prefix", "z", "nd", "km", "kr", "cross", "provider", "provider_kwargs", "use_cb", "with_IRresum", "with_APeffect",
+          "with_window", "with_icc", "with_fiber", "with_NNLO", "with_RSD", "kmax", "IRresum", "APeffect", "window", "icc",
+          "fiber", "binning", "basis", "counterform", "chained", "ls", "Nl", "optiresum", "IRcutoff", "kIR"}
+
+
+def tracer_prefix(name, cfg):
+    """theory.py:285-291 (`LeafKernelShared.set_tracer_prefix` / `build_basis`): an absent `prefix` means `<tracer>_`;
+    an explicitly empty one is kept for the tracer itself"""
+    prefix = cfg.get("prefix")
+    return name + "_" if prefix is None else prefix
+
+
+def related_prefix(name, cfg):
+    """theory.py:290-291: the parents of a cross tracer fall back to `<tracer>_` also for an EMPTY prefix"""
+    return cfg["prefix"] if cfg.get("prefix") else name + "_"
 
 
 def _construct(cls, cfg, **fixed):
@@ -122,8 +134,8 @@ class EFTLSS:
             kmA, krA, ndA, kmB, krB, ndB = self._scales(name)
             basis_cls = find_param_basis(cfg.get("basis", "westcoast"))
             cross = cfg.get("cross")
-            cross_prefix = [self.tracers[t]["prefix"] for t in cross] if isinstance(cross, (list, tuple)) else []
-            basis = basis_cls(prefix=cfg.get("prefix", ""), cross_prefix=cross_prefix)
+            cross_prefix = [related_prefix(t, self.tracers[t]) for t in cross] if isinstance(cross, (list, tuple)) else []
+            basis = basis_cls(prefix=tracer_prefix(name, cfg), cross_prefix=cross_prefix)
             co = Common(Nl=Nl, No=No, kmax=cfg.get("kmax", 0.3), kmA=kmA, krA=krA, ndA=ndA, kmB=kmB, krB=krB, ndB=ndB,
                         counterform=basis.counterform(), with_NNLO=bool(cfg.get("with_NNLO", False)),
                         optiresum=bool(cfg.get("optiresum", False)), IRcutoff=cfg.get("IRcutoff", False),
@@ -139,8 +151,10 @@ class EFTLSS:
             ww = cfg.get("with_window")
             if ww:
                 wc = dict(cfg.get("window") or {})
-                if cfg.get("icc"):
-                    icc = _construct(IntegralConstraint, dict(cfg["icc"]), co=co)
+                if cfg.get("with_icc", False):  # theory.py:384-388, :463-471
+                    if cross:
+                        raise LoggedError("integral constraint correction (icc) not yet supported for cross power spectrum")
+                    icc = _construct(IntegralConstraint, dict(cfg.get("icc") or {}), co=co)
                 if isinstance(ww, str) and ww not in ("auto", "default"):
                     # theory.py:62-72, :370-377: a class by dotted path with an in-place `.Window(bird)`; probed once
                     # into a fixed operator (plugins.probe_linear_stage) - ICC and the Picc constant included
@@ -244,8 +258,7 @@ class EFTLSS:
         return self._derived
 
     def _derive(self, name, c):
-        prefix = self.tracers[name].get("prefix")
-        prefix = name + "_" if prefix is None else prefix
+        prefix = tracer_prefix(name, self.tracers[name])
         apo = self.info.get(name, {}).get("ap")
         if apo is not None and c.get("DA") is not None and c.get("H") is not None:
             qperp, qpar = np.asarray(_host(c["DA"]), float) / apo.DA, apo.H / np.asarray(_host(c["H"]), float)  # pybird.py:1560-1562
@@ -265,10 +278,10 @@ class EFTLSS:
         return info["ls"], info["kout"], self.bases[tracer].reduce_Plk(self._view(tracer), params)
 
     def get_eft_params_values_dict(self, tracer, params):
-        """the tracer's own EFT parameters out of `params` (theory.py:262-263)"""
+        """the tracer's EFT parameters, absent ones as 0.0 (theory.py:262-263, :839-843)"""
         basis = self.bases[tracer]
-        names = list(basis.non_gaussian_params()) + list(basis.gaussian_params())
-        return {n: params[n] for n in names if n in params}
+        names = list(basis.gaussian_params()) + list(basis.non_gaussian_params())
+        return {n: params.get(n, 0.0) for n in names}
 
     def get_snapshots(self, tracer):
         raise LoggedError("snapshots are taken on the stage-by-stage path (pybird.Bird.create_snapshot); the fused "

@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-#define EFTB_ABI_VERSION 3
+#define EFTB_ABI_VERSION 4
+#define EFTB_NPAR 19 /* nuisance columns per tracer read by the bias reduction (eftb_like_constants.par_index) */
 
 typedef enum {
   EFTB_OK = 0,
@@ -187,8 +188,10 @@ typedef struct {
   const int32_t* nout;        /* [ntracer] rows of that tracer's projected terms */
   const int32_t* nterm;       /* [ntracer] */
   const double* scales;       /* [ntracer][6] kmA, krA, ndA, kmB, krB, ndB (parambasis.py:68-75) */
-  const int32_t* par_index;   /* [ntracer][17] columns of the nuisance array holding
-                                 b1A,b2A,b3A,b4A,cctA,cr1A,cr2A, b1B..cr2B, ce0,cemono,cequad; -1 = 0.0 */
+  const int32_t* par_index;   /* [ntracer][EFTB_NPAR] columns of the nuisance array holding
+                                 b1A,b2A,b3A,b4A,cctA,cr1A,cr2A, b1B..cr2B, ce0,cemono,cequad, and the NNLO
+                                 counterterm coefficients cr4,cr6 (west) / ctilde,- (east; parambasis.py:96-107),
+                                 read only when the tracer has 27 term rows (with_NNLO); -1 = 0.0 */
   const int32_t* eastcoast;   /* [ntracer] counterform flag (parambasis.py:102) */
   /* per data point */
   const int32_t* d_tracer;    /* [ndata] */
@@ -197,7 +200,8 @@ typedef struct {
   const double* picc;         /* [ndata] constant integral-constraint contribution */
   const double* invcov;       /* [ndata][ndata] */
   /* gaussian (marginalised) parameters: dP/dg = sum_{q<3} c_q * v_q * term[i_q] on tracer g_tracer,
-     v in {0: 1, 1: b1A, 2: b1B, 3: f, 4: f^2} (parambasis.py:249-316, :403-454) */
+     v = b1A^pa * b1B^pb * f^pf coded as g_var = pa | pb << 2 | pf << 4 (pa, pb <= 3, pf <= 7)
+     (parambasis.py:249-316, :403-454; the NNLO rows cr4, cr6, ctilde need b1^2 and f^4..f^6) */
   const int32_t* g_count;     /* [ngauss] number of (tracer) entries, <= 2 */
   const int32_t* g_tracer;    /* [ngauss][2] */
   const int32_t* g_term;      /* [ngauss][2][3] */
