@@ -63,6 +63,7 @@ SIGNATURES = {
     "eftb_abi_version": (C.c_int, []),
     "eftb_last_error": (C.c_char_p, []),
     "eftb_padded_batch": (C.c_int, [_I]),
+    "eftb_launch_count": (C.c_ulonglong, []),
     "eftb_probe_fp64": (C.c_int, [_I, c_double_p, _VP]),
     "eftb_plan_create": (C.c_int, [C.POINTER(EftbConfig), C.POINTER(EftbConstants), C.POINTER(_VP)]),
     "eftb_plan_destroy": (None, [_VP]),

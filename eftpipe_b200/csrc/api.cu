@@ -67,6 +67,8 @@ __global__ void probe_fp64_kernel(double* sink, int iters) {
 
 }  // namespace
 
+unsigned long long g_eftb_launches = 0;
+
 int eftb_current_device() {
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);
@@ -89,6 +91,7 @@ int eftb_sm_count() {
 extern "C" {
 
 int eftb_abi_version(void) { return EFTB_ABI_VERSION; }
+unsigned long long eftb_launch_count(void) { return __atomic_load_n(&g_eftb_launches, __ATOMIC_RELAXED); }
 const char* eftb_last_error(void) { return g_error; }
 int eftb_padded_batch(int B) { return B < 1 ? 0 : eftb_round_up(B, 32); }
 

@@ -20,8 +20,11 @@ void eftb_set_error(const char* fmt, ...);
     }                                                                                      \
   } while (0)
 
+extern unsigned long long g_eftb_launches;  // kernels launched (or recorded into a capturing stream) by this library
+
 #define EFTB_LAUNCH_CHECK()                                                                \
   do {                                                                                     \
+    __atomic_fetch_add(&g_eftb_launches, 1ull, __ATOMIC_RELAXED);                          \
     cudaError_t _e = cudaGetLastError();                                                   \
     if (_e != cudaSuccess) {                                                               \
       eftb_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e));    \

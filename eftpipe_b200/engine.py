@@ -36,8 +36,12 @@ def capture_graph(fn, warmup=2):
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
+    lib = _lib.load()
+    n0 = lib.eftb_launch_count()
     with torch.cuda.graph(graph):
         out = fn()
+    # kernels of this library recorded into the graph = kernels every replay launches (bench.py `gpu_launches`)
+    graph.library_launches = int(lib.eftb_launch_count() - n0)
     return graph, out
 
 

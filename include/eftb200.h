@@ -99,6 +99,9 @@ typedef struct {
 int eftb_abi_version(void);
 const char* eftb_last_error(void);
 int eftb_padded_batch(int B);
+/* number of kernels this library has launched - or recorded into a capturing stream - since it was loaded (bench.py's
+   `gpu_launches`: the difference across the capture of one step is the kernel count of the replayed graph) */
+unsigned long long eftb_launch_count(void);
 /* FP64 FMA-pipe peak probe: runs `iters` dependent-chain DFMA bundles on every SM and returns the
    measured TFLOP/s through *tflops (synchronises; used by bench.py for the roofline denominator) */
 int eftb_probe_fp64(int iters, double* tflops, void* stream);

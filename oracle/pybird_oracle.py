@@ -656,6 +656,14 @@ def bird_terms(bird: Bird):
 # --------------------------------------------------------------------------------------
 # bias reduction (parambasis.py:42-136, :249-316) - west-coast basis
 # --------------------------------------------------------------------------------------
+def nnlo_vector(co: Common, f, b1A, cnnlo):
+    """bctNNLOAB (parambasis.py:96-107): west [b1^2 cr4, b1 cr6, 0] / (4 kr^4); east ctilde [-b1^2 f^4, -2 b1 f^5, -f^6]"""
+    if co.counterform == "westcoast":
+        cr4, cr6 = cnnlo
+        return np.array([0.25 * b1A**2 / co.krA**4 * cr4, 0.25 * b1A / co.krA**4 * cr6, 0.0])
+    return cnnlo[0] * np.array([-(b1A**2) * f**4, -2 * b1A * f**5, -(f**6)])
+
+
 def bias_vectors(co: Common, f, bsA, bsB=None, es=(0.0, 0.0, 0.0)):
     b1A, b2A, b3A, b4A, cctA, cr1A, cr2A = bsA
     b1B, b2B, b3B, b4B, cctB, cr1B, cr2B = bsB if bsB is not None else bsA
@@ -684,15 +692,41 @@ def bias_vectors(co: Common, f, bsA, bsB=None, es=(0.0, 0.0, 0.0)):
     return b11, bct, bloop, bst
 
 
-def reduce_Plk(co: Common, f, terms: dict, bsA, bsB=None, es=(0.0, 0.0, 0.0)):
-    """Full multipoles P_l(k) = sum_b bias_b * term_b + Picc (parambasis.py:129-136 + `.sum()`)."""
+def reduce_Plk(co: Common, f, terms: dict, bsA, bsB=None, es=(0.0, 0.0, 0.0), cnnlo=None):
+    """Full multipoles P_l(k) = sum_b bias_b * term_b + Picc (parambasis.py:129-136 + `.sum()`).
+    cnnlo: (cr4, cr6) west / (ctilde,) east when co.with_NNLO (parambasis.py:96-107, :132-134)."""
     b11, bct, bloop, bst = bias_vectors(co, f, bsA, bsB, es)
     No = min(co.No, terms["P11l"].shape[0])
     out = np.einsum("b,lbx->lx", b11, terms["P11l"][:No])
     out = out + np.einsum("b,lbx->lx", bloop, terms["Ploopl"][:No])
-    out = out + np.einsum("b,lbx->lx", bct, terms["Pctl"][:No])
+    pct = np.einsum("b,lbx->lx", bct, terms["Pctl"][:No])
+    if co.with_NNLO and cnnlo is not None:
+        pct = pct + np.einsum("b,lbx->lx", nnlo_vector(co, f, bsA[0], cnnlo), terms["PctNNLOl"][:No])
+    out = out + pct
     out = out + np.einsum("b,lbx->lx", bst, terms["Pstl"][:No])
     return out + terms["Picc"][:No]
+
+
+def east_to_west(f, b1, b2, bG2, bGamma3, c0, c2, c4, Pshot, a0, a2):
+    """EastCoastBasis.reduce_Plk parameter map (parambasis.py:379-400): returns (bsA, es)"""
+    bsA = [b1, b1 + 7 / 2 * bG2, b1 + 15 * bG2 + 6 * bGamma3, 1 / 2 * b2 - 7 / 2 * bG2,
+           c0 - f / 3 * c2 + 3 / 35 * f**2 * c4, c2 - 6 / 7 * f * c4, c4]
+    return bsA, [Pshot, a0 + 1 / 3 * a2, 2 / 3 * a2]
+
+
+def gaussian_table_east(co: Common, f, terms: dict, b1):
+    """EastCoastBasis.reduce_Plk_gaussian_table (parambasis.py:403-454)"""
+    No = min(co.No, terms["P11l"].shape[0])
+    L, C, S = terms["Ploopl"][:No], terms["Pctl"][:No], terms["Pstl"][:No]
+    x1 = 0.5 * (1.0 / co.ndA + 1.0 / co.ndB)
+    x2 = 0.5 * (1.0 / co.ndA / co.kmA**2 + 1.0 / co.ndB / co.kmB**2)
+    out = {"bGamma3": 6.0 * (L[:, 3] + b1 * L[:, 7]), "c0": -2.0 * C[:, 0], "c2": 2 / 3 * f * C[:, 0] - 2.0 * f * C[:, 1],
+           "c4": -6 / 35 * f**2 * C[:, 0] + 12 / 7 * f**2 * C[:, 1] - 2.0 * f**2 * C[:, 2]}
+    if co.with_NNLO:
+        N = terms["PctNNLOl"][:No]
+        out["ctilde"] = -(b1**2) * f**4 * N[:, 0] - 2.0 * b1 * f**5 * N[:, 1] - f**6 * N[:, 2]
+    out["Pshot"], out["a0"], out["a2"] = x1 * S[:, 0], x2 * S[:, 1], x2 / 3 * (S[:, 1] + 2.0 * S[:, 2])
+    return out
 
 
 def gaussian_table_west(co: Common, f, terms: dict, b1A, b1B=None, cross=False):
@@ -716,6 +750,9 @@ def gaussian_table_west(co: Common, f, terms: dict, b1A, b1B=None, cross=False):
         out["cct"] = 2.0 * b1A / kmA**2 * C[:, 0] + 2.0 * f / kmA**2 * C[:, 3]
         out["cr1"] = 2.0 * b1A / krA**2 * C[:, 1] + 2.0 * f / krA**2 * C[:, 4]
         out["cr2"] = 2.0 * b1A / krA**2 * C[:, 2] + 2.0 * f / krA**2 * C[:, 5]
+    if co.with_NNLO and not cross:  # parambasis.py:303-307
+        N = terms["PctNNLOl"][:No]
+        out["cr4"], out["cr6"] = 0.25 * b1A**2 / krA**4 * N[:, 0], 0.25 * b1A / krA**4 * N[:, 1]
     x1 = 0.5 * (1.0 / ndA + 1.0 / ndB)
     x2 = 0.5 * (1.0 / ndA / kmA**2 + 1.0 / ndB / kmB**2)
     out["ce0"], out["cemono"], out["cequad"] = S[:, 0] * x1, S[:, 1] * x2, S[:, 2] * x2

@@ -2,23 +2,28 @@ import logging
 
 
 class LoggedError(Exception):
-    def __init__(self, logger, *args, **kwargs):
-        msg = args[0] % args[1:] if len(args) > 1 else (args[0] if args else "")
+    """cobaya.log.LoggedError(logger, msg, *args)"""
+
+    def __init__(self, logger=None, *args, **kwargs):
+        if isinstance(logger, str):  # tolerate LoggedError("message")
+            args, logger = (logger,) + args, None
+        msg = (args[0] % args[1:] if len(args) > 1 else args[0]) if args else ""
         super().__init__(msg)
 
 
 class HasLogger:
     def set_logger(self, lowercase=True, name=None):
-        self.log = logging.getLogger(name or self.__class__.__name__)
+        name = name or self.__class__.__name__
+        self.log = logging.getLogger(name.lower() if lowercase else name)
 
     def mpi_info(self, msg, *args):
-        pass
+        self.log.info(msg, *args)
 
     def mpi_warning(self, msg, *args):
-        pass
+        self.log.warning(msg, *args)
 
     def mpi_debug(self, msg, *args):
-        pass
+        self.log.debug(msg, *args)
 
 
 def logger_setup(*args, **kwargs):

@@ -305,7 +305,9 @@ def test_multitracer_likelihood_against_oracle(dr16_setup, dr16):
     np.testing.assert_allclose(th.derived["LRG_NGC_alperp"], bl.DA / syn.angular_distance(0.307115, 0.696), rtol=1e-12)
     np.testing.assert_allclose(th.derived["LRG_NGC_alpara"], syn.hubble(0.307115, 0.696) / bl.H, rtol=1e-12)
     np.testing.assert_allclose(th.derived["ELG_NGC_fz"], S["batches"]["ELG_NGC"].f)
-    assert set(th.get_eft_params_values_dict("LRG_NGC", S["params"])) == {"LRG_NGC_b1", "LRG_NGC_b2", "LRG_NGC_b4"}
+    vals = th.get_eft_params_values_dict("LRG_NGC", S["params"])  # theory.py:839-843: every EFT parameter, absent ones 0.0
+    assert {"LRG_NGC_b1", "LRG_NGC_b2", "LRG_NGC_b4", "LRG_NGC_b3", "LRG_NGC_cct", "LRG_NGC_cequad"} <= set(vals)
+    assert vals["LRG_NGC_b3"] == 0.0 and vals["LRG_NGC_b1"] is S["params"]["LRG_NGC_b1"]
     ls, kk, comp = th.get_bird_component("LRG_NGC", {k: v for k, v in S["params"].items() if k.startswith("LRG")})
     assert ls == [0, 2, 4] and kk.size == 18 and tuple(comp.sum().shape) == (S["B"], 3, 18)
     res = like.calculate(S["params"], want_bestfit=True)
