@@ -29,6 +29,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -56,7 +57,8 @@ def load_fixture():
 
 
 def cache_dir(sub=""):
-    d = os.path.join(ROOT, ".bench_cache", sub)  # git- and gpurun-ignored scratch (window matrices, the reference's text inputs)
+    # scratch outside the repository (window matrices, the reference's text inputs): nothing here is product or evidence
+    d = os.path.join(os.environ.get("EFTB_BENCH_CACHE") or os.path.join(tempfile.gettempdir(), "eftpipe_b200_bench_cache"), sub)
     os.makedirs(d, exist_ok=True)
     return d
 

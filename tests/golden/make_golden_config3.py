@@ -41,7 +41,7 @@ def meta(script):
 def config3():
     paths = refdriver.write_dr16("/tmp/dr16txt")
     tables = refdriver.synthetic_tables(B)
-    cache = os.path.join(ROOT, ".bench_cache", "ref")
+    cache = "/tmp/eftpipe_b200_bench_cache/ref"
     os.makedirs(cache, exist_ok=True)
     info = refdriver.config3_info(paths, tables, cache_dir=cache, likelihoods=("jeffreys", "gauss"))
     model = refdriver.reference_model(info)
