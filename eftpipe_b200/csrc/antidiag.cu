@@ -17,6 +17,13 @@
 // works through its own list of anti-diagonals (host-balanced by pair count, longest-first).  The table is
 // stored in fragment order (1280 B per k-step, compact complex) and streamed through a per-warp ring of
 // shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), one stage (4 k-steps, 5 KB) ahead.
+//
+// Scheduling: a task = (group of 32 cosmologies, one of `nb` bins of 4 warp lists).  The grid is persistent - at most
+// SMs x 2 CTAs, each taking a contiguous range of the group-major task list, so that it re-stages the coefficients only
+// when its range crosses into the next group - and nb is chosen so that the tasks fill whole rounds of the resident CTAs:
+// at a config-4 shard (256 groups) one CTA per group left 40 of the 148 SMs with a single CTA; 256 x 15 tasks over 296
+// CTAs are 12 or 13 tasks each.
+#include <stdlib.h>
 #include <algorithm>
 #include <map>
 #include <mutex>
@@ -40,6 +47,7 @@ struct AdArgs {
   const int32_t* bin_off; // [nbins + 1]
   double* D;
   int Nmax, Bp;
+  int nb, ntasks;         // bins of AD_WARPS warp lists per cosmology group; ngroups * nb
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,41 +82,20 @@ __device__ __forceinline__ double flip_sign(double v, uint32_t mask) {  // mask 
   return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
 }
 
-__global__ void __launch_bounds__(AD_WARPS * 32) antidiag_kernel(AdArgs a) {
-  extern __shared__ __align__(128) unsigned char smraw[];
-  const int Nh = a.Nmax >> 1;
-  const int nrow = 2 * (Nh + 1);
-  double* cs = reinterpret_cast<double*>(smraw);                                   // [Nh+1][2][32]
-  unsigned char* ring0 = smraw + (size_t)nrow * 32 * sizeof(double);               // [warps][NST][S * 1280]
-  uint64_t* bars0 = reinterpret_cast<uint64_t*>(ring0 + (size_t)AD_WARPS * AD_NST * AD_S * AD_KSTEP_BYTES);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b0 = blockIdx.x * 32;
-  unsigned char* ring = ring0 + (size_t)warp * AD_NST * AD_S * AD_KSTEP_BYTES;
-  uint64_t* bars = bars0 + warp * AD_NST;
-
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < AD_NST; ++i) mbar_init(bars + i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  // FFTLog coefficients of this CTA's 32 cosmologies: rows (n, re), (n, im)
-  for (int i = tid; i < nrow * 32; i += AD_WARPS * 32) {
-    const int row = i >> 5, n = i & 31, idx = row >> 1;
-    const double* src = (row & 1) ? a.cim : a.cre;
-    cs[i] = src[(size_t)idx * a.Bp + b0 + n];
-  }
-  __syncthreads();
-
-  const int bin = blockIdx.y * AD_WARPS + warp;
-  const int d0 = a.bin_off[bin], d1 = a.bin_off[bin + 1];
-  if (d0 >= d1) return;
-
+// One task: this warp's list `bin` of anti-diagonals for the 32 cosmologies staged in `cs`, written to D at column b0.
+// Kept out of line on purpose: inlined into the persistent task loop the 80 accumulators plus the loop's own state hit the
+// 255-register ceiling and ptxas serialises the ten A-fragment loads of a k-step on one register pair (measured: +25 %).
+// iter0 = ring stages this warp has consumed so far (all tasks): ring slot and mbarrier parity follow from it.
+__device__ __noinline__ uint32_t antidiag_task(const double* __restrict__ cs, unsigned char* ring, uint64_t* bars, const double2* tab,
+                                               const int4* descs, int d0, int d1, double* D, int Nmax, int Bp, int b0, uint32_t iter0) {
+  const int lane = threadIdx.x & 31;
+  const int Nh = Nmax >> 1;
   auto issue = [&](int d) {  // lane 0 only
-    const int4 ds = __ldg(a.descs + d);
-    const int slot = (d - d0) % AD_NST;
+    const int4 ds = __ldg(descs + d);
+    const int slot = (int)((iter0 + (uint32_t)(d - d0)) % AD_NST);
     const uint32_t bytes = (uint32_t)(ds.y & 0xff) * AD_KSTEP_BYTES;
     mbar_expect_tx(bars + slot, bytes);
-    tma_bulk_load(ring + (size_t)slot * AD_S * AD_KSTEP_BYTES, reinterpret_cast<const unsigned char*>(a.tab) + (size_t)ds.x * AD_KSTEP_BYTES,
+    tma_bulk_load(ring + (size_t)slot * AD_S * AD_KSTEP_BYTES, reinterpret_cast<const unsigned char*>(tab) + (size_t)ds.x * AD_KSTEP_BYTES,
                   bytes, bars + slot);
   };
   if (lane == 0)
@@ -129,10 +116,11 @@ __global__ void __launch_bounds__(AD_WARPS * 32) antidiag_kernel(AdArgs a) {
     for (int j = 0; j < AD_NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   for (int d = d0; d < d1; ++d) {
-    const int it = d - d0, slot = it % AD_NST;
-    const int4 ds = __ldg(a.descs + d);
+    const uint32_t it = iter0 + (uint32_t)(d - d0);
+    const int slot = (int)(it % AD_NST);
+    const int4 ds = __ldg(descs + d);
     const int cnt = ds.y & 0xff, last = ds.y >> 8, t = ds.z;
-    mbar_wait(bars + slot, (uint32_t)((it / AD_NST) & 1));
+    mbar_wait(bars + slot, (it / AD_NST) & 1u);
     const double2* stage = reinterpret_cast<const double2*>(ring + (size_t)slot * AD_S * AD_KSTEP_BYTES);
     const int half = t >> 1;
     for (int ks = 0; ks < cnt; ++ks) {
@@ -140,7 +128,7 @@ __global__ void __launch_bounds__(AD_WARPS * 32) antidiag_kernel(AdArgs a) {
       const int p = min(ds.w + 2 * ks + q, half);   // a padded second pair multiplies zero table entries
       const int m = t - p;
       const bool folded = m > Nh;                    // c_m = conj(c_{Nmax-m})
-      const int mi = folded ? a.Nmax - m : m;
+      const int mi = folded ? Nmax - m : m;
       // value = xr * (comp ? yi : yr) + (comp ? xi : -xi) * (comp ? yr : yi),   yi carries the fold sign
       const double* xrow = cs + (size_t)(2 * p) * 32 + grp;
       const double* yrow = cs + (size_t)(2 * mi) * 32 + grp;
@@ -166,12 +154,12 @@ __global__ void __launch_bounds__(AD_WARPS * 32) antidiag_kernel(AdArgs a) {
     if (lane == 0 && d + AD_NST < d1) issue(d + AD_NST);
     if (last) {
       // D[ch][t][part][b]: row R = 8 i + grp -> channel R >> 1, part R & 1; columns 8 j + 2 col + {0, 1}
-      const size_t tstride = (size_t)2 * a.Bp, chstride = (size_t)(a.Nmax + 1) * tstride;
+      const size_t tstride = (size_t)2 * Bp, chstride = (size_t)(Nmax + 1) * tstride;
 #pragma unroll
       for (int i = 0; i < AD_MT; ++i) {
         const int ch = 4 * i + a_cc;
         if (ch < EFTB_NCH) {
-          double* out = a.D + (size_t)ch * chstride + (size_t)t * tstride + (size_t)a_part * a.Bp + b0 + 2 * col;
+          double* out = D + (size_t)ch * chstride + (size_t)t * tstride + (size_t)a_part * Bp + b0 + 2 * col;
 #pragma unroll
           for (int j = 0; j < AD_NT; ++j) *reinterpret_cast<double2*>(out + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
         }
@@ -179,6 +167,45 @@ __global__ void __launch_bounds__(AD_WARPS * 32) antidiag_kernel(AdArgs a) {
         for (int j = 0; j < AD_NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
       }
     }
+  }
+  return iter0 + (uint32_t)(d1 - d0);
+}
+
+__global__ void __launch_bounds__(AD_WARPS * 32) antidiag_kernel(AdArgs a) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int Nh = a.Nmax >> 1;
+  const int nrow = 2 * (Nh + 1);
+  double* cs = reinterpret_cast<double*>(smraw);                                   // [Nh+1][2][32]
+  unsigned char* ring0 = smraw + (size_t)nrow * 32 * sizeof(double);               // [warps][NST][S * 1280]
+  uint64_t* bars0 = reinterpret_cast<uint64_t*>(ring0 + (size_t)AD_WARPS * AD_NST * AD_S * AD_KSTEP_BYTES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned char* ring = ring0 + (size_t)warp * AD_NST * AD_S * AD_KSTEP_BYTES;
+  uint64_t* bars = bars0 + warp * AD_NST;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < AD_NST; ++i) mbar_init(bars + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  uint32_t iter0 = 0;
+  const int task0 = (int)((long long)blockIdx.x * a.ntasks / gridDim.x), task1 = (int)((long long)(blockIdx.x + 1) * a.ntasks / gridDim.x);
+  int group = -1;
+  for (int task = task0; task < task1; ++task) {
+    const int b0 = (task / a.nb) * 32;
+    if (task / a.nb != group) {
+      group = task / a.nb;
+      if (task != task0) __syncthreads();  // every warp is done with the previous group's coefficients
+      // FFTLog coefficients of this group's 32 cosmologies: rows (n, re), (n, im)
+      for (int i = tid; i < nrow * 32; i += AD_WARPS * 32) {
+        const int row = i >> 5, n = i & 31, idx = row >> 1;
+        const double* src = (row & 1) ? a.cim : a.cre;
+        cs[i] = src[(size_t)idx * a.Bp + b0 + n];
+      }
+      __syncthreads();
+    }
+    const int bin = (task % a.nb) * AD_WARPS + warp;
+    const int d0 = a.bin_off[bin], d1 = a.bin_off[bin + 1];
+    if (d0 < d1) iter0 = antidiag_task(cs, ring, bars, a.tab, a.descs, d0, d1, a.D, a.Nmax, a.Bp, b0, iter0);
   }
 }
 
@@ -286,20 +313,32 @@ int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cuda
   EFTB_SET_SMEM(configured, antidiag_kernel, smem);
   const int sms = eftb_sm_count();
   if (!sms) return EFTB_ERR_CUDA;
-  // one wave: CTAs per SM limited by shared memory (and 2 by registers)
+  // resident CTAs: limited by shared memory (and to 2 per SM by registers)
   const int per_sm = std::max(1, std::min(2, (int)((227 * 1024) / (smem + 1024))));
-  int ctas_per_group = std::max(1, (sms * per_sm) / ngroups);
-  ctas_per_group = std::min(ctas_per_group, (c.Nmax + 1 + AD_WARPS - 1) / AD_WARPS);
+  const int slots = sms * per_sm;
+  // bins per group: the tasks should fill whole rounds of the resident CTAs; ties go to fewer, larger tasks
+  const int maxnb = std::min(16, (c.Nmax + 1 + AD_WARPS - 1) / AD_WARPS);
+  int nb = 1;
+  double best = -1.0;
+  for (int cand = 1; cand <= maxnb; ++cand) {
+    const long nt = (long)ngroups * cand;
+    const long rounds = (nt + slots - 1) / slots;
+    const double eff = (double)nt / (double)(rounds * slots);
+    if (eff > best + 1e-3) { best = eff; nb = cand; }
+  }
+  static const int force_nb = getenv("EFTB_AD_NB") ? atoi(getenv("EFTB_AD_NB")) : 0;  // tuning knob (A/B runs)
+  if (force_nb > 0) nb = std::min(force_nb, maxnb);
+  const int ntasks = ngroups * nb;
   AdSchedule sc;
-  int rc = get_schedule(P, c.Nmax, ctas_per_group * AD_WARPS, &sc);
+  int rc = get_schedule(P, c.Nmax, nb * AD_WARPS, &sc);
   if (rc) return rc;
   AdArgs a;
   const bool second = cf_set && c.row_cre_cf >= 0;  // pybird.py:1151-1160: coef_cf differs from coef_pk
   a.cre = F + (size_t)(second ? c.row_cre_cf : c.row_cre) * Bp;
   a.cim = F + (size_t)(second ? c.row_cim_cf : c.row_cim) * Bp;
   a.tab = P->tab; a.descs = sc.descs; a.bin_off = sc.bin_off; a.D = D; a.Nmax = c.Nmax; a.Bp = Bp;
-  dim3 grid(ngroups, ctas_per_group);
-  antidiag_kernel<<<grid, AD_WARPS * 32, smem, s>>>(a);
+  a.nb = nb; a.ntasks = ntasks;
+  antidiag_kernel<<<std::min(ntasks, slots), AD_WARPS * 32, smem, s>>>(a);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;
 }

@@ -43,6 +43,7 @@ __device__ __forceinline__ double rsqrt_newton(double x) {
 }
 
 constexpr int GEOM_THREADS = 128;
+constexpr int BAS_P = 17;     // shared-memory pitch of one interval's basis polynomials
 constexpr int APPLY_WS = 10;  // window columns of a node held in the compact operator (wider windows: rest in the dense overflow)
 __host__ __device__ constexpr int apply_kp(int NL) { return (NL * APPLY_WS + 3) / 4 * 4; }  // K of the per-node product, padded to k4 steps
 // doubles between the B-spline coefficient blocks [l'][term][j] of consecutive cosmologies: whole 16-byte units (TMA source)
@@ -86,12 +87,12 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
   static_assert(1 + NL * NL <= AP_TAB, "mu table too narrow");
   extern __shared__ __align__(16) double sm[];
   double* knots = sm;                      // [nint]
-  double* bas = knots + a.nint;            // [nint][4][4]
-  double* tabs = bas + a.nint * 16;        // [ncos][tile][AP_TAB] (16-byte aligned: nint * 17 is even or padded below)
-  tabs += (a.nint * 17) & 1;
+  double* bas = knots + a.nint;            // [nint][BAS_P]: 4 x 4 coefficients per interval, pitch 17 (lanes of a warp sit in
+                                           // different intervals: a pitch of 16 doubles puts all of them on the same banks)
+  double* tabs = bas + a.nint * BAS_P;     // [ncos][tile][AP_TAB] (16-byte aligned: nint * 18 is even)
   const int tid = threadIdx.x;
   for (int i = tid; i < a.nint; i += GEOM_THREADS) knots[i] = a.knot_lo[i];
-  for (int i = tid; i < a.nint * 16; i += GEOM_THREADS) bas[i] = a.basis[i];
+  for (int i = tid; i < a.nint * 16; i += GEOM_THREADS) bas[(i >> 4) * BAS_P + (i & 15)] = a.basis[i];
   const int ntot = a.nb * a.Nk;
   const int gid0 = blockIdx.x * GEOM_THREADS, gid = gid0 + tid;
   const bool active = gid < ntot;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
   int j = jfirst;
   double bc[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) bc[i] = bas[j * 16 + i];
+  for (int i = 0; i < 16; ++i) bc[i] = bas[j * BAS_P + i];
   double knot = knots[j];
 
   for (int t0 = 0; t0 < a.nmu; t0 += tile) {
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
       }
       ++j;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) bc[i] = bas[j * 16 + i];
+      for (int i = 0; i < 16; ++i) bc[i] = bas[j * BAS_P + i];
       knot = knots[j];
     }
     while (down && j > jlo && kp < knot) {
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
       }
       --j;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) bc[i] = bas[j * 16 + i];
+      for (int i = 0; i < 16; ++i) bc[i] = bas[j * BAS_P + i];
       knot = knots[j];
     }
     const double x = kp - knot;
@@ -351,10 +352,12 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
   }
 }
 
-// cosmologies per launch: the banded operator G is stored dense in j (any window fits), bounded to ~256 MB
+// cosmologies per launch: the overflow operator G is stored dense in j (any window fits) and only ever touched for windows
+// wider than APPLY_WS, i.e. it is address space, not traffic: bounded to 2 GB so that a config-4 shard (8192 points) is
+// ONE launch of each kernel (6 chunks of 1491 points ran 1.3 waves each: a third of every geometry launch was tail)
 int ap_chunk(const eftb_config& c, int B) {
   const size_t per = (size_t)c.Nk * c.Nl * c.Nl * c.Nk;
-  size_t n = ((size_t)32 << 20) / per;  // doubles
+  size_t n = ((size_t)256 << 20) / per;  // doubles
   if (n < 1) n = 1;
   return (int)(n < (size_t)B ? n : (size_t)B);
 }
@@ -363,7 +366,7 @@ template <int NL>
 int run(ApArgs a, int B, cudaStream_t s, int phase) {
   const int geom_cos = (GEOM_THREADS - 2 + a.Nk) / a.Nk + 1;  // cosmologies a CTA's GEOM_THREADS consecutive (b, k) nodes can touch
   const int mu_tile = a.nmu < GEOM_MU_TILE ? a.nmu : GEOM_MU_TILE;
-  const size_t smem_g = sizeof(double) * (a.nint + (size_t)a.nint * 16 + 1 + (size_t)geom_cos * mu_tile * AP_TAB);
+  const size_t smem_g = sizeof(double) * (a.nint + (size_t)a.nint * BAS_P + (size_t)geom_cos * mu_tile * AP_TAB);
   const size_t smem_a = sizeof(double) * (coef_stride(NL, a.nterm, a.Nk) + APPLY_SLACK + (size_t)a.Nk * NL * apply_kp(NL)) + sizeof(int2) * a.Nk + 16;
   if (a.nterm > 32 || smem_g > 200 * 1024 || smem_a > 200 * 1024) {
     eftb_set_error("ap: unsupported sizes nmu=%d nterm=%d Nk=%d", a.nmu, a.nterm, a.Nk);
