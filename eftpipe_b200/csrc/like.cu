@@ -3,6 +3,7 @@
 // and the analytic marginalisation  -2 ln P = -F1^T F2^-1 F1 + F0 + ln det(F2 / 2 pi)  (marginal.py:79-196)
 // by a per-point Cholesky factorisation in shared memory.
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 #include "common.cuh"
 
@@ -16,7 +17,9 @@ struct eftb_like {
   int32_t *d_tracer = nullptr, *d_row = nullptr, *d_row_g = nullptr;
   int32_t* res_perm = nullptr;  // rows d * (ngauss + 1) of the vector block: the residual PNG - data of data point d
   double *data = nullptr, *picc = nullptr;
-  GemmMatrix invcov;
+  GemmMatrix invcov;   // C^-1 (two-operand form: A = V, Bm = C^-1 V), used when C^-1 has no Cholesky factor
+  GemmMatrix factor;   // L^T with C^-1 = L L^T: W = L^T V and the Gram matrix is W^T W (one operand, half the traffic)
+  bool has_factor = false;
   int32_t *g_count = nullptr, *g_tracer = nullptr, *g_term = nullptr, *g_var = nullptr;
   double *g_coef = nullptr, *sigma_inv = nullptr, *sigma_inv_mu = nullptr;
   double mu_sigma_mu = 0.0;
@@ -147,7 +150,8 @@ __global__ void __launch_bounds__(128) like_vectors_kernel(VecArgs a) {
 }
 
 struct FinArgs {
-  const double *V, *Y, *sigma_inv, *sigma_inv_mu;
+  const double *A, *Bm;  // [ndata][ngauss+1][Bp]: Gram[a][b] = sum_d A[d][a] Bm[d][b]  (A == Bm = L^T V, or A = V, Bm = C^-1 V)
+  const double *sigma_inv, *sigma_inv_mu;
   const double *pp_loc, *pp_sinv;  // per-point Gaussian prior (callable loc / scale, marginal.py:13-20, :60-77): [B][nG] or NULL
   double mu_sigma_mu;
   double *logp, *bestfit, *fullchi2;
@@ -155,137 +159,195 @@ struct FinArgs {
   int B, Bp, ndata, ngauss, jeffreys;
 };
 
-// block (LF_PX points, ny entry-rows): every entry of the packed lower triangle of F2, of F1 and F0 is one dot product
-// over the data index, sum_d V[d][ra] * Y[d][rb]; entry-rows are spread over threadIdx.y, loads are coalesced
-// over the LF_PX points and unrolled 4x (independent partial sums) to keep several loads in flight
-// LF_PX points per CTA (Bp is a multiple of 32, hence of LF_PX): 8 rather than a full warp of points, so that a batch of
-// 1024 spreads over 128 CTAs instead of 32 - the kernel is latency bound and there are 148 SMs to hide it on
-constexpr int LF_PX = 8;
+__device__ __forceinline__ void cp_async16z(void* smem, const void* gmem, bool pred) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int bytes = pred ? 16 : 0;  // 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
+}
 
-__global__ void like_finish_kernel(FinArgs a) {
-  extern __shared__ double sm[];
+// Marginalisation of one tile of PX points (marginal.py:79-196).
+//
+// Phase 1 - Gram matrix.  Every entry of F2 (packed upper triangle), of F1 and F0 is a dot product over the data index of
+// two columns of the vector block, i.e. the (nc x nc) Gram matrix G = A^T Bm per point, nc = ngauss + 1 (column 0 = the
+// residual PNG - d).  The tile's rows stream ONCE from HBM through a double-buffered cp.async ring of LG_DCH data rows
+// (the first version re-read every row from L2 for each of the ~130 entries: 2.5 GB of L2 traffic per 8192 points, the
+// whole cost of the stage); thread = (point x, 4 x 4 block of G's upper triangle): 8 conflict-free shared loads per 16 FMA.
+// Phase 2 - one warp per point: F2 = G + Sigma^-1, left-looking Cholesky with lane = row (the lanes' partial dots run in
+// parallel, the pivot of column j is broadcast with __shfl_sync), forward / backward substitution and the best-fit
+// chi^2 the same way.
+constexpr int LG_DCH = 8;  // data rows per stage
+
+template <int NC, int PX>  // NC: padded nc (16 or 32); PX: points per CTA
+__global__ void __launch_bounds__(PX * (NC / 4) * (NC / 4 + 1) / 2) like_gram_kernel(FinArgs a) {
+  constexpr int NBR = NC / 4, NBLK = NBR * (NBR + 1) / 2, NTHR = PX * NBLK, SP = NC + 1;
+  extern __shared__ __align__(16) double sm[];
   const int nG = a.ngauss, nc = nG + 1;
-  double* F2 = sm;                    // [nG][nG][LF_PX]
-  double* F1 = F2 + (size_t)nG * nG * LF_PX;  // [nG][LF_PX]
-  double* F0 = F1 + (size_t)nG * LF_PX;       // [LF_PX]
-  double* F1o = F0 + LF_PX;                    // [nG][LF_PX]  F1 and diag(F2) before the factorisation (fullchi2 only)
-  double* F2d = F1o + (size_t)nG * LF_PX;      // [nG][LF_PX]
-  const int lx = threadIdx.x, g = threadIdx.y;
-  const int b = blockIdx.x * LF_PX + lx;
-  const size_t Bp = a.Bp, stride = (size_t)nc * Bp;
-  const int ntri = nG * (nG + 1) / 2, nent = ntri + nG + 1;
-  // prior terms: plan constants, or this point's own location / inverse variance (diagonal Sigma^-1; padding lanes: none)
-  const bool pp = a.pp_sinv != nullptr;
-  const double* ps = pp ? a.pp_sinv + (size_t)(b < a.B ? b : 0) * nG : nullptr;
-  const double* pl = pp ? a.pp_loc + (size_t)(b < a.B ? b : 0) * nG : nullptr;
-  auto sinv = [&](int i, int j) { return pp ? (i == j ? ps[i] : 0.0) : a.sigma_inv[i * nG + j]; };
-  auto sinv_mu = [&](int i) { return pp ? ps[i] * pl[i] : a.sigma_inv_mu[i]; };
-  auto mu_s_mu = [&]() {
-    if (!pp) return a.mu_sigma_mu;
-    double s = 0.0;
-    for (int i = 0; i < nG; ++i) s = fma(ps[i] * pl[i], pl[i], s);
-    return s;
+  const bool two = a.A != a.Bm;
+  double* tileA = sm;                                          // [2][LG_DCH][NC][PX]
+  double* tileB = tileA + (two ? 2 * LG_DCH * NC * PX : 0);    // second operand (or the same tile)
+  double* S = tileB + 2 * LG_DCH * NC * PX;                    // [PX][NC][SP]: upper triangle = G, strict lower = L
+  double* dg = S + (size_t)PX * NC * SP;                       // [PX][NC]: diag(F2), later 1 / L_jj
+  const int tid = threadIdx.x, x = tid % PX, blk = tid / PX;
+  const int b0 = blockIdx.x * PX;
+  const size_t Bp = a.Bp;
+  // block (bi <= bj) of the upper triangle
+  int bi = 0, rem = blk;
+  while (rem >= NBR - bi) { rem -= NBR - bi; ++bi; }
+  const int bj = bi + rem;
+
+  auto load_stage = [&](int d0, int buf) {
+    // rows d0 .. d0 + LG_DCH: for every (d, c < NC) the PX consecutive points, 16 bytes at a time; c >= nc and d >= ndata are zero-filled
+    constexpr int CH = LG_DCH * NC * (PX / 2);
+    for (int i = tid; i < CH; i += NTHR) {
+      const int q = i % (PX / 2), c = (i / (PX / 2)) % NC, d = i / ((PX / 2) * NC);
+      const bool ok = c < nc && d0 + d < a.ndata;
+      const size_t off = ok ? ((size_t)(d0 + d) * nc + c) * Bp + b0 + 2 * q : 0;
+      const int so = buf * LG_DCH * NC * PX + (d * NC + c) * PX + 2 * q;
+      cp_async16z(tileA + so, a.A + off, ok);
+      if (two) cp_async16z(tileB + so, a.Bm + off, ok);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
   };
-  for (int e = threadIdx.y; e < nent; e += blockDim.y) {
-    int eg = 0, ej = 0, ra = 0, rb = 0;
-    if (e < ntri) {
-      while ((eg + 1) * (eg + 2) / 2 <= e) ++eg;
-      ej = e - eg * (eg + 1) / 2;
-      ra = 1 + eg; rb = 1 + ej;
-    } else if (e < ntri + nG) {
-      eg = e - ntri;
-      ra = 1 + eg;
-    }
-    const double* pv = a.V + (size_t)ra * Bp + b;
-    const double* py = a.Y + (size_t)rb * Bp + b;
-    // 8 independent partial sums: 16 loads in flight per thread (the loop is a chain of L2 round trips otherwise)
-    double sp[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    int d = 0;
-    for (; d + 8 <= a.ndata; d += 8) {
-      double v[8], y[8];
+
+  double acc[4][4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { v[u] = pv[(size_t)(d + u) * stride]; y[u] = py[(size_t)(d + u) * stride]; }
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) sp[u] = fma(v[u], y[u], sp[u]);
-    }
-    double st = 0.0;
-    for (; d < a.ndata; ++d) st = fma(pv[(size_t)d * stride], py[(size_t)d * stride], st);
-    const double sum = (((sp[0] + sp[1]) + (sp[2] + sp[3])) + ((sp[4] + sp[5]) + (sp[6] + sp[7]))) + st;
-    if (e < ntri) {
-      const double v = sum + sinv(eg, ej);  // marginal.py:167-175
-      F2[((size_t)eg * nG + ej) * LF_PX + lx] = v;
-      F2[((size_t)ej * nG + eg) * LF_PX + lx] = v;
-    } else if (e < ntri + nG) {
-      F1[(size_t)eg * LF_PX + lx] = -sum + sinv_mu(eg);  // marginal.py:177-185
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  const int nst = (a.ndata + LG_DCH - 1) / LG_DCH;
+  load_stage(0, 0);
+  for (int st = 0; st < nst; ++st) {
+    const int buf = st & 1;
+    if (st + 1 < nst) {
+      load_stage((st + 1) * LG_DCH, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;\n" ::);
     } else {
-      F0[lx] = sum + mu_s_mu();  // marginal.py:187-196
+      asm volatile("cp.async.wait_group 0;\n" ::);
     }
+    __syncthreads();
+    const double* ta = tileA + buf * LG_DCH * NC * PX + x;
+    const double* tb = tileB + buf * LG_DCH * NC * PX + x;
+#pragma unroll
+    for (int d = 0; d < LG_DCH; ++d) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = ta[(d * NC + 4 * bi + i) * PX];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = tb[(d * NC + 4 * bj + j) * PX];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  {  // G into shared memory (entries below the diagonal of a diagonal block are simply not used)
+    double* Sx = S + (size_t)x * NC * SP;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (4 * bi + i <= 4 * bj + j) Sx[(4 * bi + i) * SP + 4 * bj + j] = acc[i][j];
   }
   __syncthreads();
-  if (g != 0 || b >= a.B) return;
-  if (a.fullchi2)
-    for (int i = 0; i < nG; ++i) {
-      F1o[(size_t)i * LF_PX + lx] = F1[(size_t)i * LF_PX + lx];
-      F2d[(size_t)i * LF_PX + lx] = F2[((size_t)i * nG + i) * LF_PX + lx];
+
+  // ---- one warp per point ----
+  const int warp = tid >> 5, lane = tid & 31, nwarp = NTHR / 32;
+  for (int px = warp; px < PX; px += nwarp) {
+    const int b = b0 + px;
+    if (b >= a.B) continue;  // padding lanes of the batch
+    double* Sx = S + (size_t)px * NC * SP;
+    double* dx = dg + (size_t)px * NC;
+    // rows / columns of Sx: 0 = residual, 1 + i = Gaussian parameter i; lane = Gaussian row i
+    const int i = lane;
+    const bool row = i < nG;
+    const bool pp = a.pp_sinv != nullptr;
+    const double* ps = pp ? a.pp_sinv + (size_t)b * nG : nullptr;
+    const double* pl = pp ? a.pp_loc + (size_t)b * nG : nullptr;
+    auto sinv = [&](int r, int c) { return pp ? (r == c ? ps[r] : 0.0) : a.sigma_inv[r * nG + c]; };
+    // F2 = G + Sigma^-1 (marginal.py:167-175): strict lower triangle <- upper + prior, diagonal to dx
+    double f1 = 0.0, musmu_part = 0.0;
+    if (row) {
+      for (int j = 0; j < i; ++j) Sx[(1 + i) * SP + 1 + j] = Sx[(1 + j) * SP + 1 + i] + sinv(i, j);
+      dx[i] = Sx[(1 + i) * SP + 1 + i] + sinv(i, i);
+      const double smu = pp ? ps[i] * pl[i] : a.sigma_inv_mu[i];
+      f1 = -Sx[1 + i] + smu;  // F1 = -PG C^-1 (PNG - d) + Sigma^-1 mu (marginal.py:177-185); G[0][1+i]
+      if (pp) musmu_part = smu * pl[i];
     }
-  // in-place Cholesky F2 = L L^T on this point's column of shared memory
-  bool ok = true;
-  double logdet = 0.0;
-  for (int j = 0; j < nG && ok; ++j) {
-    double dj = F2[((size_t)j * nG + j) * LF_PX + lx];
-    for (int k = 0; k < j; ++k) { const double l = F2[((size_t)j * nG + k) * LF_PX + lx]; dj -= l * l; }
-    if (!(dj > 0.0)) { ok = false; break; }
-    const double ljj = sqrt(dj), rjj = 1.0 / ljj;
-    F2[((size_t)j * nG + j) * LF_PX + lx] = rjj;  // the diagonal holds 1 / L_jj: the solves below multiply instead of dividing
-    if (!a.jeffreys) logdet += log(dj);           // 2 ln L_jj; not needed without the ln det term (marginal.py:119-120)
-    for (int i = j + 1; i < nG; ++i) {
-      double s = F2[((size_t)i * nG + j) * LF_PX + lx];
-      for (int k = 0; k < j; ++k) s -= F2[((size_t)i * nG + k) * LF_PX + lx] * F2[((size_t)j * nG + k) * LF_PX + lx];
-      F2[((size_t)i * nG + j) * LF_PX + lx] = s * rjj;
+    double musmu = a.mu_sigma_mu;
+    if (pp) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) musmu_part += __shfl_xor_sync(0xffffffffu, musmu_part, o);
+      musmu = musmu_part;
     }
-  }
-  if (!ok) {  // reference raises RuntimeError("det of F2ij <= 0") (marginal.py:113-116); here: flag the point
-    a.logp[b] = -INFINITY;
-    a.status[b] = 1;
-    if (a.bestfit) for (int i = 0; i < nG; ++i) a.bestfit[(size_t)b * nG + i] = NAN;
-    if (a.fullchi2) a.fullchi2[b] = NAN;
-    return;
-  }
-  // y = L^-1 F1 ;  F1^T F2^-1 F1 = |y|^2
-  double quad = 0.0;
-  for (int i = 0; i < nG; ++i) {
-    double s = F1[(size_t)i * LF_PX + lx];
-    for (int k = 0; k < i; ++k) s -= F2[((size_t)i * nG + k) * LF_PX + lx] * F1[(size_t)k * LF_PX + lx];
-    s *= F2[((size_t)i * nG + i) * LF_PX + lx];
-    F1[(size_t)i * LF_PX + lx] = s;
-    quad += s * s;
-  }
-  logdet -= nG * log(2.0 * M_PI);  // ln det(F2 / 2 pi)
-  const double chi2 = -quad + F0[lx] + (a.jeffreys ? 0.0 : logdet);  // marginal.py:118-122
-  a.logp[b] = -0.5 * chi2;
-  a.status[b] = 0;
-  if (a.bestfit || a.fullchi2) {  // bG = L^-T y (marginal.py:117)
-    for (int i = nG - 1; i >= 0; --i) {
-      double s = F1[(size_t)i * LF_PX + lx];
-      for (int k = i + 1; k < nG; ++k) s -= F2[((size_t)k * nG + i) * LF_PX + lx] * F1[(size_t)k * LF_PX + lx];
-      s *= F2[((size_t)i * nG + i) * LF_PX + lx];
-      F1[(size_t)i * LF_PX + lx] = s;
-      if (a.bestfit) a.bestfit[(size_t)b * nG + i] = s;
+    const double F0 = Sx[0] + musmu;  // marginal.py:187-196
+    __syncwarp();
+    // left-looking Cholesky F2 = L L^T: column j of L from the rows' partial dot products, pivot broadcast by shuffle
+    bool ok = true;
+    double logdet = 0.0, rdiag = 0.0;
+    for (int j = 0; j < nG; ++j) {
+      double sacc = 0.0;
+      if (row && i >= j) {
+        sacc = i == j ? dx[j] : Sx[(1 + i) * SP + 1 + j];
+        const double* li = Sx + (1 + i) * SP + 1;
+        const double* lj = Sx + (1 + j) * SP + 1;
+        for (int k = 0; k < j; ++k) sacc = fma(-li[k], lj[k], sacc);
+      }
+      const double dj = __shfl_sync(0xffffffffu, sacc, j);
+      if (!(dj > 0.0)) { ok = false; break; }
+      const double rj = 1.0 / sqrt(dj);
+      if (!a.jeffreys) logdet += log(dj);  // 2 ln L_jj; not needed without the ln det term (marginal.py:119-120)
+      if (row && i > j) Sx[(1 + i) * SP + 1 + j] = sacc * rj;
+      if (i == j) rdiag = rj;
+      __syncwarp();
     }
-  }
-  if (a.fullchi2) {
-    // marginal.py:129-131: chi^2 of the data at the best-fit bG, r = PNG + bG.PG - d, without the prior terms:
-    //   r^T C^-1 r = F0' + 2 bG.g + bG^T F2' bG,  F2' = F2 - Sigma^-1,  g = PG C^-1 (PNG - d) = -(F1 - Sigma^-1 mu),
-    //   F0' = F0 - mu^T Sigma^-1 mu.  The strict upper triangle of F2 still holds the values from before the factorisation.
-    double full = F0[lx] - mu_s_mu();
-    for (int i = 0; i < nG; ++i) {
-      const double bi = F1[(size_t)i * LF_PX + lx];
-      full -= 2.0 * bi * (F1o[(size_t)i * LF_PX + lx] - sinv_mu(i));
-      full += bi * bi * (F2d[(size_t)i * LF_PX + lx] - sinv(i, i));
-      for (int j = i + 1; j < nG; ++j)
-        full += 2.0 * bi * F1[(size_t)j * LF_PX + lx] * (F2[((size_t)i * nG + j) * LF_PX + lx] - sinv(i, j));
+    if (!ok) {  // reference raises RuntimeError("det of F2ij <= 0") (marginal.py:113-116); here: flag the point
+      if (lane == 0) {
+        a.logp[b] = -INFINITY;
+        a.status[b] = 1;
+        if (a.fullchi2) a.fullchi2[b] = NAN;
+      }
+      if (a.bestfit && row) a.bestfit[(size_t)b * nG + i] = NAN;
+      continue;
     }
-    a.fullchi2[b] = full;
+    // y = L^-1 F1 ;  F1^T F2^-1 F1 = |y|^2
+    double quad = 0.0, y = 0.0, bcur = f1;
+    for (int j = 0; j < nG; ++j) {
+      const double yj = __shfl_sync(0xffffffffu, bcur, j) * __shfl_sync(0xffffffffu, rdiag, j);
+      quad = fma(yj, yj, quad);
+      if (row && i > j) bcur = fma(-Sx[(1 + i) * SP + 1 + j], yj, bcur);
+      if (i == j) y = yj;
+    }
+    if (lane == 0) {
+      logdet -= nG * log(2.0 * M_PI);  // ln det(F2 / 2 pi)
+      const double chi2 = -quad + F0 + (a.jeffreys ? 0.0 : logdet);  // marginal.py:118-122
+      a.logp[b] = -0.5 * chi2;
+      a.status[b] = 0;
+    }
+    if (a.bestfit || a.fullchi2) {  // bG = L^-T y (marginal.py:117)
+      double xb = 0.0, ycur = y;
+      for (int j = nG - 1; j >= 0; --j) {
+        const double xj = __shfl_sync(0xffffffffu, ycur, j) * __shfl_sync(0xffffffffu, rdiag, j);
+        if (row && i < j) ycur = fma(-Sx[(1 + j) * SP + 1 + i], xj, ycur);
+        if (i == j) xb = xj;
+      }
+      if (a.bestfit && row) a.bestfit[(size_t)b * nG + i] = xb;
+      if (a.fullchi2) {
+        // marginal.py:129-131: chi^2 of the data at the best-fit bG, r = PNG + bG.PG - d, without the prior terms:
+        //   r^T C^-1 r = G00 + 2 sum_i bG_i G[0][i] + sum_ij bG_i bG_j G[i][j]   (G = the upper triangle, untouched)
+        double t = 0.0;
+        if (row) dx[i] = xb;  // diag(F2) is no longer needed: the best fit, for the other lanes
+        __syncwarp();
+        if (row) {
+          double off = 0.0;
+          for (int j = i + 1; j < nG; ++j) off = fma(dx[j], Sx[(1 + i) * SP + 1 + j], off);
+          t = xb * (2.0 * Sx[1 + i] + xb * Sx[(1 + i) * SP + 1 + i] + 2.0 * off);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) a.fullchi2[b] = Sx[0] + t;
+      }
+    }
   }
 }
 
@@ -312,6 +374,22 @@ int fill_vectors(const eftb_like* L, int Bp, const double* const* terms, const d
   like_vectors_kernel<<<grid, 128, 0, s>>>(a);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;
+}
+
+template <int NC, int PX>
+int launch_gram_t(const FinArgs& a, cudaStream_t s) {
+  constexpr int NBR = NC / 4, NTHR = PX * NBR * (NBR + 1) / 2;
+  const bool two = a.A != a.Bm;
+  const size_t smem = sizeof(double) * ((size_t)(two ? 2 : 1) * 2 * LG_DCH * NC * PX + (size_t)PX * NC * (NC + 1) + (size_t)PX * NC);
+  static DeviceSmem configured;
+  EFTB_SET_SMEM(configured, (like_gram_kernel<NC, PX>), smem);
+  like_gram_kernel<NC, PX><<<a.Bp / PX, NTHR, smem, s>>>(a);
+  EFTB_LAUNCH_CHECK();
+  return EFTB_OK;
+}
+
+int launch_gram(const FinArgs& a, cudaStream_t s) {
+  return a.ngauss + 1 <= 16 ? launch_gram_t<16, 16>(a, s) : launch_gram_t<32, 8>(a, s);
 }
 
 }  // namespace
@@ -345,6 +423,29 @@ int eftb_like_create(const eftb_like_config* cfg, const eftb_like_constants* h, 
   rc |= upload(&L->data, h->data, nd);
   rc |= upload(&L->picc, h->picc, nd);
   rc |= gemm_upload(h->invcov, 1, nd, nd, &L->invcov);
+  {  // C^-1 = L L^T on the host (nd x nd, once); a matrix that is not positive definite keeps the two-operand form
+    std::vector<double> lo((size_t)nd * nd, 0.0);
+    bool pd = true;
+    for (int j = 0; j < nd && pd; ++j) {
+      double dj = h->invcov[(size_t)j * nd + j];
+      for (int k = 0; k < j; ++k) dj -= lo[(size_t)j * nd + k] * lo[(size_t)j * nd + k];
+      if (!(dj > 0.0)) { pd = false; break; }
+      const double ljj = sqrt(dj);
+      lo[(size_t)j * nd + j] = ljj;
+      for (int i = j + 1; i < nd; ++i) {
+        double v = 0.5 * (h->invcov[(size_t)i * nd + j] + h->invcov[(size_t)j * nd + i]);
+        for (int k = 0; k < j; ++k) v -= lo[(size_t)i * nd + k] * lo[(size_t)j * nd + k];
+        lo[(size_t)i * nd + j] = v / ljj;
+      }
+    }
+    if (pd) {
+      std::vector<double> lt((size_t)nd * nd, 0.0);
+      for (int i = 0; i < nd; ++i)
+        for (int j = 0; j <= i; ++j) lt[(size_t)j * nd + i] = lo[(size_t)i * nd + j];
+      rc |= gemm_upload(lt.data(), 1, nd, nd, &L->factor);
+      L->has_factor = true;
+    }
+  }
   rc |= upload(&L->g_count, h->g_count, ng);
   rc |= upload(&L->g_tracer, h->g_tracer, (size_t)ng * 2);
   rc |= upload(&L->g_term, h->g_term, (size_t)ng * 6);
@@ -364,6 +465,7 @@ void eftb_like_destroy(eftb_like* L) {
                   L->g_count, L->g_tracer, L->g_term, L->g_var, L->g_coef, L->sigma_inv, L->sigma_inv_mu};
   for (void* p : ptrs) if (p) cudaFree(p);
   gemm_free(&L->invcov);
+  gemm_free(&L->factor);
   delete L;
 }
 
@@ -403,19 +505,13 @@ int eftb_like_eval_priors(const eftb_like* L, int B, const double* const* terms,
   double* Y = V + (size_t)nd * nc * Bp;
   int rc = fill_vectors(L, Bp, terms, fgrowth, nuis, V, s);
   if (rc) return rc;
-  rc = gemm_run(L->invcov, V, Y, nc * Bp, 1, 1, 0, 0, 0, 0, s);
+  static const bool force_two = getenv("EFTB_LIKE_TWO_OPERAND") != nullptr;  // tuning / test knob: the C^-1 V form
+  const bool one = L->has_factor && !force_two;
+  rc = gemm_run(one ? L->factor : L->invcov, V, Y, nc * Bp, 1, 1, 0, 0, 0, 0, s);
   if (rc) return rc;
-  FinArgs a{V, Y, L->sigma_inv, L->sigma_inv_mu, prior_loc, prior_sigma_inv, L->mu_sigma_mu, logp, bestfit, fullchi2, status, B, Bp, nd,
-            L->cfg.ngauss, L->cfg.jeffreys};
-  const int nG = L->cfg.ngauss;
-  size_t smem = sizeof(double) * ((size_t)nG * nG * LF_PX + (size_t)3 * nG * LF_PX + LF_PX);
-  static DeviceSmem configured;
-  EFTB_SET_SMEM(configured, like_finish_kernel, smem);
-  const int nent = nG * (nG + 1) / 2 + nG + 1;
-  dim3 block(LF_PX, nent < 64 ? nent : 64), grid(Bp / LF_PX);
-  like_finish_kernel<<<grid, block, smem, s>>>(a);
-  EFTB_LAUNCH_CHECK();
-  return EFTB_OK;
+  FinArgs a{one ? Y : V, Y, L->sigma_inv, L->sigma_inv_mu, prior_loc, prior_sigma_inv, L->mu_sigma_mu, logp, bestfit, fullchi2, status, B, Bp,
+            nd, L->cfg.ngauss, L->cfg.jeffreys};
+  return launch_gram(a, s);
 }
 
 int eftb_like_vectors(const eftb_like* L, int B, const double* const* terms, const double* const* fgrowth, const double* nuis,

@@ -234,3 +234,52 @@ def test_config3_gaussian_priors_against_reference(golden3):
     np.testing.assert_allclose(_np(res["eftlike_fullchi2"]), g["LEX_NGC_gauss.fullchi2"], rtol=1e-6)
     best = np.stack([_np(res["bestfit"]["marg_" + n]) for n in like.gaussian_names], axis=1)
     np.testing.assert_allclose(best, g["LEX_NGC_gauss.best"], rtol=1e-5, atol=1e-7)
+
+
+def test_wide_marginalisation_and_two_operand_form(golden3, monkeypatch):
+    """17 marginalised parameters (the 32-column variant of the Gram / warp-Cholesky kernel) and the two-operand
+    fallback (C^-1 V instead of the Cholesky factor of C^-1): both against marginal.py restated on the kernel's own
+    PNG / PG vectors, which the tests above pin to the reference."""
+    import pybird_oracle as orc
+    import refdriver
+
+    g = golden3
+    marg = refdriver.marg_block(refdriver.GAUSS_SCALES)
+    for pre in ("LRG_NGC_", "ELG_NGC_"):
+        marg[pre] = dict(marg[pre], cemono={"scale": 2.0})
+    marg["X_NGC_cemono"] = {"scale": 2.0}
+    th, like = _config3(dict(np.load(DATA)), marg, False)
+    assert len(like.gaussian_names) == 17
+    cosmo, params = _inputs(g)
+    th.calculate(cosmo)
+    png, pg = like.PNG_PG(params)
+    png, pg = _np(png), _np(pg)
+    sig = like.sigma_inv
+
+    def check():
+        res = like.calculate(params, want_bestfit=True)
+        lp, full = _np(res["logp"]), _np(res["eftlike_fullchi2"])
+        best = np.stack([_np(res["bestfit"]["marg_" + n]) for n in like.gaussian_names], axis=1)
+        for i in range(0, png.shape[0], 5):
+            ref_lp, ref_full, ref_best = orc.marginalized_logp(png[i], pg[i], like.data_vector, like.invcov, sigma_inv=sig, return_bestfit=True)
+            assert lp[i] == pytest.approx(ref_lp, rel=1e-9)
+            assert full[i] == pytest.approx(ref_full, rel=1e-7)
+            np.testing.assert_allclose(best[i], ref_best, rtol=1e-5, atol=1e-7)
+        return lp
+
+    lp_one = check()
+    # the environment knob is read once per process by the library: exercise the two-operand form through a fresh process
+    import subprocess
+    import sys
+
+    code = ("import os, sys, numpy as np; sys.path[:0] = [%r, %r, %r]; os.environ['EFTB_LIKE_TWO_OPERAND'] = '1'\n"
+            "import test_gpu_config3 as t, refdriver\n"
+            "g = dict(np.load(os.path.join(t.GOLDEN, 'config3_like.npz')))\n"
+            "th, like = t._config3(dict(np.load(t.DATA)), refdriver.marg_block(), True)\n"
+            "cosmo, params = t._inputs(g); th.calculate(cosmo); res = like.calculate(params)\n"
+            "np.testing.assert_allclose(res['logp'].cpu().numpy(), g['LEX_NGC.logp'], rtol=1e-9); print('two-operand ok')\n"
+            % (os.path.dirname(os.path.abspath(__file__)), os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"),
+               os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "two-operand ok" in out.stdout, out.stderr[-2000:]
+    assert np.isfinite(lp_one).all()
