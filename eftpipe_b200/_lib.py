@@ -83,6 +83,7 @@ SIGNATURES = {
     "eftb_ap_scratch_bytes": (C.c_size_t, [_VP, _I]),
     "eftb_project": (C.c_int, [_VP, _I, _VP, _VP, _VP]),
     "eftb_eval_terms": (C.c_int, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "eftb_workspace_terms": (C.c_int, [_VP, _I, _VP, _SZ, _I, _VP, _VP]),
     "eftb_operator_create": (C.c_int, [_I, _I, c_double_p, C.POINTER(_VP)]),
     "eftb_operator_destroy": (None, [_VP]),
     "eftb_operator_apply": (C.c_int, [_VP, _VP, _VP, _I, _VP]),

@@ -416,6 +416,24 @@ int eftb_eval_terms(const eftb_plan* p, int B, const double* plin, const double*
   return EFTB_OK;
 }
 
+int eftb_workspace_terms(const eftb_plan* p, int B, const void* workspace, size_t workspace_bytes, int stage, double* terms_bm,
+                         void* stream) {
+  EFTB_NEED(p && workspace && terms_bm && B >= 1 && (stage == 0 || stage == 1), "NULL/invalid argument");
+  const eftb_config& c = p->cfg;
+  if (stage == 1 && !c.has_ap) { eftb_set_error("eftb_workspace_terms: plan built without AP"); return EFTB_ERR_NOT_BUILT; }
+  if (workspace_bytes < eftb_workspace_bytes(p, B)) { eftb_set_error("eftb_workspace_terms: workspace too small"); return EFTB_ERR_WORKSPACE; }
+  // the layout of eftb_eval_terms: u | F | D (coef | T2 after the AP stage) | P22 | Dg | T | ...
+  const int Bp = eftb_padded_batch(B);
+  Sizes z = sizes(p, Bp);
+  const double* w = (const double*)workspace;
+  const size_t ncoef = c.has_ap ? ap_coef_doubles(p, Bp) : 0;
+  const double* D = w + z.u + z.F;
+  const double* T = D + (z.D > ncoef + z.T ? z.D : ncoef + z.T) + z.P22 + z.Dg;
+  const double* src = stage == 0 ? T : D + ncoef;
+  EFTB_CUDA_CHECK(cudaMemcpyAsync(terms_bm, src, z.T * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return EFTB_OK;
+}
+
 struct eftb_operator {
   GemmMatrix A;
 };

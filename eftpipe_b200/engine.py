@@ -340,6 +340,18 @@ class DevicePlan:
         return (out_pm if want_pm else None), (out_bm if want_bm else None)
 
 
+    def stage_terms(self, B, stage):
+        """(Nl, Nk, nterm, Bp) batch-minor term arrays the last `eval_terms` left in the workspace: stage 0 = after the IR
+        resummation, 1 = after AP (the reference's "IRresum" / "APeffect" Bird snapshots)"""
+        if self._ws is None:
+            raise RuntimeError("stage_terms: no evaluation has run on this plan yet")
+        need = self.lib.eftb_workspace_bytes(self.handle, int(B))
+        out = self._empty(self.cfg.Nl, self.cfg.Nk, self.cfg.nterm, self.padded(B))
+        _lib.check(self.lib.eftb_workspace_terms(self.handle, B, _p(self._ws), need, int(stage), _p(out), _stream_ptr(self.torch)),
+                   "eftb_workspace_terms")
+        return out
+
+
 class DeviceLikelihood:
     """likelihood.py EFTLike.calculate + marginal.py for a batch of points (see likelihood.py here)."""
 

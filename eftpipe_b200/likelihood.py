@@ -366,6 +366,11 @@ class EFTLike(Marginalizable):
                 reqs["nonlinear_Plk_gaussian_grid"][t] = req
         return {k: v for k, v in reqs.items() if v}
 
+    def _product_key(self, t):
+        """which of the tracer's products this likelihood reads (likelihood.py:503-516, :535-547)"""
+        binned = bool(self.with_binning[t])
+        return dict(chained=bool(self.chained[t]), binned=binned, interp=not binned and bool(self.with_interp[t]))
+
     def marginalizable_params(self):
         params = []
         for b in self.eft_bases:
@@ -399,7 +404,7 @@ class EFTLike(Marginalizable):
         specs = []
         for t in self.tracers:
             m = self.minfodict[t]
-            info = theory.product_info(t, chained=self.chained[t], binned=self.with_binning[t])
+            info = theory.product_info(t, **self._product_key(t))
             nk, rows_g = info["nk"], None
             if self.with_binning[t]:
                 if nk != m.kout.size or info.get("interp_nk") is not None:
@@ -435,7 +440,7 @@ class EFTLike(Marginalizable):
         th = self.provider
         terms, fs = [], []
         for t in self.tracers:
-            bm, f_bm = th.get_nonlinear_Plk_terms(t, chained=self.chained[t], binned=self.with_binning[t])
+            bm, f_bm = th.get_nonlinear_Plk_terms(t, **self._product_key(t))
             terms.append(bm)
             fs.append(f_bm)
         B = th.B

@@ -534,6 +534,19 @@ def build_tracer_plan(Nl=3, kmax=0.3, NFFT=256, with_NNLO=False, kin=None, windo
     return plan
 
 
+def stack_projections(blocks):
+    """Several projections of one tracer (its (chained, binned) products, theory.py:590-604, un-binned interpolation
+    points, window / fibre snapshots) as ONE operator: the blocks' rows one after the other, so that a single projection
+    GEMM of the fused pipeline yields every product; `offsets[i] : offsets[i + 1]` are the rows of block i."""
+    mats = [np.asarray(b["matrix"], float) for b in blocks]
+    out = dict(matrix=np.vstack(mats), picc=np.concatenate([np.asarray(b["picc"], float).reshape(-1) for b in blocks]),
+               shape=(1, int(sum(m.shape[0] for m in mats))), st=True, matrix_st=None,
+               offsets=np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]).astype(int))
+    if any(b.get("matrix_st") is not None for b in blocks):
+        out["matrix_st"] = np.vstack([np.asarray(b["matrix_st"] if b.get("matrix_st") is not None else b["matrix"], float) for b in blocks])
+    return out
+
+
 def compose_projection(g: GridConfig, window=None, icc=None, binning=None, chained=False, window_st=True, fiber=None,
                        fiber_st=False, window_stoch=None, window_picc=None):
     """Compose window (+ICC), fibre collisions, binning and chained mixing into one matrix on the Nl*Nk nodes, in the

@@ -66,45 +66,113 @@ def _merge(default, cfg):
     return out
 
 
+def _bool_list(x):
+    """tools.bool_or_list: a bool or a list of bools -> ordered list without repetitions"""
+    vals = [bool(x)] if isinstance(x, (bool, int, np.bool_)) else [bool(v) for v in x]
+    return list(dict.fromkeys(vals))
+
+
 class EFTLSS:
+    """The batched core of the theory tree.  `eftpipe_b200.cobaya` wraps it into Cobaya components with the reference's
+    class layout (EFTLSS -> EFTLeafKernel -> EFTLeaf); it can also be driven directly:
+
+        th = EFTLSS(tracers).must_provide(requirements).initialize()
+        th.calculate({tracer: dict(pkh=(B, 200), f=, DA=, H=) or a BoltzmannExtractor})
+        ls, k, Plk = th.get_nonlinear_Plk_grid(tracer, params, chained=False, binned=True)
+
+    Every (chained, binned) product a tracer is asked for (theory.py:590-604), the un-binned interpolation points and the
+    window / fibre snapshots are row blocks of ONE stacked projection operator (plan.stack_projections): one pass of the
+    fused pipeline per tracer yields them all."""
+
     def __init__(self, tracers: dict, cache_dir_path=None):
         tracers = deepcopy(tracers)
         default = tracers.pop("default", {})
         self.tracers = {name: _merge(default, cfg or {}) for name, cfg in tracers.items()}
+        if not self.tracers:
+            raise LoggedError("No tracer specified")
         for name, cfg in self.tracers.items():
             unknown = set(cfg) - _KNOWN
             if unknown:
                 raise LoggedError(f"tracer {name}: unknown configuration keys {sorted(unknown)}")
+            cross = cfg.get("cross", False)  # theory.py:145-155
+            if not isinstance(cross, bool):
+                if not isinstance(cross, (list, tuple)) or len(cross) != 2:
+                    raise LoggedError(f"tracer {name}: expect a list of 2 elements, but given cross={cross!r}")
+                if diff := set(cross).difference(self.tracers):
+                    raise LoggedError(f"tracer {name}: cross={cross!r} contains unknown tracer names: {diff!r}")
         self.cache_dir_path = cache_dir_path
         self.requirements = {}
         self.bases, self.commons, self.plans, self.info = {}, {}, {}, {}
         self._state = {}
         self.B = 0
 
-    # ---- requirements (theory.py:773-799) ----
+    # ---- requirements (theory.py:165-194, :497-555, :773-827) ----
     def must_provide(self, requirements: dict):
-        """`nonlinear_Plk_interpolator` (theory.py:785-790) takes one extra key here, `kout`: the abscissae the
-        consumer will evaluate the interpolator at.  The reference hands out a callable; on the batched path the
-        interpolation is a fixed operator composed into the tracer's projection (plan.interp_matrices), so the theory
-        has to know the points when the plan is built."""
+        """Reference grammar: `{product: {tracer: {"ls": [...], "chained": bool | [bool], "binned": bool | [bool], "binning":
+        {"kout": ...}}}}` for `nonlinear_Plk_grid`, `nonlinear_Plk_gaussian_grid`, `nonlinear_Plk_interpolator`; `snapshots`,
+        `bird_component`, `eft_params_values_dict` take no settings.  A `default` tracer entry applies to every tracer named
+        in the same product (theory.py:188-192).
+
+        One extension: `nonlinear_Plk_interpolator` accepts `kout`, the abscissae the consumer will evaluate the
+        interpolator at.  The reference hands out a callable; on the batched path an interpolation at fixed points is a
+        fixed operator composed into the projection (plan.interp_matrices), which the un-binned likelihood read-out
+        (likelihood.py:503-547) uses.  Without `kout` the interpolator is built from the un-binned grid product, as in
+        theory.py:862-871."""
         for product, per_tracer in requirements.items():
-            if product not in ("nonlinear_Plk_grid", "nonlinear_Plk_gaussian_grid", "nonlinear_Plk_interpolator"):
-                raise LoggedError(f"unsupported requirement {product} on the batched path")
-            for tracer, req in per_tracer.items():
+            if product not in ("nonlinear_Plk_grid", "nonlinear_Plk_gaussian_grid", "nonlinear_Plk_interpolator", "snapshots",
+                               "bird_component", "eft_params_values_dict"):
+                raise LoggedError(f"Unexpected requirement {product}")
+            per_tracer = dict(per_tracer or {})
+            default = per_tracer.pop("default", None)
+            for tracer, cfg in per_tracer.items():
                 if tracer not in self.tracers:
-                    raise LoggedError(f"unknown tracer {tracer}")
-                old = self.requirements.get(tracer)
-                new = dict(ls=sorted(req["ls"]), chained=bool(req.get("chained", False)),
-                           binned=bool(req.get("binned", False)), binning=req.get("binning"), interp=None)
+                    raise LoggedError(f"Unknown tracer name: {tracer}")
+                cfg = _merge(default or {}, cfg or {}) if default else dict(cfg or {})
+                req = self.requirements.setdefault(tracer, dict(Nl=0, No=0, chained=[], binned=[], binning=None, interp={},
+                                                                snapshots=False, bird_component=False, order=[]))
+                if product in ("snapshots", "bird_component"):
+                    req[product] = True
+                    continue
+                if product == "eft_params_values_dict":
+                    continue
+                ls = [cfg["ls"]] if isinstance(cfg["ls"], (int, np.integer)) else list(cfg["ls"])  # mandatory key
+                chained = _bool_list(cfg.get("chained", False))
+                if chained == [True]:  # ls are chained multipoles: the power spectrum needs one more (theory.py:511-512)
+                    ls = sorted(set(ls + [l + 2 for l in ls]))
+                if any(l % 2 == 1 for l in ls):
+                    raise LoggedError(f"Invalid multipoles: {ls}")
+                if max(ls) > 4:
+                    raise LoggedError(f"Unsupported multipoles: {ls}")
+                Nl = max(ls) // 2 + 1
+                req["Nl"], req["No"] = max(req["Nl"], Nl), max(req["No"], Nl)
+                binned = _bool_list(cfg.get("binned", False))
                 if product == "nonlinear_Plk_interpolator":
-                    if "kout" not in req:
-                        raise LoggedError("nonlinear_Plk_interpolator: the batched path needs the evaluation points `kout`")
-                    new["binned"], new["interp"] = False, np.asarray(req["kout"], float)
-                if old is not None and (old["ls"], old["chained"], old["binned"]) != (new["ls"], new["chained"], new["binned"]):
-                    raise LoggedError("does not support multiple different product requirements per tracer")
-                if old is not None and new["interp"] is None:
-                    new["interp"] = old["interp"]
-                self.requirements[tracer] = new
+                    if True in binned:
+                        raise LoggedError("binned Plk interpolator not supported")
+                    if cfg.get("kout") is not None:
+                        for c in chained:
+                            kout = np.asarray(cfg["kout"], float)
+                            if c in req["interp"] and not np.array_equal(req["interp"][c], kout):
+                                raise LoggedError("does not support multiple different interpolation grids per tracer")
+                            req["interp"][c] = kout
+                            req["order"].append(("interp", c, False))
+                        req["chained"] = list(dict.fromkeys(req["chained"] + chained))
+                        continue
+                if True in binned:
+                    binning = cfg.get("binning")
+                    if binning is None:
+                        raise LoggedError("binned=True but missing binning")
+                    if "kout" not in binning and "kedges" not in binning:
+                        raise LoggedError("missing kout in binning")
+                    old = req["binning"]
+                    if old is not None:  # theory.py:536-548: different binning settings are not allowed
+                        same = set(old) == set(binning) and all(np.array_equal(np.asarray(old[k]), np.asarray(binning[k])) for k in old)
+                        if not same:
+                            raise LoggedError("does not support multiple different binning requirements")
+                    req["binning"] = deepcopy(binning)
+                req["chained"] = list(dict.fromkeys(req["chained"] + chained))
+                req["binned"] = list(dict.fromkeys(req["binned"] + binned))
+                req["order"] += [("grid", c, b) for c in chained for b in binned]
         return self
 
     # ---- plan construction (theory.py:399-495) ----
@@ -123,30 +191,46 @@ class EFTLSS:
             return own(a) + own(b)
         return own(cfg) + own(cfg)
 
+    def build_basis(self, name):
+        """theory.py:284-294"""
+        cfg = self.tracers[name]
+        cross = cfg.get("cross")
+        cross_prefix = [related_prefix(t, self.tracers[t]) for t in cross] if isinstance(cross, (list, tuple)) else []
+        return find_param_basis(cfg.get("basis", "westcoast"))(prefix=tracer_prefix(name, cfg), cross_prefix=cross_prefix)
+
     def initialize(self):
+        import itertools
+
         for name, cfg in self.tracers.items():
+            self.bases[name] = self.build_basis(name)
             req = self.requirements.get(name)
-            if req is None:
+            if req is None or req["No"] == 0:
                 continue
-            ls = req["ls"]
-            No = max(ls) // 2 + 1 + (1 if req["chained"] else 0)
-            Nl = max(cfg.get("Nl", No), No)
+            No = req["No"]
+            Nl = max(cfg.get("Nl", 0) or 0, req["Nl"])
             kmA, krA, ndA, kmB, krB, ndB = self._scales(name)
-            basis_cls = find_param_basis(cfg.get("basis", "westcoast"))
+            basis = self.bases[name]
             cross = cfg.get("cross")
-            cross_prefix = [related_prefix(t, self.tracers[t]) for t in cross] if isinstance(cross, (list, tuple)) else []
-            basis = basis_cls(prefix=tracer_prefix(name, cfg), cross_prefix=cross_prefix)
+            counterform = cfg.get("counterform") or basis.counterform()
             co = Common(Nl=Nl, No=No, kmax=cfg.get("kmax", 0.3), kmA=kmA, krA=krA, ndA=ndA, kmB=kmB, krB=krB, ndB=ndB,
-                        counterform=basis.counterform(), with_NNLO=bool(cfg.get("with_NNLO", False)),
+                        counterform=counterform, with_NNLO=bool(cfg.get("with_NNLO", False)),
                         optiresum=bool(cfg.get("optiresum", False)), IRcutoff=cfg.get("IRcutoff", False),
                         kIR=cfg.get("kIR"))  # theory.py:421-437
+            snaps = {}
+            rs = dict(cfg.get("IRresum") or {})
+            with_resum = bool(cfg.get("with_IRresum", True))
+            if with_resum and rs.get("snapshot"):
+                snaps["IRresum"] = ("stage", 0)
             ap = None
             if cfg.get("with_APeffect"):
                 apc = dict(cfg.get("APeffect") or {})
-                apc.setdefault("z_AP", cfg["z"])  # theory.py:458: z_AP defaults to the tracer's z
+                if apc.get("z_AP") is None:
+                    apc["z_AP"] = cfg["z"]  # theory.py:458: z_AP defaults to the tracer's z
                 apo = _construct(APeffect, apc, co=Common(Nl=Nl))
                 ap = dict(DA=apo.DA, H=apo.H, nbinsmu=apc.get("nbinsmu", 200), accboost=apc.get("accboost", 1), APst=apo.APst)
                 self.info.setdefault(name, {})["ap"] = apo
+                if apc.get("snapshot"):
+                    snaps["APeffect"] = ("stage", 1)
             window = icc = custom = None
             ww = cfg.get("with_window")
             if ww:
@@ -165,52 +249,90 @@ class EFTLSS:
             fiber = None
             if cfg.get("with_fiber"):  # theory.py:378-385, :482-485
                 fiber = _construct(FiberCollision, dict(cfg.get("fiber") or {}), co=co)
-            binm = None
-            keff = co.k
-            if req["binned"]:
-                bo = Binning(co=co, **(req["binning"] or cfg.get("binning") or {}))
-                binm, keff = bo.matrix, bo.keff
-            elif req["interp"] is not None:
-                # un-binned interpolated products: rows [0, nkout) = PlkInterpolator (theory.py:75-106), rows
-                # [nkout, 2 nkout) = the plain cubic interpolation of the marginalised rows (likelihood.py:510-513)
-                keff = req["interp"]
-                binm = np.vstack(P.interp_matrices(co.k, keff))
             g = P.GridConfig(Nl=Nl, kmax=cfg.get("kmax", 0.3), with_NNLO=co.with_NNLO, optiresum=co.optiresum)
-            proj = None
-            if custom is not None:
-                proj = P.compose_projection(g, window=custom["matrix"], icc=None, binning=binm, chained=req["chained"],
-                                            fiber=None if fiber is None else fiber.matrix(),
-                                            fiber_st=False if fiber is None else fiber.fiberst,
-                                            window_stoch=custom["matrix_st"], window_picc=custom["picc"])
-                proj["kout"] = keff
-            elif window is not None or binm is not None or req["chained"] or fiber is not None:
-                proj = P.compose_projection(
+            bo = Binning(co=co, **req["binning"]) if req["binning"] is not None else None
+
+            def project(binm, chained, with_fiber=True):
+                fm = fiber.matrix() if (fiber is not None and with_fiber) else None
+                fst = fiber.fiberst if (fiber is not None and with_fiber) else False
+                if custom is not None:
+                    return P.compose_projection(g, window=custom["matrix"], icc=None, binning=binm, chained=chained, fiber=fm, fiber_st=fst,
+                                                window_stoch=custom["matrix_st"], window_picc=custom["picc"])
+                return P.compose_projection(
                     g, window=None if window is None else window_matrix(window),
                     icc=None if icc is None else dict(matrix=icc.effective_matrix(), PSN_times_Pshot=icc.PSN),
-                    binning=binm, chained=req["chained"], window_st=True if window is None else window.window_st,
-                    fiber=None if fiber is None else fiber.matrix(), fiber_st=False if fiber is None else fiber.fiberst)
-                proj["kout"] = keff
-            rs = cfg.get("IRresum") or {}
-            host = P.build_tracer_plan(Nl=Nl, kmax=cfg.get("kmax", 0.3), with_NNLO=co.with_NNLO,
-                                       with_resum=bool(cfg.get("with_IRresum", True)), resum_NFFT=rs.get("NFFT", 192),
-                                       ap=ap, projection=proj, optiresum=co.optiresum, ircutoff=co.IRcutoff, kIR=co.kIR,
-                                       lambda_ir=rs.get("LambdaIR", P.LAMBDA_IR))
-            self.bases[name], self.commons[name] = basis, co
+                    binning=binm, chained=chained, window_st=True if window is None else window.window_st, fiber=fm, fiber_st=fst)
+
+            # the products, in the order they were asked for (the first one is the tracer's default product)
+            keys = list(dict.fromkeys(req["order"] + [("grid", c, b) for c, b in itertools.product(req["chained"], req["binned"])]))
+            blocks, meta = [], {}
+            for key in keys:
+                kind, chained, binned = key
+                if kind == "interp":
+                    # rows [0, nkout) of every multipole = PlkInterpolator (theory.py:75-106), rows [nkout, 2 nkout) = the
+                    # plain cubic interpolation of the marginalised rows (likelihood.py:510-513)
+                    keff = req["interp"][chained]
+                    binm = np.vstack(P.interp_matrices(co.k, keff))
+                elif binned:
+                    binm, keff = bo.matrix, bo.keff
+                else:
+                    binm, keff = None, co.k
+                blk = project(binm, chained)
+                nl_out, nk = blk["shape"]
+                nmult = (No - 1) if chained else No  # theory.py:599-603
+                meta[key] = dict(nl_out=nl_out, nk=nk, nout=nl_out * nk, nterm=g.nterm, kout=np.asarray(keff, float),
+                                 ls=[2 * i for i in range(min(nmult, nl_out))], No=No, interp_nk=len(keff) if kind == "interp" else None)
+                blocks.append(blk)
+            if req["snapshots"]:  # theory.py:260, :576-581: what the plugins were told to keep (`snapshot: True`)
+                for plug, wcfg, with_f in (("window", cfg.get("window"), False), ("fiber", cfg.get("fiber"), True)):
+                    if (wcfg or {}).get("snapshot") and (window is not None or custom is not None) and (plug == "window" or fiber is not None):
+                        key = ("snapshot", plug, False)
+                        blk = project(None, False, with_fiber=with_f)
+                        meta[key] = dict(nl_out=blk["shape"][0], nk=blk["shape"][1], nout=blk["shape"][0] * blk["shape"][1], nterm=g.nterm,
+                                         kout=co.k, ls=[2 * i for i in range(blk["shape"][0])], No=No, interp_nk=None)
+                        blocks.append(blk)
+                        snaps[plug] = ("block", key)
+            trivial = window is None and custom is None and fiber is None and all(k == ("grid", False, False) for k in meta)
+            proj = None
+            if not trivial:
+                proj = P.stack_projections(blocks)
+                for key, off0, off1, blk in zip(meta, proj["offsets"][:-1], proj["offsets"][1:], blocks):
+                    meta[key].update(row0=int(off0), row1=int(off1), picc=np.asarray(blk["picc"], float).reshape(-1))
+            else:
+                for key in meta:
+                    meta[key].update(row0=0, row1=Nl * g.Nk, picc=np.zeros(Nl * g.Nk))
+            host = P.build_tracer_plan(Nl=Nl, kmax=cfg.get("kmax", 0.3), with_NNLO=co.with_NNLO, with_resum=with_resum,
+                                       resum_NFFT=rs.get("NFFT", 192), ap=ap, projection=proj, optiresum=co.optiresum,
+                                       ircutoff=co.IRcutoff, kIR=co.kIR, lambda_ir=rs.get("LambdaIR", P.LAMBDA_IR))
+            self.commons[name] = co
             self.plans[name] = DevicePlan(host)
-            nl_out, nk = host.out_shape if proj is not None else (Nl, g.Nk)
-            picc = host.picc_out if proj is not None else np.zeros(Nl * g.Nk)
-            self.info.setdefault(name, {}).update(nout=nl_out * nk, nterm=g.nterm, nk=nk, picc=picc, kout=keff,
-                                                  ls=[2 * i for i in range(nl_out)], No=No,
-                                                  interp_nk=None if req["interp"] is None else len(keff))
+            first = meta[keys[0]]
+            self.info.setdefault(name, {}).update(products=meta, default=keys[0], snapshots=snaps, **first)
         return self
 
-    def product_info(self, tracer, chained=False, binned=True):
-        return self.info[tracer]
+    def _product(self, tracer, chained=None, binned=None, interp=False):
+        info = self.info[tracer]
+        if chained is None and binned is None and not interp:
+            return info["products"][info["default"]]
+        key = ("interp", bool(chained), False) if interp else ("grid", bool(chained), bool(binned))
+        try:
+            return info["products"][key]
+        except KeyError:
+            what = "nonlinear_Plk_interpolator" if interp else "nonlinear_Plk_grid"
+            raise LoggedError(f"{what} (chained={bool(chained)}, binned={bool(binned)}) of tracer {tracer} not computed, please check if "
+                              "you have specified it in requirements")
+
+    def product_info(self, tracer, chained=None, binned=None, interp=False):
+        return self._product(tracer, chained, binned, interp)
 
     # ---- per batch (theory.py:557-609) ----
-    def calculate(self, cosmo: dict):
-        """cosmo[tracer] = dict(pkh=(B, 200) on kh = logspace(-5, 0, 200), f=, DA=, H= (B,) [, rdrag, h])."""
-        self._state, self._derive_inputs, self._derived = {}, {}, None
+    def calculate(self, cosmo: dict, reset=True):
+        """cosmo[tracer] = dict(pkh=(B, 200) on kh = logspace(-5, 0, 200), f=, DA=, H= (B,) [, rdrag, h]), or a
+        boltzmann.BoltzmannExtractor.  reset=False keeps the state of the tracers not named in `cosmo` (the Cobaya
+        components evaluate one tracer per call)."""
+        if reset or not hasattr(self, "_derive_inputs"):
+            self._state, self._derive_inputs = {}, {}
+        self._derived = None
         import os
 
         import torch
@@ -225,6 +347,8 @@ class EFTLSS:
             fork = torch.cuda.Event()
             fork.record(main)
         for name, dp in self.plans.items():
+          if name not in cosmo:
+              continue
           with torch.cuda.stream(self._streams[name]) if concurrent else _nullcontext():
             if concurrent:
                 self._streams[name].wait_event(fork)
@@ -269,13 +393,12 @@ class EFTLSS:
         else:
             self._derived[prefix + "alperp"] = self._derived[prefix + "alpara"] = -1
         self._derived[prefix + "fz"] = np.asarray(_host(c["f"]), float)
-        if c.get("fsigma8_z") is not None:
-            self._derived[prefix + "fsigma8_z"] = np.asarray(_host(c["fsigma8_z"]), float)
+        self._derived[prefix + "fsigma8_z"] = np.asarray(_host(c["fsigma8_z"]), float) if c.get("fsigma8_z") is not None else -1
 
-    def get_bird_component(self, tracer, params, chained=False, binned=True):
+    def get_bird_component(self, tracer, params, chained=None, binned=None):
         """(ls, k, BirdComponent) - theory.py:265-266, :844-847"""
-        info = self.info[tracer]
-        return info["ls"], info["kout"], self.bases[tracer].reduce_Plk(self._view(tracer), params)
+        prod = self._product(tracer, chained, binned)
+        return prod["ls"], prod["kout"], self.bases[tracer].reduce_Plk(self._view(tracer, prod), params)
 
     def get_eft_params_values_dict(self, tracer, params):
         """the tracer's EFT parameters, absent ones as 0.0 (theory.py:262-263, :839-843)"""
@@ -284,51 +407,62 @@ class EFTLSS:
         return {n: params.get(n, 0.0) for n in names}
 
     def get_snapshots(self, tracer):
-        raise LoggedError("snapshots are taken on the stage-by-stage path (pybird.Bird.create_snapshot); the fused "
-                          "batched pipeline keeps no intermediate term arrays")
-
-    def get_nonlinear_Plk_terms(self, tracer, chained=False, binned=True):
-        return self._state[tracer]
-
-    def get_nonlinear_Plk_grid(self, tracer, params, chained=False, binned=True):
-        """(ls, k, Plk (B, No, nk)) - theory.py:244-252 + EFTLeaf reduction (theory.py:846-860)."""
-        bird = self._view(tracer)
-        comp = self.bases[tracer].reduce_Plk(bird, params)
-        info = self.info[tracer]
-        plk = comp.sum()
-        if info["interp_nk"] is not None:  # interpolated products: the PlkInterpolator rows
-            plk = plk[..., : info["interp_nk"]]
-        return info["ls"], info["kout"], plk
-
-    def get_nonlinear_Plk_gaussian_grid(self, tracer, params, chained=False, binned=True):
-        bird = self._view(tracer)
-        info = self.info[tracer]
-        table = self.bases[tracer].reduce_Plk_gaussian_table(bird, params)
-        if info["interp_nk"] is not None:  # the rows interpolated without the inserted origin
-            table = {name: v[..., info["interp_nk"]:] for name, v in table.items()}
-        return info["ls"], info["kout"], table
-
-    def get_nonlinear_Plk_interpolator(self, tracer, params, chained=False):
-        """theory.py:254-258: a `PlkInterpolator` over the tracer's un-binned grid (request `nonlinear_Plk_grid` with
-        `binned: False`).  A tracer whose plan was built for fixed evaluation points (`nonlinear_Plk_interpolator`
-        requirement with `kout`) already holds the interpolated values: use `get_nonlinear_Plk_grid` there."""
-        info = self.info[tracer]
-        if info["interp_nk"] is not None or self.requirements[tracer]["binned"]:
-            raise LoggedError("get_nonlinear_Plk_interpolator needs the un-binned grid of the tracer")
-        ls, k, plk = self.get_nonlinear_Plk_grid(tracer, params, chained=chained, binned=False)
-        return PlkInterpolator(ls[: plk.shape[-2]], k, plk)
-
-    def _view(self, tracer):
+        """theory.py:260-261: {name: BirdSnapshot-like view} of what the plugins were configured to keep (`snapshot: True` in
+        the IRresum / APeffect / window / fiber blocks; request `snapshots` in must_provide).  "IRresum" and "APeffect" are the
+        term arrays the fused pipeline left in its workspace (eftb_workspace_terms), "window" and "fiber" are extra row blocks
+        of the projection."""
         from .transformer import PlainBird
 
-        bm, f_bm = self._state[tracer]
         info = self.info[tracer]
-        nl_out = len(info["ls"])
-        T = bm.reshape(nl_out, info["nk"], info["nterm"], bm.shape[-1])
-        co = self.commons[tracer]
-        view = PlainBird(None, co, T, np.asarray(info["picc"]).reshape(nl_out, info["nk"]), self.B, False, f_bm)
+        if not self.requirements.get(tracer, {}).get("snapshots"):
+            raise LoggedError("snapshots not computed, please check if you have specified it in requirements")
+        co, dp = self.commons[tracer], self.plans[tracer]
+        bm, f_bm = self._state[tracer]
+        out = {}
+        for name, (kind, what) in info["snapshots"].items():
+            if kind == "stage":
+                T = dp.stage_terms(self.B, what)
+                snap = PlainBird(None, co, T, np.zeros((co.Nl, co.Nk)), self.B, False, f_bm)
+            else:
+                snap = self._view(tracer, info["products"][what])
+            snap.k, snap.ls = co.k.copy(), [2 * i for i in range(co.Nl)]
+            out[name] = snap
+        return out
+
+    def get_nonlinear_Plk_terms(self, tracer, chained=None, binned=None, interp=False):
+        """(batch-minor terms (rows, nterm, Bp) of the product, growth rate (Bp,)) - what the likelihood kernels read"""
+        prod = self._product(tracer, chained, binned, interp)
+        bm, f_bm = self._state[tracer]
+        return bm[prod["row0"] : prod["row1"]], f_bm
+
+    def get_nonlinear_Plk_grid(self, tracer, params, chained=None, binned=None, interp=False):
+        """(ls, k, Plk (B, No, nk)) - theory.py:244-252 + EFTLeaf reduction (theory.py:846-860)."""
+        prod = self._product(tracer, chained, binned, interp)
+        plk = self.bases[tracer].reduce_Plk(self._view(tracer, prod), params).sum()
+        if prod["interp_nk"] is not None:  # interpolated products: the PlkInterpolator rows
+            plk = plk[..., : prod["interp_nk"]]
+        return prod["ls"], prod["kout"], plk[..., : len(prod["ls"]), :]
+
+    def get_nonlinear_Plk_gaussian_grid(self, tracer, params, chained=None, binned=None, interp=False):
+        prod = self._product(tracer, chained, binned, interp)
+        table = self.bases[tracer].reduce_Plk_gaussian_table(self._view(tracer, prod), params)
+        if prod["interp_nk"] is not None:  # the rows interpolated without the inserted origin
+            table = {name: v[..., prod["interp_nk"]:] for name, v in table.items()}
+        return prod["ls"], prod["kout"], {name: v[..., : len(prod["ls"]), :] for name, v in table.items()}
+
+    def get_nonlinear_Plk_interpolator(self, tracer, params, chained=False):
+        """theory.py:254-258, :862-871: a `PlkInterpolator` over the tracer's un-binned grid product"""
+        ls, k, plk = self.get_nonlinear_Plk_grid(tracer, params, chained=chained, binned=False)
+        return PlkInterpolator(ls, k, plk)
+
+    def _view(self, tracer, prod=None):
+        from .transformer import PlainBird
+
+        prod = prod or self._product(tracer)
+        bm, f_bm = self._state[tracer]
+        T = bm[prod["row0"] : prod["row1"]].reshape(prod["nl_out"], prod["nk"], prod["nterm"], bm.shape[-1])
         # the reduction honours co.No: chained products expose one multipole fewer (theory.py:599-602)
-        return view
+        return PlainBird(None, self.commons[tracer], T, np.asarray(prod["picc"]).reshape(prod["nl_out"], prod["nk"]), self.B, False, f_bm)
 
 
 class PlkInterpolator:

@@ -172,6 +172,13 @@ int eftb_eval_terms(const eftb_plan*, int B, const double* plin, const double* f
                     const double* H, double* terms_bm, double* terms_pm, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* Intermediate term arrays of the LAST eftb_eval_terms call that used `workspace` (the reference's Bird snapshots,
+ * pybird.py:726-735, taken by Resum / APeffect with snapshot=True, :1463-1464, :1620-1621): stage 0 = after the IR
+ * resummation (after setPsCfl when the plan has none), stage 1 = after the AP stage.  terms_bm: [Nl][Nk][nterm][Bp].
+ * Nothing is recomputed: the fused pipeline leaves both in its workspace. */
+int eftb_workspace_terms(const eftb_plan*, int B, const void* workspace, size_t workspace_bytes, int stage,
+                         double* terms_bm, void* stream);
+
 /* ---- standalone fixed operators -------------------------------------------------------------------
  * A single stage of the projection chain applied on its own (Window.integrWindow window.py:371-387,
  * IntegralConstraint.integrWindow icc.py:471-484, Binning.integrBinning binning.py:131-144,
