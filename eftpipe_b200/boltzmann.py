@@ -147,6 +147,70 @@ class LinearPowerFile(BoltzmannExtractor):
         return 1
 
 
+class EisensteinHu(BoltzmannExtractor):
+    """A batched, on-device producer of the pipeline's inputs: the Eisenstein & Hu (1998) linear power of
+    flat LCDM at the tracer's redshift, sigma8-normalised, with the matching f, DA, H - `eftb_eh_power`, one CTA per point.
+    It stands where CLASS / CAMB stand in the reference (neither exists in this image) and is the model every synthetic
+    input here comes from (synthetic.linear_power), so it is checked against that host code.
+
+    Sampled parameters (names configurable through `params`): Omega_m, h, sigma8, scalars or (B,) arrays, read from the
+    provider like the reference's extractors read theirs (boltzmann.py:289-305).  Everything it returns is a CUDA tensor:
+    P_lin never crosses PCIe; per point the host hands over three numbers."""
+
+    def __init__(self, params=("omegam", "h", "sigma8"), omega_b=0.02214, ns=0.9611, Tcmb=2.7255, rdrag=None, prefix="", ngl=96,
+                 nsig=2000):
+        self.names = [prefix + p for p in params]
+        self.omega_b, self.ns, self.Tcmb, self._rdrag, self.ngl, self.nsig = omega_b, ns, Tcmb, rdrag, ngl, nsig
+        self.provider, self._out = None, None
+
+    def get_requirements(self):
+        return {n: None for n in self.names}
+
+    def _param(self, name):
+        p = self.provider
+        return p.get_param(name) if hasattr(p, "get_param") else p[name]
+
+    def calculate(self, **params_values_dict):
+        import ctypes as C
+
+        from . import _lib
+
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        vals = [params_values_dict[n] if n in params_values_dict else self._param(n) for n in self.names]
+        cols = [v.to("cuda", torch.float64).reshape(-1) if isinstance(v, torch.Tensor) else
+                torch.as_tensor(np.atleast_1d(np.asarray(v, float)), device="cuda") for v in vals]
+        B = max(c.numel() for c in cols)
+        theta = torch.stack([c.expand(B) for c in cols], dim=1).contiguous()
+        if getattr(self, "_consts", None) is None:
+            u, w = np.polynomial.legendre.leggauss(self.ngl)
+            self._consts = tuple(torch.as_tensor(a, device="cuda") for a in (KH, 0.5 * (u + 1.0), 0.5 * w))
+        kh, gu, gw = self._consts
+        pkh = torch.empty((B, kh.numel()), dtype=torch.float64, device="cuda")
+        f, DA, H = (torch.empty(B, dtype=torch.float64, device="cuda") for _ in range(3))
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(lib.eftb_eh_power(B, p(theta), float(self.zeff), float(self.omega_b), float(self.ns), float(self.Tcmb), p(kh),
+                                     kh.numel(), p(gu), p(gw), self.ngl, self.nsig, p(pkh), p(f), p(DA), p(H),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "eftb_eh_power")
+        self._out = dict(pkh=pkh, f=f, DA=DA, H=H, h=theta[:, 1].contiguous())
+        if self._rdrag is not None:
+            self._out["rdrag"] = torch.full((B,), float(self._rdrag), dtype=torch.float64, device="cuda")
+
+    def Pkh(self, kh):
+        if not np.array_equal(np.asarray(kh, float), KH):
+            raise ValueError("EisensteinHu serves kh = logspace(-5, 0, 200) (theory.py:562)")
+        return self._out["pkh"]
+
+    f = lambda self: self._out["f"]
+    DA = lambda self: self._out["DA"]
+    H = lambda self: self._out["H"]
+    h = lambda self: self._out["h"]
+    rdrag = lambda self: self._out.get("rdrag")
+
+    def cosmo(self, kh=KH):
+        return dict(self._out)
+
+
 def find_boltzmann_extractor(name, kwargs=None):
     """boltzmann.py:351-363; the Cobaya-backed CLASS / CAMB / Matryoshka extractors are not available here"""
     if not isinstance(name, str):

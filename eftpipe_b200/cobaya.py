@@ -222,14 +222,20 @@ class EFTLeafKernel(HelperTheory, _LeafShared):
         if self.required_power_spectrum():
             boltzmann.calculate(**params_values_dict)
             kh = np.logspace(-5, 0, 200)  # theory.py:562
-            pkh = np.atleast_2d(np.asarray(_np_or_tensor(boltzmann.Pkh(kh))))
-            B = pkh.shape[0]
-            vec = lambda v: None if v is None else np.broadcast_to(np.asarray(_np_or_tensor(v), float).reshape(-1), (B,)).copy()
-            cosmo = dict(pkh=pkh, f=vec(boltzmann.f()), DA=vec(boltzmann.DA()), H=vec(boltzmann.H()), rdrag=vec(boltzmann.rdrag()),
-                         h=vec(boltzmann.h()))
+            pkh = boltzmann.Pkh(kh)
+            if hasattr(pkh, "detach"):  # a device producer (boltzmann.EisensteinHu): tensors go straight to the pipeline
+                B = pkh.shape[0]
+                cosmo = {k: v for k, v in dict(pkh=pkh, f=boltzmann.f(), DA=boltzmann.DA(), H=boltzmann.H(), rdrag=boltzmann.rdrag(),
+                                               h=boltzmann.h()).items() if v is not None}
+            else:
+                pkh = np.atleast_2d(np.asarray(pkh, float))
+                B = pkh.shape[0]
+                vec = lambda v: None if v is None else np.broadcast_to(np.asarray(_np_or_tensor(v), float).reshape(-1), (B,)).copy()
+                cosmo = dict(pkh=pkh, f=vec(boltzmann.f()), DA=vec(boltzmann.DA()), H=vec(boltzmann.H()), rdrag=vec(boltzmann.rdrag()),
+                             h=vec(boltzmann.h()))
             fs8 = boltzmann.fsigma8_z()
             if not (np.isscalar(fs8) and fs8 == -1):
-                cosmo["fsigma8_z"] = vec(fs8)
+                cosmo["fsigma8_z"] = fs8
             core.calculate({self.tracer: cosmo}, reset=False)
             self._epoch += 1
             state[self.product_name()] = {"tracer": self.tracer, "epoch": self._epoch, "B": B}

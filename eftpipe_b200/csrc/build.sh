@@ -6,7 +6,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v"
 mkdir -p build
 pids=()
-SRCS="api gemm layout antidiag group resum ap like"
+SRCS="api gemm layout antidiag group resum ap like producer"
 for f in $SRCS; do
   $NVCC $FLAGS -c $f.cu -o build/$f.o > build/$f.log 2>&1 &
   pids+=($!)

@@ -188,6 +188,17 @@ int eftb_operator_create(int M, int K, const double* host_matrix, eftb_operator*
 void eftb_operator_destroy(eftb_operator*);
 int eftb_operator_apply(const eftb_operator*, const double* X, double* C, int N, void* stream);
 
+/* ---- input side (boltzmann.py:22-101 BoltzmannExtractor: Pkh, f, DA, H per evaluation) ------------------------------
+ * A batched producer of the pipeline's inputs on the device, standing where CLASS / CAMB stand in the reference: the
+ * Eisenstein & Hu (1998) with-wiggles linear power spectrum of flat LCDM, sigma8-normalised, at redshift z, and the
+ * matching growth rate f, angular distance DA (in c / H0) and H / H0 - the same model as eftpipe_b200/synthetic.py.
+ * theta: [B][3] = (Omega_m, h, sigma8) point-major; kh: [nk] wavenumbers in h / Mpc; gl_u / gl_w: Gauss-Legendre nodes and
+ * weights on [0, 1] (ngl of them) for the growth and distance integrals; nsig: nodes of the sigma8 quadrature on
+ * logspace(-4, 2).  Outputs: pkh [B][nk] (point-major, what eftb_eval_terms takes), f, DA, H [B]. */
+int eftb_eh_power(int B, const double* theta, double z, double omega_b, double ns, double Tcmb, const double* kh, int nk,
+                  const double* gl_u, const double* gl_w, int ngl, int nsig, double* pkh, double* f, double* DA, double* H,
+                  void* stream);
+
 /* ---- likelihood (parambasis.py:42-136,:249-316; likelihood.py:483-594; marginal.py:79-196) ------- */
 typedef struct {
   int32_t ntracer, ndata, ngauss, npar, jeffreys;
