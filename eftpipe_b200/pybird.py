@@ -74,29 +74,34 @@ class Common:
         self.nterm = g.nterm
         # stage registry -> one device plan per Common (built lazily, rebuilt when a stage is added)
         self._stages = {}
-        self._device = None
+        self._devices = {}  # FFTLog taper of the loop coefficients -> (version, DevicePlan)
         self._version = 0
 
     def _register(self, kind, obj):
         self._stages[kind] = obj
         self._version += 1
 
-    def device_plan(self):
+    def device_plan(self, window=None):
+        """the device plan of the stages registered on this Common; `window`: the FFTLog taper `NonLinear.PsCf(bird, window=)`
+        was called with (pybird.py:1143; default: the NonLinear object's own) - one plan per distinct value, since the taper
+        is part of the front operator"""
         from .engine import DevicePlan
 
-        if self._device is None or self._device[0] != self._version:
-            nl = self._stages.get("nonlinear")
-            if nl is None:
-                raise RuntimeError("a NonLinear object must be constructed for this Common before evaluation")
+        nl = self._stages.get("nonlinear")
+        if nl is None:
+            raise RuntimeError("a NonLinear object must be constructed for this Common before evaluation")
+        window = nl.window if window is None else window
+        dev = self._devices.get(window)
+        if dev is None or dev[0] != self._version:
             rs, ap = self._stages.get("resum"), self._stages.get("ap")
             host = P.build_tracer_plan(
-                Nl=self.Nl, kmax=self.kmax, NFFT=nl.NFFT, with_NNLO=self.with_NNLO, kin=nl.kin, window=nl.window,
+                Nl=self.Nl, kmax=self.kmax, NFFT=nl.NFFT, with_NNLO=self.with_NNLO, kin=nl.kin, window=window,
                 with_resum=rs is not None, resum_NFFT=rs.NFFT if rs is not None else 192,
                 ap=None if ap is None else dict(DA=ap.DA, H=ap.H, nbinsmu=ap._nbinsmu, accboost=ap._accboost, APst=ap.APst),
                 loop_cache=nl._loop_cache, optiresum=self.optiresum, ircutoff=self.IRcutoff, kIR=self.kIR,
                 lambda_ir=rs.LambdaIR if rs is not None else P.LAMBDA_IR)
-            self._device = (self._version, DevicePlan(host))
-        return self._device[1]
+            dev = self._devices[window] = (self._version, DevicePlan(host))
+        return dev[1]
 
 
 common = Common()
@@ -117,10 +122,24 @@ class _TermsView:
         v = self._T[:, :, a:b, : self.B].permute(3, 0, 2, 1)
         return v[0] if self._squeeze else v
 
-    P11l = property(lambda self: self._terms(0, 3))
-    Pctl = property(lambda self: self._terms(3, 9))
-    Ploopl = property(lambda self: self._terms(9, 21))
-    Pstl = property(lambda self: self._terms(21, 24))
+    def _set_terms(self, a, b, value):
+        """the reference's stages rebind (`bird.P11l = ...`, pybird.py:1613) or update in place (`bird.Ploopl += ...`,
+        :1445) the term arrays: the getters hand out views of the device array, so in-place updates already land in it;
+        rebinding copies the new values in.  `value`: (B, Nl, n, nk) [or (Nl, n, nk) for an unbatched bird], tensor or array."""
+        import torch
+
+        if self._T is None:
+            raise AttributeError("term arrays are not available before setPsCfl()")
+        v = value if isinstance(value, torch.Tensor) else torch.as_tensor(np.asarray(value, float))
+        v = v.to(self._T.device, self._T.dtype)
+        if self._squeeze:
+            v = v[None]
+        self._T[:, :, a:b, : self.B] = v.permute(1, 3, 2, 0)
+
+    P11l = property(lambda self: self._terms(0, 3), lambda self, v: self._set_terms(0, 3, v))
+    Pctl = property(lambda self: self._terms(3, 9), lambda self, v: self._set_terms(3, 9, v))
+    Ploopl = property(lambda self: self._terms(9, 21), lambda self, v: self._set_terms(9, 21, v))
+    Pstl = property(lambda self: self._terms(21, 24), lambda self, v: self._set_terms(21, 24, v))
 
     @property
     def PctNNLOl(self):
@@ -130,6 +149,12 @@ class _TermsView:
             return z[0] if self._squeeze else z
         return self._terms(24, 27)
 
+    @PctNNLOl.setter
+    def PctNNLOl(self, value):
+        if not self.co.with_NNLO:
+            raise AttributeError("this bird carries no NNLO counterterm rows (co.with_NNLO is False)")
+        self._set_terms(24, 27, value)
+
     @property
     def Picc(self):
         import torch
@@ -137,6 +162,16 @@ class _TermsView:
         p = self._picc if self._picc is not None else np.zeros((self._T.shape[0], self._T.shape[1]))
         t = torch.as_tensor(p, device="cuda")
         return t if self._squeeze else t.expand(self.B, *t.shape)
+
+    @Picc.setter
+    def Picc(self, value):
+        """`bird.Picc = bird.Picc - x` (window.py:405): Picc is one constant array per plan here (cosmology independent)"""
+        v = value.detach().cpu().numpy() if hasattr(value, "detach") else np.asarray(value, float)
+        if v.ndim == 3:
+            if not np.allclose(v, v[:1]):
+                raise ValueError("Picc must not depend on the cosmology")
+            v = v[0]
+        self._picc = np.array(v, float)
 
     def add_Picc(self, delta):
         base = self._picc if self._picc is not None else np.zeros((self._T.shape[0], self._T.shape[1]))
@@ -177,6 +212,7 @@ class Bird(_TermsView):
         self.DA, self.H, self.z, self.rdrag, self.h = DA, H, z, rdrag, h
         self._F = self._D = self._P22 = self._Cs = self._Cr = self._T = None
         self._bm = {}
+        self._window = None  # FFTLog taper chosen by NonLinear.PsCf(bird, window=) (None: the NonLinear object's)
         self.snapshots = {}
 
     # ---- lazily produced device state ----
@@ -185,16 +221,19 @@ class Bird(_TermsView):
             src = getattr(self, "_" + name)
             if src is None:
                 raise ValueError(f"Bird was constructed without {name}")
-            self._bm[name] = self.co.device_plan().to_batch_minor(src)[0]
+            self._bm[name] = self._plan().to_batch_minor(src)[0]
         return self._bm[name]
+
+    def _plan(self):
+        return self.co.device_plan(self._window)
 
     def _front(self):
         if self._F is None:
-            self._F = self.co.device_plan().front(self.Pin)
+            self._F = self._plan().front(self.Pin)
         return self._F
 
     def _rows(self, name):
-        a, n = self.co.device_plan().host.front.rows[name]
+        a, n = self._plan().host.front.rows[name]
         return self._front()[a : a + n, : self.B]
 
     def _out(self, v):
@@ -240,7 +279,7 @@ class Bird(_TermsView):
         """Legendre weighting, f-grouping, stochastic basis, shot-noise subtraction (pybird.py:737-866)."""
         if self._P22 is None:
             raise RuntimeError("NonLinear.PsCf(bird) must run before setPsCfl()")
-        dp = self.co.device_plan()
+        dp = self._plan()
         self._T, self._Cr = dp.group(self._front(), self._P22, self._Cs, self._bm_scalar("f"), self.B)
 
     def create_snapshot(self, name):
@@ -282,10 +321,13 @@ class NonLinear:
         co._register("nonlinear", self)
 
     def PsCf(self, bird: Bird, window=None):
-        """pybird.py:1143-1171.  The taper is fixed at construction (`window=` keyword, default 0.2)."""
-        if window is not None and window != self.window:
-            raise ValueError("the FFTLog taper is a plan constant here: pass window= to NonLinear(...)")
-        dp = bird.co.device_plan()
+        """pybird.py:1143-1171.  `window`: the FFTLog taper of this call (reference default 0.2; here the default is the value
+        given to NonLinear(window=...)).  The taper is part of the front operator: every distinct value gets its own device
+        plan, built the first time it is used."""
+        window = self.window if window is None else window
+        if window != (bird._window if bird._window is not None else self.window):
+            bird._window, bird._F, bird._bm = window, None, {}
+        dp = bird._plan()
         F = bird._front()
         bird._D = dp.antidiag(F, bird.B)
         # IRcutoff "loop"/"resum": coef_cf differs from coef_pk (pybird.py:1151-1160) -> a second anti-diagonal pass
@@ -307,7 +349,7 @@ class Resum:
     def Ps(self, bird: Bird, window=None):
         if bird._T is None:
             raise RuntimeError("bird.setPsCfl() must run before Resum.Ps")
-        dp = bird.co.device_plan()
+        dp = bird._plan()
         dp.resum(bird._front(), bird._Cr, bird._bm_scalar("f"), bird._T, bird.B)
         if self.snapshot:
             bird.create_snapshot("IRresum")
@@ -346,7 +388,7 @@ class APeffect:
         return bird._DA / self.DA * ratio, self.H / bird._H * ratio  # pybird.py:1576-1578
 
     def AP(self, bird: Bird, q=None):
-        dp = bird.co.device_plan()
+        dp = bird._plan()
         if q is not None:  # pybird.py:1603-1606: explicit (qperp, qpar), scalars or one pair per cosmology
             t = bird.torch
             dev = lambda x: (x if isinstance(x, t.Tensor) else t.as_tensor(np.asarray(x, float))).to("cuda", t.float64)

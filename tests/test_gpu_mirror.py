@@ -534,3 +534,36 @@ def test_cobaya_yaml_drop_in(dr16_setup, dr16, tmp_path):
     th2, likes2 = cobaya_info.load_info(str(tmp_path / "run.yaml"))
     th2.calculate(S["cosmo"])
     np.testing.assert_allclose(_np(likes2["LEX_NGC"].logp(S["params"])), want, rtol=1e-12)
+
+
+def test_per_call_taper_and_mutable_term_arrays(golden2):
+    """pybird.py:1143 `PsCf(bird, window=0.2)` takes the FFTLog taper per call; the stages of the reference rebind and
+    update the Bird's term arrays in place (pybird.py:1445, :1613; SURVEY.md 8b ownership)."""
+    import pybird_oracle as orc
+    from eftpipe_b200 import pybird
+
+    g = golden2
+    co = pybird.Common(Nl=3)
+    nl, rs = pybird.NonLinear(load=False, save=False, co=co), pybird.Resum(co=co)
+    oco = orc.Common(Nl=3)
+    onl = orc.NonLinear(oco)
+    for w in (0.3, 0.2):  # a non-default taper first, then back to the default on a fresh bird
+        bird = pybird.Bird(g["kin"], g["plin"], g["f"], co=co)
+        nl.PsCf(bird, window=w)
+        ob = orc.Bird(oco, g["kin"], g["plin"][1], g["f"][1])
+        onl.PsCf(ob, window=w)
+        assert rowmax_rel(_np(bird.P22)[1], ob.P22) <= TOL and rowmax_rel(_np(bird.C13)[1], ob.C13) <= TOL
+    assert rowmax_rel(_np(bird.P22), g["P22"]) <= TOL  # the last one is the golden's default taper
+    bird.setPsCfl()
+    rs.Ps(bird)
+    before = _np(bird.Ploopl).copy()
+    bird.Ploopl = bird.Ploopl * 2.0             # rebinding (a new array)
+    assert np.array_equal(_np(bird.Ploopl), 2.0 * before)
+    bird.Ploopl += 1.0                          # in-place update through the view
+    assert np.array_equal(_np(bird.Ploopl), 2.0 * before + 1.0)
+    bird.P11l = np.zeros((3, 3, 3, 50))         # numpy input, (B, Nl, 3, Nk)
+    assert not _np(bird.P11l).any() and np.array_equal(_np(bird.Pctl), _np(bird.Pctl))
+    bird.Picc = bird.Picc - 1.5                 # window.py:405 style
+    assert np.allclose(_np(bird.Picc), -1.5)
+    with pytest.raises(AttributeError):
+        bird.PctNNLOl = np.zeros((3, 3, 3, 50))
