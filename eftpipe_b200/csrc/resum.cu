@@ -613,13 +613,11 @@ int run(ResumArgs a, cudaStream_t s, int phase) {
                                             (size_t)a.nslots * NL * a.KPAD + (size_t)NL * NL * NIR * RS_SLOTS);
   if (smem_lin > smem) smem = smem_lin;
   if (smem > 200 * 1024) { eftb_set_error("resum: %zu bytes of shared memory needed", smem); return EFTB_ERR_ARG; }
-  static DeviceSmem conf3, conf4, conf5;
+  static DeviceSmem conf3, conf4;
   static const int minb = getenv("EFTB_RESUM_MINB") ? atoi(getenv("EFTB_RESUM_MINB")) : 4;  // tuning knob: CTAs per SM
   EFTB_SET_SMEM(conf3, (resum_kernel<NL, NIR, NNLO, 3>), smem);
   EFTB_SET_SMEM(conf4, (resum_kernel<NL, NIR, NNLO, 4>), smem);
-  EFTB_SET_SMEM(conf5, (resum_kernel<NL, NIR, NNLO, 5>), smem);
-  if (minb == 5) resum_kernel<NL, NIR, NNLO, 5><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
-  else if (minb == 3) resum_kernel<NL, NIR, NNLO, 3><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
+  if (minb == 3) resum_kernel<NL, NIR, NNLO, 3><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
   else resum_kernel<NL, NIR, NNLO, 4><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;

@@ -2,6 +2,8 @@
 
   python tools/ncu_summary.py launches gpurun_out/launches_r1.csv profiles/r1_launches.txt
   python tools/ncu_summary.py full gpurun_out/prof_r1.ncu-rep profiles/r1_top_kernels.txt
+  python tools/ncu_summary.py dram profiles/r2_ncu_dram.json BATCH rep1.ncu-rep [rep2.ncu-rep ...]
+  python tools/ncu_summary.py sass eftpipe_b200/libeftb200.so profiles/r2_sass_summary.txt
 """
 import collections
 import csv
@@ -75,5 +77,83 @@ def full(src, dst, max_ids=6):
                 out.write(f"   RULE {r[ix['Rule Name']]}: {r[ix['Rule Description']][:260]}\n")
 
 
+STAGE_OF = {"resum_kernel": "resum", "antidiag_kernel": "antidiag", "ap_geom_kernel": "ap", "ap_apply_kernel": "ap",
+            "regroup_kernel": "spectral", "like_gram_kernel": "likelihood", "like_vectors_kernel": "likelihood",
+            "group_kernel": "group", "front_tails_kernel": "front"}
+
+
+def dram(dst, batch, *reps):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel of every stage, from `ncu --set full`
+    captures: what bench.py reports as `roofline.traffic` (scaled to its batch)"""
+    import json
+    import os
+
+    stages, kernels = {}, {}
+    for src in reps:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rr = list(csv.reader(raw.splitlines()))
+        ix = {h: i for i, h in enumerate(rr[0])}
+        unit = lambda m: {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[rr[1][ix[m]]]
+        for r in rr[2:]:
+            name = r[ix["Kernel Name"]].split("(")[0].split("::")[-1].split("<")[0]
+            byt = float(r[ix["dram__bytes_read.sum"]]) * unit("dram__bytes_read.sum") + \
+                float(r[ix["dram__bytes_write.sum"]]) * unit("dram__bytes_write.sum")
+            ent = dict(kernel=name, dram_bytes_per_launch=byt, batch=int(batch), capture=os.path.basename(src),
+                       duration_us=float(r[ix["gpu__time_duration.sum"]]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}[rr[1][ix["gpu__time_duration.sum"]]],
+                       fp64_pipe_pct=float(r[ix["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]]),
+                       dmma_pipe_pct=float(r[ix["sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active"]])
+                       if "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active" in ix else None,
+                       registers=int(float(r[ix["launch__registers_per_thread"]])))
+            kernels.setdefault(name, ent)
+            st = STAGE_OF.get(name)
+            if st and (st not in stages or byt > stages[st]["dram_bytes_per_launch"]):
+                stages[st] = ent
+    with open(dst, "w") as out:
+        json.dump(dict(capture="ncu --set full --clock-control none, " + ", ".join(os.path.basename(r) for r in reps), stages=stages,
+                       kernels=kernels), out, indent=1)
+
+
+def sass(lib, dst):
+    """per-kernel opcode counts of the built library: the evidence for DMMA (FP64 tensor core), UBLKCP (TMA bulk copy),
+    UTMALDG (TMA tensor map), LDGSTS (cp.async), SYNCS (mbarrier)"""
+    import re
+
+    txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    want = ["DMMA", "DFMA", "DMUL", "DADD", "UBLKCP", "UTMALDG", "LDGSTS", "SYNCS", "LDS", "STS", "LDG", "STG", "SHFL", "RED", "ATOMG", "MUFU"]
+    cur, counts, order = None, {}, []
+    for line in txt.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            dem = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+            mm = re.search(r"(?:\(anonymous namespace\)::)?([A-Za-z_][A-Za-z_0-9]*(?:<[^>]*>)?)\(", dem.replace("void ", ""))
+            cur = mm.group(1) if mm else dem[:90]
+            while cur in counts:
+                cur += "'"
+            counts[cur] = collections.Counter()
+            order.append(cur)
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and cur:
+            counts[cur][m.group(1)] += 1
+            counts[cur]["_total"] += 1
+    with open(dst, "w") as out:
+        out.write(f"# static SASS opcode counts per kernel of {lib} (cuobjdump -sass, sm_100a)\n")
+        out.write("# DMMA = FP64 tensor-core MMA (mma.sync.m8n8k4.f64; tcgen05 has no f64 kind), UBLKCP = TMA bulk copy (cp.async.bulk),\n")
+        out.write("# UTMALDG = TMA tensor-map load, LDGSTS = cp.async, SYNCS = mbarrier\n")
+        out.write(f"{'kernel':52s} {'total':>6} " + " ".join(f"{w:>7}" for w in want) + "\n")
+        tot = collections.Counter()
+        for k in order:
+            c = counts[k]
+            out.write(f"{k:52s} {c['_total']:6d} " + " ".join(f"{c[w]:7d}" for w in want) + "\n")
+            tot.update(c)
+        out.write(f"{'ALL':52s} {tot['_total']:6d} " + " ".join(f"{tot[w]:7d}" for w in want) + "\n")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    mode = sys.argv[1]
+    if mode == "dram":
+        dram(sys.argv[2], sys.argv[3], *sys.argv[4:])
+    elif mode == "sass":
+        sass(sys.argv[2], sys.argv[3])
+    else:
+        {"launches": launches, "full": full}[mode](sys.argv[2], sys.argv[3])
