@@ -54,6 +54,7 @@ class EftbLikeConstants(C.Structure):
         ("picc", c_double_p), ("invcov", c_double_p), ("g_count", c_int32_p), ("g_tracer", c_int32_p),
         ("g_term", c_int32_p), ("g_var", c_int32_p), ("g_coef", c_double_p), ("sigma_inv", c_double_p),
         ("sigma_inv_mu", c_double_p), ("mu_sigma_mu", C.c_double), ("d_row_g", c_int32_p),
+        ("mode", c_int32_p), ("xb_off", c_int32_p), ("xg_off", c_int32_p),
     ]
 
 

@@ -15,6 +15,7 @@ struct eftb_like {
   int32_t h_nout[EFTB_MAX_TRACERS], h_nterm[EFTB_MAX_TRACERS];
   double* scales = nullptr;
   int32_t *d_tracer = nullptr, *d_row = nullptr, *d_row_g = nullptr;
+  int32_t *mode = nullptr, *xb_off = nullptr, *xg_off = nullptr;  // explicit-bias tracers (custom EFT bases)
   int32_t* res_perm = nullptr;  // rows d * (ngauss + 1) of the vector block: the residual PNG - data of data point d
   double *data = nullptr, *picc = nullptr;
   GemmMatrix invcov;   // C^-1 (two-operand form: A = V, Bm = C^-1 V), used when C^-1 has no Cholesky factor
@@ -35,6 +36,8 @@ struct TracerPtrs {
 struct VecArgs {
   TracerPtrs tp;
   const int32_t *nterm, *par_index, *eastcoast, *d_tracer, *d_row, *d_row_g, *g_count, *g_tracer, *g_term, *g_var;
+  const int32_t *mode, *xb_off, *xg_off;
+  int ntracer;
   const double *scales, *data, *picc, *g_coef, *nuis;
   double* V;  // [ndata][ngauss+1][Bp]
   int Bp, ndata, ngauss;
@@ -48,6 +51,25 @@ __global__ void __launch_bounds__(128) like_vectors_kernel(VecArgs a) {
   const int tr = a.d_tracer[d], nt = a.nterm[tr];
   const double* term = a.tp.terms[tr] + ((size_t)a.d_row[d] * nt) * Bp + b;
   const double* termg = a.tp.terms[tr] + ((size_t)a.d_row_g[d] * nt) * Bp + b;  // rows of the marginalised derivatives
+  if (a.mode && a.mode[tr]) {
+    // a custom basis: the coefficient of every term row comes with the point (probed on the host from the basis' own
+    // reduce_Plk / reduce_Plk_gaussian_table, parambasis.py:139-162)
+    const double* xb = a.nuis + (size_t)a.xb_off[tr] * Bp + b;
+    double png = 0.0;
+    for (int i = 0; i < nt; ++i) png = fma(xb[(size_t)i * Bp], term[(size_t)i * Bp], png);
+    double* out = a.V + ((size_t)d * (a.ngauss + 1)) * Bp + b;
+    out[0] = (png + a.picc[d]) - a.data[d];
+    for (int g = 0; g < a.ngauss; ++g) {
+      const int off = a.xg_off[g * a.ntracer + tr];
+      double v = 0.0;
+      if (off >= 0) {
+        const double* xg = a.nuis + (size_t)off * Bp + b;
+        for (int i = 0; i < nt; ++i) v = fma(xg[(size_t)i * Bp], termg[(size_t)i * Bp], v);
+      }
+      out[(size_t)(1 + g) * Bp] = v;
+    }
+    return;
+  }
   const double f = a.tp.fg[tr][b];
   double par[EFTB_NPAR];
 #pragma unroll
@@ -368,6 +390,7 @@ int fill_vectors(const eftb_like* L, int Bp, const double* const* terms, const d
   }
   a.nterm = L->nterm; a.par_index = L->par_index; a.eastcoast = L->eastcoast; a.d_tracer = L->d_tracer; a.d_row = L->d_row; a.d_row_g = L->d_row_g;
   a.g_count = L->g_count; a.g_tracer = L->g_tracer; a.g_term = L->g_term; a.g_var = L->g_var; a.scales = L->scales;
+  a.mode = L->mode; a.xb_off = L->xb_off; a.xg_off = L->xg_off; a.ntracer = L->cfg.ntracer;
   a.data = L->data; a.picc = L->picc; a.g_coef = L->g_coef; a.nuis = nuis; a.V = V; a.Bp = Bp; a.ndata = L->cfg.ndata;
   a.ngauss = L->cfg.ngauss;
   dim3 grid((Bp + 127) / 128, L->cfg.ndata);
@@ -415,6 +438,12 @@ int eftb_like_create(const eftb_like_config* cfg, const eftb_like_constants* h, 
   rc |= upload(&L->d_tracer, h->d_tracer, nd);
   rc |= upload(&L->d_row, h->d_row, nd);
   rc |= upload(&L->d_row_g, h->d_row_g ? h->d_row_g : h->d_row, nd);
+  if (h->mode) {
+    if (!h->xb_off || (ng && !h->xg_off)) { eftb_set_error("eftb_like_create: mode given without xb_off / xg_off"); eftb_like_destroy(L); return EFTB_ERR_ARG; }
+    rc |= upload(&L->mode, h->mode, nt);
+    rc |= upload(&L->xb_off, h->xb_off, nt);
+    rc |= upload(&L->xg_off, h->xg_off, (size_t)ng * nt);
+  }
   {
     std::vector<int32_t> perm(nd);
     for (int d = 0; d < nd; ++d) perm[d] = d * (ng + 1);
@@ -461,7 +490,8 @@ int eftb_like_create(const eftb_like_config* cfg, const eftb_like_constants* h, 
 
 void eftb_like_destroy(eftb_like* L) {
   if (!L) return;
-  void* ptrs[] = {L->nout, L->nterm, L->scales, L->par_index, L->eastcoast, L->d_tracer, L->d_row, L->d_row_g, L->res_perm, L->data, L->picc,
+  void* ptrs[] = {L->mode, L->xb_off, L->xg_off,
+                  L->nout, L->nterm, L->scales, L->par_index, L->eastcoast, L->d_tracer, L->d_row, L->d_row_g, L->res_perm, L->data, L->picc,
                   L->g_count, L->g_tracer, L->g_term, L->g_var, L->g_coef, L->sigma_inv, L->sigma_inv_mu};
   for (void* p : ptrs) if (p) cudaFree(p);
   gemm_free(&L->invcov);

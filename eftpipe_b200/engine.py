@@ -384,6 +384,9 @@ class DeviceLikelihood:
         cst.sigma_inv_mu = dp(spec["sigma_inv_mu"] if spec["ngauss"] else np.zeros(ng))
         cst.mu_sigma_mu = float(spec["mu_sigma_mu"])
         cst.d_row_g = ip(spec.get("d_row_g", spec["d_row"]))
+        if spec.get("mode") is not None and np.any(spec["mode"]):  # custom EFT bases: explicit bias columns
+            cst.mode, cst.xb_off = ip(spec["mode"]), ip(spec["xb_off"])
+            cst.xg_off = ip(spec["xg_off"] if spec["ngauss"] else np.zeros(1))
         handle = C.c_void_p()
         _lib.check(self.lib.eftb_like_create(C.byref(cfg), C.byref(cst), C.byref(handle)), "eftb_like_create")
         self.handle, self.cfg = handle, cfg

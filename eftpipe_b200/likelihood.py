@@ -199,7 +199,21 @@ def build_spec(tracers, data, invcov, gaussian=(), sigma_inv=None, mu=None, jeff
     g_term = np.zeros((max(ng, 1), 2, 3), dtype=np.int32)
     g_var = np.zeros((max(ng, 1), 2, 3), dtype=np.int32)
     g_coef = np.zeros((max(ng, 1), 2, 3))
+    mode = np.array([int(getattr(t["basis"], "kernel_mode", "") == "explicit") for t in tracers], dtype=np.int32)
+    xb_off = np.zeros(nt, dtype=np.int32)
+    xg_off = np.full((max(ng, 1), nt), -1, dtype=np.int32)
+    owned = np.zeros(max(ng, 1), dtype=bool)
+    ncol = NPAR * nt  # explicit blocks follow the built-in columns
     for it, t in enumerate(tracers):
+        if mode[it]:  # custom basis: nterm bias columns + nterm columns per Gaussian parameter it knows
+            xb_off[it] = ncol
+            ncol += t["nterm"]
+            for g, name in enumerate(gaussian):
+                if name in t["basis"].gaussian_params():
+                    xg_off[g, it] = ncol
+                    ncol += t["nterm"]
+                    owned[g] = True
+            continue
         desc = t["basis"].gaussian_descriptors(t["co"])
         for name, entries in desc.items():
             if name not in gaussian:
@@ -212,14 +226,16 @@ def build_spec(tracers, data, invcov, gaussian=(), sigma_inv=None, mu=None, jeff
             for q, (term, var, coef) in enumerate(entries):
                 g_term[g, e, q], g_var[g, e, q], g_coef[g, e, q] = term, var, coef
             g_count[g] = e + 1
-    if ng and (g_count[:ng] == 0).any():
-        missing = [n for n, c in zip(gaussian, g_count) if c == 0]
+            owned[g] = True
+    if ng and not owned[:ng].all():
+        missing = [n for n, c in zip(gaussian, owned) if not c]
         raise LoggedError(f"marginalised parameters {missing} do not belong to any tracer")
     sigma_inv = np.zeros((ng, ng)) if sigma_inv is None else np.asarray(sigma_inv, float)
     mu = np.zeros(ng) if mu is None else np.asarray(mu, float)
     scales = np.array([[t["co"].kmA, t["co"].krA, t["co"].ndA, t["co"].kmB, t["co"].krB, t["co"].ndB] for t in tracers])
     return dict(
-        ntracer=nt, ndata=ndata, ngauss=ng, npar=NPAR * nt, jeffreys=bool(jeffreys),
+        ntracer=nt, ndata=ndata, ngauss=ng, npar=ncol, jeffreys=bool(jeffreys), mode=mode, xb_off=xb_off, xg_off=xg_off,
+        gaussian=list(gaussian), tracer_nterm=[t["nterm"] for t in tracers], tracer_co=[t["co"] for t in tracers],
         nout=np.array([t["nout"] for t in tracers], dtype=np.int32),
         nterm=np.array([t["nterm"] for t in tracers], dtype=np.int32), scales=scales,
         par_index=np.arange(NPAR * nt, dtype=np.int32).reshape(nt, NPAR),
@@ -230,10 +246,12 @@ def build_spec(tracers, data, invcov, gaussian=(), sigma_inv=None, mu=None, jeff
     )
 
 
-def pack_nuisance(torch, bases, params, f_list, B, Bp):
-    """(NPAR*ntracer, Bp) batch-minor nuisance array from a parameter dictionary (scalars or (B,) arrays).
-    Parameters missing from `params` are 0, as in the reference (`basis.default()`, parambasis.py:234-236)."""
-    nuis = torch.zeros((NPAR * len(bases), Bp), dtype=torch.float64, device="cuda")
+def pack_nuisance(torch, bases, params, f_list, B, Bp, spec=None):
+    """(npar, Bp) batch-minor nuisance array from a parameter dictionary (scalars or (B,) arrays).
+    Parameters missing from `params` are 0, as in the reference (`basis.default()`, parambasis.py:234-236).
+    `spec` (build_spec): needed when a tracer uses a custom basis (explicit bias columns after the built-in ones)."""
+    npar = NPAR * len(bases) if spec is None else int(spec["npar"])
+    nuis = torch.zeros((npar, Bp), dtype=torch.float64, device="cuda")
     conv = {}
 
     def dev(v):
@@ -247,6 +265,19 @@ def pack_nuisance(torch, bases, params, f_list, B, Bp):
 
     pdev = {k: dev(v) for k, v in params.items()}
     for it, basis in enumerate(bases):
+        if getattr(basis, "kernel_mode", "") == "explicit":
+            if spec is None:
+                raise ValueError("a custom basis needs the likelihood spec to place its columns")
+            bias, table = basis.explicit_columns(params, f_list[it][:B], B, spec["tracer_co"][it], spec["tracer_nterm"][it], spec["gaussian"])
+            put = lambda off, arr: nuis[off : off + arr.shape[1]].__setitem__((slice(None), slice(0, B)), torch.as_tensor(arr.T.copy(), device="cuda"))
+            put(int(spec["xb_off"][it]), bias)
+            for g, name in enumerate(spec["gaussian"]):
+                off = int(spec["xg_off"][g, it])
+                if off >= 0:
+                    put(off, table[name])
+            if Bp > B:
+                nuis[:, B:] = nuis[:, B - 1 : B]
+            continue
         cols = basis.kernel_columns(pdev, f_list[it][:B] if f_list[it] is not None else None)
         for i, v in enumerate(cols):
             if isinstance(v, float):
@@ -257,6 +288,12 @@ def pack_nuisance(torch, bases, params, f_list, B, Bp):
                 if Bp > B:
                     nuis[NPAR * it + i, B:] = v[-1]
     return nuis
+
+
+def _probe_co(co):
+    from types import SimpleNamespace
+
+    return SimpleNamespace(**{k: getattr(co, k) for k in ("kmA", "krA", "ndA", "kmB", "krB", "ndB", "counterform", "with_NNLO")}, No=1)
 
 
 def reduce_on_device(basis, bird, params, want_table=False):
@@ -271,7 +308,17 @@ def reduce_on_device(basis, bird, params, want_table=False):
     No = min(co.No, Nl_out)
     rows = np.arange(No * nk, dtype=np.int32)
     picc = np.zeros(Nl_out * nk) if bird._picc is None else np.asarray(bird._picc, float).reshape(-1)
-    gaussian = [n for n in basis.gaussian_descriptors(co)] if want_table else []
+    explicit = getattr(basis, "kernel_mode", "") == "explicit"
+    if not want_table:
+        gaussian = []
+    elif explicit:  # what the basis' own table holds for this configuration (probed once on a unit bird)
+        from .parambasis import _UnitBird
+
+        probe = basis.inner.reduce_Plk_gaussian_table(_UnitBird(_probe_co(co), 0.5, nterm), {n: 1.0 for n in
+                                                      list(basis.inner.gaussian_params()) + list(basis.inner.non_gaussian_params())})
+        gaussian = list(probe)
+    else:
+        gaussian = [n for n in basis.gaussian_descriptors(co)]
     key = (type(basis).__name__, basis.prefix, tuple(basis.cross_prefix), Nl_out, nk, want_table, id(co))
     cache = bird.__dict__.setdefault("_reduce_cache", {})
     if key not in cache:
@@ -280,7 +327,7 @@ def reduce_on_device(basis, bird, params, want_table=False):
         cache[key] = DeviceLikelihood(spec)
     like = cache[key]
     f_bm = f_batch_minor(bird)
-    nuis = pack_nuisance(torch, [basis], params, [f_bm], bird.B, Bp)
+    nuis = pack_nuisance(torch, [basis], params, [f_bm], bird.B, Bp, spec=like.spec)
     vec = like.vectors(bird.B, [bird._T.contiguous()], [f_bm], nuis)  # (B, ndata, 1+ng)
     total = vec[:, :, 0].reshape(bird.B, No, nk)
     table = {name: vec[:, :, 1 + i].reshape(bird.B, No, nk) for i, name in enumerate(gaussian)}
@@ -445,7 +492,7 @@ class EFTLike(Marginalizable):
             fs.append(f_bm)
         B = th.B
         Bp = terms[0].shape[-1]
-        nuis = pack_nuisance(torch, self.eft_bases, params, fs, B, Bp)
+        nuis = pack_nuisance(torch, self.eft_bases, params, fs, B, Bp, spec=self.spec)
         return B, terms, fs, nuis
 
     def PNG_PG(self, params):

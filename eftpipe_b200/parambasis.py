@@ -239,10 +239,95 @@ def reduce_Plk(bird, bsA, bsB=None, es=(0.0, 0.0, 0.0), cnnloA=(0.0, 0.0), cnnlo
     return reduce_on_device(basis, bird, params)[0]
 
 
+class _UnitBird:
+    """A numpy birdlike (pybird.py:598-608) whose term arrays are unit vectors along a probe axis: what a linear reduction
+    returns for it are its coefficients"""
+
+    def __init__(self, co, f, nterm):
+        self.co, self.f = co, f
+        eye = np.eye(nterm)
+        row = lambda a, b: np.ascontiguousarray(eye[a:b][None])  # (1, n, nterm): multipole axis of length 1
+        self.P11l, self.Pctl, self.Ploopl, self.Pstl = row(0, 3), row(3, 9), row(9, 21), row(21, 24)
+        self.PctNNLOl = row(24, 27) if nterm > 24 else np.zeros((1, 3, nterm))
+        self.Picc = np.zeros((1, nterm))
+
+
+class ProbedBasis:
+    """A reference-style `EFTBasis` (parambasis.py:139-162) given by dotted path - numpy code with `reduce_Plk(bird, params)
+    -> BirdComponent` and `reduce_Plk_gaussian_table(bird, params, requires)` - on the batched device path.
+
+    Both reductions are linear in the term arrays, with coefficients that depend on the point (its parameters and growth
+    rate) only.  Per point, the basis' own code is run once on a unit birdlike; what comes back are the coefficient of every
+    term row in P_l(k) and in every Gaussian-parameter derivative.  These go to the device as explicit bias columns
+    (eftb_like_constants.mode = 1) and the kernels do the arithmetic on the real term arrays.  A basis whose reduction is
+    not linear, or depends on the multipole, is refused when it is first probed."""
+
+    kernel_mode = "explicit"
+
+    def __init__(self, inner):
+        self.inner = inner
+        self.prefix, self.cross_prefix = inner.prefix, list(getattr(inner, "cross_prefix", []) or [])
+
+    def __getattr__(self, name):  # get_name, counterform, gaussian_params, non_gaussian_params, default, ...
+        return getattr(self.inner, name)
+
+    def counterform(self):
+        return self.inner.counterform()
+
+    def is_cross(self):
+        return bool(self.cross_prefix)
+
+    def explicit_columns(self, params, f, B, co, nterm, gaussian):
+        """(bias (B, nterm), {gaussian name: (B, nterm)}) for the B points of `params` (scalars or (B,) arrays)"""
+        from types import SimpleNamespace
+
+        host = lambda v: v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v, float)
+        cols = {k: np.broadcast_to(host(v).reshape(-1), (B,)) if np.ndim(host(v)) else np.full(B, float(host(v))) for k, v in params.items()}
+        fB = np.broadcast_to(host(f).reshape(-1)[:B] if np.ndim(host(f)) else np.full(B, float(host(f))), (B,))
+        pco = SimpleNamespace(**{k: getattr(co, k) for k in ("kmA", "krA", "ndA", "kmB", "krB", "ndB", "counterform", "with_NNLO")}, No=1)
+        bias = np.zeros((B, nterm))
+        table = {g: np.zeros((B, nterm)) for g in gaussian}
+        mine = set(self.inner.gaussian_params())
+        for i in range(B):
+            p = {k: float(v[i]) for k, v in cols.items()}
+            bird = _UnitBird(pco, float(fB[i]), nterm)
+            bias[i] = np.asarray(self.inner.reduce_Plk(bird, p).sum(), float).reshape(-1)
+            if gaussian:
+                want = [g for g in gaussian if g in mine]
+                full = dict(self.inner.default(), **p) if hasattr(self.inner, "default") else p
+                tab = self.inner.reduce_Plk_gaussian_table(bird, full, requires=want) if want else {}
+                for g, arr in tab.items():
+                    if g in table:
+                        table[g][i] = np.asarray(arr, float).reshape(-1)
+        return bias, table
+
+    # ---- reference API on device birds ----
+    def reduce_Plk(self, bird, params_values_dict):
+        from .likelihood import reduce_on_device
+
+        return reduce_on_device(self, bird, params_values_dict)[0]
+
+    def reduce_Plk_gaussian_table(self, bird, params_values_dict, requires=None):
+        from .likelihood import reduce_on_device
+
+        table = reduce_on_device(self, bird, params_values_dict, want_table=True)[1]
+        return {k: v for k, v in table.items() if requires is None or k in requires}
+
+
 def find_param_basis(name: str):
+    """parambasis.py:457-465.  A class by dotted path that is not one of this package's own bases is wrapped into a
+    `ProbedBasis` when it is instantiated."""
     if name == "westcoast":
         return WestCoastBasis
     if name == "eastcoast":
         return EastCoastBasis
     module_name, class_name = name.rsplit(".", 1)
-    return getattr(importlib.import_module(module_name), class_name)
+    cls = getattr(importlib.import_module(module_name), class_name)
+    if hasattr(cls, "kernel_columns"):
+        return cls
+
+    def construct(prefix="", cross_prefix=None):
+        return ProbedBasis(cls(prefix=prefix, cross_prefix=list(cross_prefix or [])))
+
+    construct.__name__ = class_name
+    return construct

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define EFTB_ABI_VERSION 4
+#define EFTB_ABI_VERSION 5
 #define EFTB_NPAR 19 /* nuisance columns per tracer read by the bias reduction (eftb_like_constants.par_index) */
 
 typedef enum {
@@ -235,6 +235,14 @@ typedef struct {
                                  derivatives PG read.  Differs from d_row for the un-binned interpolated products,
                                  where PNG goes through PlkInterpolator (theory.py:75-106, origin inserted) and PG
                                  through a plain cubic interpolation (likelihood.py:510-513) */
+  /* custom EFT bases (parambasis.py:139-162 `EFTBasis` by dotted path, :457-465): a basis the kernel has no formulas for
+     hands its bias vector over explicitly.  mode[t] = 1: PNG of tracer t = sum_i nuis[xb_off[t] + i] * term[i] (nterm[t]
+     columns of the nuisance array, the coefficient of every term row for every point), and the derivative row of
+     Gaussian parameter g on tracer t = sum_i nuis[xg_off[g * ntracer + t] + i] * term[i] (xg_off < 0: none).  All three
+     NULL: every tracer uses the built-in West / East-coast formulas (mode 0). */
+  const int32_t* mode;        /* [ntracer] or NULL */
+  const int32_t* xb_off;      /* [ntracer] or NULL */
+  const int32_t* xg_off;      /* [ngauss][ntracer] or NULL */
 } eftb_like_constants;
 
 int eftb_like_create(const eftb_like_config*, const eftb_like_constants* host, eftb_like** out);

@@ -31,7 +31,7 @@ def test_library_exports_header_symbols():
 
 def test_abi_version_and_padding():
     lib = _lib.load()
-    assert lib.eftb_abi_version() == 4
+    assert lib.eftb_abi_version() == 5
     assert lib.eftb_padded_batch(1) == 32 and lib.eftb_padded_batch(33) == 64 and lib.eftb_padded_batch(0) == 0
 
 

@@ -567,3 +567,55 @@ def test_per_call_taper_and_mutable_term_arrays(golden2):
     assert np.allclose(_np(bird.Picc), -1.5)
     with pytest.raises(AttributeError):
         bird.PctNNLOl = np.zeros((3, 3, 3, 50))
+
+
+def test_custom_basis_by_dotted_path(chain, golden2, dr16):
+    """parambasis.py:457-465: `basis: "pkg.mod.Class"` with a plain numpy EFTBasis.  Its reductions are probed per point into
+    explicit bias columns (parambasis.ProbedBasis) and run through the same kernels: reduce_Plk, the Gaussian table and a
+    marginalised likelihood against the basis' own numpy code on the reference-pinned binned terms."""
+    import pybird_oracle as orc
+    from types import SimpleNamespace
+
+    import custom_basis
+    from eftpipe_b200 import likelihood, parambasis
+
+    cls = parambasis.find_param_basis("custom_basis.ToyBasis")
+    basis = cls(prefix="t_")
+    assert isinstance(basis, parambasis.ProbedBasis) and basis.gaussian_params() == ["t_c0", "t_e0"]
+    binned, co = chain["binned"], chain["co"]
+    B = binned.B
+    rng = np.random.default_rng(3)
+    params = {"t_b1": 2.0 + 0.1 * rng.standard_normal(B), "t_s": 0.3 + 0.1 * rng.standard_normal(B), "t_c0": rng.standard_normal(B),
+              "t_e0": 0.2}
+    got = _np(basis.reduce_Plk(binned, params).sum())
+    table = basis.reduce_Plk_gaussian_table(binned, params)
+    assert set(table) == {"t_c0", "t_e0"}
+    inner = custom_basis.ToyBasis(prefix="t_")
+    f = _np(chain["bird"]._f)
+    terms = {n: golden2["bin_" + n] for n in ("P11l", "Pctl", "Ploopl", "Pstl", "Picc")}
+    nk = terms["P11l"].shape[-1]
+    rows = np.arange(3 * nk, dtype=np.int32)
+    refs = []
+    for i in range(B):
+        nb = SimpleNamespace(co=SimpleNamespace(No=3, kmA=co.kmA, ndA=co.ndA), f=f[i], PctNNLOl=None, **{n: v[i] for n, v in terms.items()})
+        p = {k: (float(v[i]) if np.ndim(v) else v) for k, v in params.items()}
+        ref = inner.reduce_Plk(nb, p).sum()
+        assert rowmax_rel(got[i], ref) <= TOL
+        tab = inner.reduce_Plk_gaussian_table(nb, p)
+        for n in tab:
+            assert rowmax_rel(_np(table[n])[i], tab[n]) <= TOL, n
+        refs.append((inner.reduce_Plk(nb, dict(p, t_c0=0.0, t_e0=0.0)).sum().reshape(-1), np.array([tab["t_c0"].reshape(-1), tab["t_e0"].reshape(-1)])))
+    # marginalised likelihood over (c0, e0) with the custom basis in the device spec
+    minfo = likelihood.MultipoleInfo.load(dr16["NGC_LRG_P"], ls=[0, 2, 4], kmin=0.02, kmax=0.20)
+    spec = likelihood.build_spec([dict(basis=basis, co=co, nout=3 * nk, nterm=24, rows=rows, picc=binned._picc.reshape(-1))],
+                                 minfo.data_vector, golden2["lrg_invcov"], gaussian=["t_c0", "t_e0"], jeffreys=True)
+    from eftpipe_b200.engine import DeviceLikelihood
+    import torch
+
+    dl = DeviceLikelihood(spec)
+    free = {k: v for k, v in params.items() if k in ("t_b1", "t_s")}
+    nuis = likelihood.pack_nuisance(torch, [basis], free, [binned._f_bm], B, binned._T.shape[-1], spec=spec)
+    logp, status, _ = dl.eval(B, [binned._T.contiguous().reshape(3 * nk, 24, -1)], [binned._f_bm], nuis)
+    for i in range(B):
+        png, pg = refs[i]
+        assert _np(logp)[i] == pytest.approx(orc.marginalized_logp(png, pg, minfo.data_vector, golden2["lrg_invcov"], jeffreys=True), rel=1e-8)
