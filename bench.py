@@ -48,6 +48,7 @@ WORKLOAD3 = ("config3: DR16 NGC LRG x ELG x cross (cobaya/yamls/DR16_noric_LEX_.
              "(Nl=3, NFFT=256, IRresum + AP(APst) + window(accboost4,windowk0.1) + binning, ELG chained), 142 data points, 14 "
              "analytically marginalised parameters (Jeffreys); batch per GPU = config 4's shard (65536 / 8)")
 TRACERS3 = (("LRG_NGC", 0.696), ("ELG_NGC", 0.849), ("X_NGC", 0.763))
+GOLDEN3 = os.path.join(ROOT, "tests", "golden", "config3_like.npz")
 NCU_DRAM_FILE = os.path.join(ROOT, "profiles", "r2_ncu_dram.json")  # written by tools/ncu_summary.py from the committed capture
 
 
@@ -255,7 +256,20 @@ def config3_inputs(B, rank=0, fast=True):
     for pre, b1 in (("LRG_NGC_", 2.1), ("ELG_NGC_", 1.4)):
         pts[pre + "b1"] = b1 + 0.05 * rng.standard_normal(B)
         pts[pre + "c2"] = 0.7 + 0.1 * rng.standard_normal(B)
-    return tables, pts
+    golden = None
+    if rank == 0 and os.path.exists(GOLDEN3):
+        # the first points of rank 0's shard are the 32 points the UNMODIFIED reference evaluated for
+        # tests/golden/config3_like.npz: every bench line (any N, with or without the CPU leg) carries a parity check
+        g = np.load(GOLDEN3)
+        n = min(B, g["LEX_NGC.logp"].size)
+        for t in tables:
+            for k in tables[t]:
+                tables[t][k][:n] = g[f"{t}.{k}"][:n]
+        for k in pts:
+            if k != "point":
+                pts[k][:n] = g["pt." + k][:n]
+        golden = g["LEX_NGC.logp"][:n].copy()
+    return tables, pts, golden
 
 
 def nuisance_arrays(pts):
@@ -371,7 +385,7 @@ def run_reference(args):
         emit({"impl": "reference", "unavailable": "baseline/_ref (baseline/install_ref.sh) is missing and /root/reference does not exist"})
         return 0
     n = per_step * 2
-    tables, pts = config3_inputs(n, rank=0, fast=False)
+    tables, pts, _ = config3_inputs(n, rank=0, fast=False)
     t_build = reference_prepare(tables, pts)
     # mode (i): one process, BLAS on all cores; mode (ii): one single-threaded process per core
     r1, _ = reference_rate(range(3), 1, repeats=1)
@@ -417,7 +431,7 @@ def run_config3(args):
     if world > 1 and rank == 0:
         dist.barrier()
     t0 = time.time()
-    tables, pts = config3_inputs(B, rank=rank)
+    tables, pts, golden = config3_inputs(B, rank=rank)
     t_inputs = time.time() - t0
     nuis = nuisance_arrays(pts)
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device="cuda")
@@ -566,7 +580,7 @@ def run_config3(args):
             "launches_per_step": nlaunch, "ms_per_launch": stage_ms[top] / nlaunch,
             "peak_source": "FP64 measured live on this GPU: max(DFMA probe %.1f, cuBLAS DGEMM 8192^3 %.1f TFLOP/s); DFMA and DMMA "
                            "share one datapath (profiles/r1_pipe_probe.txt); MEASURED_PEAKS.json has no FP64 entry" % (dfma_tf, dgemm_tf),
-            "per_stage_tflops": {k: stage_fl[k] * B / (stage_ms[k] * 1e-3) / 1e12 for k in stage_ms},
+            "per_stage_tflops": {k: stage_fl[k] * B / (stage_ms[k] * 1e-3) / 1e12 for k in stage_ms if stage_fl.get(k)},
             "step_frac_of_fp64_roofline": sum(stage_fl.values()) * B / peak / 1e12 / (dev_ms / args.steps * 1e-3),
             "reference_formulation_flops_per_eval": 3 * 5.56e9}
     ws_mb = sum(dp.lib.eftb_workspace_bytes(dp.handle, B) for dp in th.plans.values()) // 2**20
@@ -592,6 +606,11 @@ def run_config3(args):
         "logp_check": {"finite": bool(torch.isfinite(logp).all()), "status_nonzero": int((status != 0).sum()),
                        "e2e_equals_device_path": bool(np.array_equal(e2e_logp, logp.cpu().numpy()))},
     }
+    if golden is not None:  # the reference's own numbers for the first points of the shard (tests/golden/config3_like.npz)
+        got = logp[: golden.size].cpu().numpy()
+        line["logp_check"]["golden_points"] = int(golden.size)
+        line["logp_check"]["max_rel_err_vs_reference_golden"] = float(np.max(np.abs(got / golden - 1.0)))
+        line["logp_check"]["gathered_equals_local"] = bool(np.array_equal(all_logp[:B].cpu().numpy(), logp.cpu().numpy()))
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         nproc = max(1, min(cores, 96))
@@ -872,7 +891,7 @@ def run_config2(args):
     flops["likelihood"] = like_flops(like.cfg)
     dfma_tf, dgemm_tf = fp64_peaks(lib, torch)
     peak = max(dfma_tf, dgemm_tf)
-    top = max(stage_ms, key=lambda k: stage_ms[k])
+    top = max((k for k in stage_ms if k in flops), key=lambda k: stage_ms[k])
     achieved = flops[top] * B / (stage_ms[top] * 1e-3) / 1e12
     traffic, capture = ncu_traffic(top, B)
     line = {
@@ -887,7 +906,7 @@ def run_config2(args):
         "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
         "roofline": {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": capture,
-                     "per_stage_tflops": {k: flops[k] * B / (stage_ms[k] * 1e-3) / 1e12 for k in stage_ms}},
+                     "per_stage_tflops": {k: flops[k] * B / (stage_ms[k] * 1e-3) / 1e12 for k in stage_ms if k in flops}},
         "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
         "logp_check": {"finite": bool(torch.isfinite(logp).all()), "status_nonzero": int((status != 0).sum()),
                        "e2e_equals_device_path": bool(np.array_equal(e2e_logp, logp.cpu().numpy()))},

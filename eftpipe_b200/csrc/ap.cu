@@ -81,8 +81,13 @@ __device__ __forceinline__ double ap_invF2(const ApArgs& a, int b) {
   return 1.0 / (Fap * Fap);
 }
 
+// Two threads per (cosmology, k) node: the live window has 4 columns (B-splines j .. j+3 of the current interval); lane
+// half h of a pair keeps columns 2h, 2h+1 - NL*NL x 2 accumulators and 2 basis polynomials instead of x 4 and 4 (the
+// one-thread form sat at 168 registers, 3 CTAs per SM, FP64 pipe 40 % busy: the serial chain load -> k' -> compare ->
+// Horner of a node had only 12 warps per SM to hide behind).  When k' crosses a knot the window shifts by one column:
+// the column that leaves is stored by the half that owns it, the one that changes sides moves with a shuffle.
 template <int NL>
-__global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
+__global__ void __launch_bounds__(GEOM_THREADS, 4) ap_geom_kernel(ApArgs a) {
   constexpr int NQ = NL * NL;
   static_assert(1 + NL * NL <= AP_TAB, "mu table too narrow");
   extern __shared__ __align__(16) double sm[];
@@ -93,10 +98,11 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
   const int tid = threadIdx.x;
   for (int i = tid; i < a.nint; i += GEOM_THREADS) knots[i] = a.knot_lo[i];
   for (int i = tid; i < a.nint * 16; i += GEOM_THREADS) bas[(i >> 4) * BAS_P + (i & 15)] = a.basis[i];
+  constexpr int NODES = GEOM_THREADS / 2;
   const int ntot = a.nb * a.Nk;
-  const int gid0 = blockIdx.x * GEOM_THREADS, gid = gid0 + tid;
-  const bool active = gid < ntot;
-  const int blA = gid0 / a.Nk, blB = (min(gid0 + GEOM_THREADS, ntot) - 1) / a.Nk, ncos = blB - blA + 1;
+  const int node0 = blockIdx.x * NODES, node = node0 + (tid >> 1), half = tid & 1;
+  const bool active = node < ntot;
+  const int blA = node0 / a.Nk, blB = (min(node0 + NODES, ntot) - 1) / a.Nk, ncos = blB - blA + 1;
   const int tile = min(a.nmu, GEOM_MU_TILE);
   // fill the rows of mu nodes [t0, t0 + nt) of this CTA's cosmologies (every thread helps, also inactive ones)
   auto fill_tile = [&](int t0, int nt) {
@@ -107,8 +113,8 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
   };
   fill_tile(0, tile);
   __syncthreads();
-  const int gidc = active ? gid : ntot - 1;  // inactive threads shadow the last node (no stores) so that they reach the barriers
-  const int bl = gidc / a.Nk, ik = gidc - bl * a.Nk, b = a.b0 + bl;
+  const int nodec = active ? node : ntot - 1;  // inactive threads shadow the last node (no stores) so that they reach the barriers
+  const int bl = nodec / a.Nk, ik = nodec - bl * a.Nk, b = a.b0 + bl;
 
   const double qperp = a.DA[b] / a.da_fid;  // pybird.py:1560
   const double kq = a.k[ik] / qperp;
@@ -136,21 +142,22 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
     if (col < APPLY_WS) Gcrow[(q / NL) * apply_kp(NL) + (q % NL) * APPLY_WS + col] = v;
     else Grow[q * a.wcap + col] = v;
   };
-  if (active) a.meta[(size_t)bl * a.Nk + ik] = make_int2(jlo, wn);
+  if (active && half == 0) a.meta[(size_t)bl * a.Nk + ik] = make_int2(jlo, wn);
   // k'(mu) is monotone, so the live window is only ever moved in the direction jfirst -> jlast (a k' that dips back
   // across a knot by rounding keeps its current interval: the spline is C2, the value agrees to ~1e-14).  Every
   // column of the window is therefore retired exactly once, with a plain store: no zero-fill, no atomics.
   const bool up = jlast > jfirst, down = jlast < jfirst;
 
-  double acc[NQ][4];
+  double acc[NQ][2];
 #pragma unroll
-  for (int q = 0; q < NQ; ++q)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) acc[q][r] = 0.0;
+  for (int q = 0; q < NQ; ++q) acc[q][0] = acc[q][1] = 0.0;
   int j = jfirst;
-  double bc[16];
+  double bc[8];
+  auto load_basis = [&]() {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) bc[i] = bas[j * BAS_P + i];
+    for (int i = 0; i < 8; ++i) bc[i] = bas[j * BAS_P + half * 8 + i];
+  };
+  load_basis();
   double knot = knots[j];
 
   for (int t0 = 0; t0 < a.nmu; t0 += tile) {
@@ -171,45 +178,61 @@ __global__ void __launch_bounds__(GEOM_THREADS, 3) ap_geom_kernel(ApArgs a) {
       wL[2 * i + 1] = v.y;
     }
     const double kp = kq * wL[0];
+    // both lanes of a pair take the same branches (same node): the shuffles below see their partner
     while (up && j < jhi && kp >= knots[j + 1]) {
-      const int col = j - jlo;               // B-spline j has no support beyond this knot: retire its column
+      const unsigned m = __activemask();
+      const int col = j - jlo;               // B-spline j has no support beyond this knot: column 0 leaves the window
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        if (active) put(q, col, acc[q][0]);
-        acc[q][0] = acc[q][1]; acc[q][1] = acc[q][2]; acc[q][2] = acc[q][3]; acc[q][3] = 0.0;
+        const double other = __shfl_xor_sync(m, acc[q][0], 1);  // half 0 receives column 2 (half 1's first)
+        if (half == 0) {
+          if (active) put(q, col, acc[q][0]);
+          acc[q][0] = acc[q][1];
+          acc[q][1] = other;
+        } else {
+          acc[q][0] = acc[q][1];
+          acc[q][1] = 0.0;
+        }
       }
       ++j;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) bc[i] = bas[j * BAS_P + i];
+      load_basis();
       knot = knots[j];
     }
     while (down && j > jlo && kp < knot) {
-      const int col = j + 3 - jlo;
+      const unsigned m = __activemask();
+      const int col = j + 3 - jlo;           // column 3 leaves the window
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        if (active) put(q, col, acc[q][3]);
-        acc[q][3] = acc[q][2]; acc[q][2] = acc[q][1]; acc[q][1] = acc[q][0]; acc[q][0] = 0.0;
+        const double other = __shfl_xor_sync(m, acc[q][1], 1);  // half 1 receives column 1 (half 0's second)
+        if (half == 1) {
+          if (active) put(q, col, acc[q][1]);
+          acc[q][1] = acc[q][0];
+          acc[q][0] = other;
+        } else {
+          acc[q][1] = acc[q][0];
+          acc[q][0] = 0.0;
+        }
       }
       --j;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) bc[i] = bas[j * BAS_P + i];
+      load_basis();
       knot = knots[j];
     }
     const double x = kp - knot;
-    double bv[4];
+    double bv[2];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) bv[r] = fma(fma(fma(bc[r * 4 + 3], x, bc[r * 4 + 2]), x, bc[r * 4 + 1]), x, bc[r * 4]);
+    for (int r = 0; r < 2; ++r) bv[r] = fma(fma(fma(bc[r * 4 + 3], x, bc[r * 4 + 2]), x, bc[r * 4 + 1]), x, bc[r * 4]);
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) acc[q][r] = fma(wL[1 + q], bv[r], acc[q][r]);
+      for (int r = 0; r < 2; ++r) acc[q][r] = fma(wL[1 + q], bv[r], acc[q][r]);
    }
   }
   if (!active) return;
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) put(q, j - jlo + r, acc[q][r]);
+    for (int r = 0; r < 2; ++r) put(q, j - jlo + 2 * half + r, acc[q][r]);
+  if (half) return;
   // zero padding of the compact rows: columns [wn, APPLY_WS) of every (l, l') and the K padding of every l
   for (int c = wn; c < APPLY_WS; ++c)
 #pragma unroll
@@ -364,7 +387,7 @@ int ap_chunk(const eftb_config& c, int B) {
 
 template <int NL>
 int run(ApArgs a, int B, cudaStream_t s, int phase) {
-  const int geom_cos = (GEOM_THREADS - 2 + a.Nk) / a.Nk + 1;  // cosmologies a CTA's GEOM_THREADS consecutive (b, k) nodes can touch
+  const int geom_cos = (GEOM_THREADS / 2 - 2 + a.Nk) / a.Nk + 1;  // cosmologies a CTA's GEOM_THREADS / 2 consecutive (b, k) nodes can touch
   const int mu_tile = a.nmu < GEOM_MU_TILE ? a.nmu : GEOM_MU_TILE;
   const size_t smem_g = sizeof(double) * (a.nint + (size_t)a.nint * BAS_P + (size_t)geom_cos * mu_tile * AP_TAB);
   const size_t smem_a = sizeof(double) * (coef_stride(NL, a.nterm, a.Nk) + APPLY_SLACK + (size_t)a.Nk * NL * apply_kp(NL)) + sizeof(int2) * a.Nk + 16;
@@ -380,7 +403,7 @@ int run(ApArgs a, int B, cudaStream_t s, int phase) {
   for (int b0 = 0; b0 < B; b0 += chunk) {
     a.b0 = b0;
     a.nb = B - b0 < chunk ? B - b0 : chunk;
-    const int nthreads = a.nb * a.Nk;
+    const int nthreads = a.nb * a.Nk * 2;  // two lanes per node
     if (phase & EFTB_PHASE_FIRST) {
       ap_geom_kernel<NL><<<(nthreads + GEOM_THREADS - 1) / GEOM_THREADS, GEOM_THREADS, smem_g, s>>>(a);
       EFTB_LAUNCH_CHECK();

@@ -4,6 +4,7 @@
   python tools/ncu_summary.py full gpurun_out/prof_r1.ncu-rep profiles/r1_top_kernels.txt
   python tools/ncu_summary.py dram profiles/r2_ncu_dram.json BATCH rep1.ncu-rep [rep2.ncu-rep ...]
   python tools/ncu_summary.py sass eftpipe_b200/libeftb200.so profiles/r2_sass_summary.txt
+  python tools/ncu_summary.py source gpurun_out/r2_resum_kernel.ncu-rep profiles/r2_resum_kernel_source.txt
 """
 import collections
 import csv
@@ -149,11 +150,50 @@ def sass(lib, dst):
         out.write(f"{'ALL':52s} {tot['_total']:6d} " + " ".join(f"{tot[w]:7d}" for w in want) + "\n")
 
 
+def source(src, dst):
+    """warp-stall samples and executed-instruction mix of one kernel from the source page of an `--import-source on` capture"""
+    import re
+
+    txt = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, data = rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    si, so, ie = col["# Samples"], col["Source"], col["Instructions Executed"]
+    stalls = collections.Counter()
+    ops, ops_s = collections.Counter(), collections.Counter()
+    for r in data:
+        for h in hdr:
+            if h.startswith("stall_") and "Not Issued" not in h and r[col[h]].isdigit():
+                stalls[h[6:]] += int(r[col[h]])
+        m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)", r[so])
+        if m:
+            ops[m.group(2)] += int(r[ie])
+            ops_s[m.group(2)] += int(r[si])
+    T, TI = sum(int(r[si]) for r in data), sum(ops.values())
+    with open(dst, "w") as out:
+        out.write(f"# {rows[0][1] if len(rows[0]) > 1 else ''}\n# source page of {src}: {T} warp-stall samples, {TI} warp instructions executed\n")
+        out.write("\nstall reason (all samples)      share\n")
+        for k, v in stalls.most_common(12):
+            out.write(f"  {k:28s} {100 * v / T:5.1f}%\n")
+        out.write("\nopcode        instructions   samples\n")
+        for k, v in ops.most_common(16):
+            out.write(f"  {k:10s} {100 * v / TI:9.1f}%  {100 * ops_s[k] / T:7.1f}%\n")
+        out.write("\ntop instructions by samples (not DFMA / DMMA)\n")
+        items = sorted(((int(r[si]), n, r[so].strip()[:70], int(r[ie])) for n, r in enumerate(data) if "DFMA" not in r[so] and "DMMA" not in r[so]), reverse=True)
+        for sct, n, t, e in items[:20]:
+            out.write(f"  {100 * sct / T:5.2f}%  #{n:<6d} executed {e:>10d}  {t}\n")
+
+
 if __name__ == "__main__":
     mode = sys.argv[1]
     if mode == "dram":
         dram(sys.argv[2], sys.argv[3], *sys.argv[4:])
     elif mode == "sass":
         sass(sys.argv[2], sys.argv[3])
+    elif mode == "source":
+        source(sys.argv[2], sys.argv[3])
     else:
-        {"launches": launches, "full": full}[mode](sys.argv[2], sys.argv[3])
+        if mode == "full" and len(sys.argv) > 4:
+            full(sys.argv[2], sys.argv[3], max_ids=int(sys.argv[4]))
+        else:
+            {"launches": launches, "full": full}[mode](sys.argv[2], sys.argv[3])
