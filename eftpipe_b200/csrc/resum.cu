@@ -47,6 +47,7 @@ struct ResumArgs {
   int nslot[3];     // canonical slots of l': 0 = (X, v = l'), 1 + v = (Y, v); nslot = 1 + number of Y orders used
   int nslots;       // every non-zero polynomial as (l', canonical slot)
   int mma;          // 1: row contraction of the a = 1 half on DMMA (resum_body_mma), 0: scalar sweep (resum_body)
+  int mix;          // CTA order: 0 = all a = 1 halves, then all a = 0 halves; k > 0 = one a = 0 CTA after every k a = 1 CTAs
   signed char slot_lp[12], slot_s[12];
 };
 
@@ -57,6 +58,20 @@ __host__ __device__ inline int rl_pitch(int NsP) { return NsP + ((4 - NsP % 16) 
 
 // accumulators of one (l, k) output column: IA = 0 (linear terms, Q_0, contracted with C11) keeps one sum per l';
 // IA = 1 (Q_1) keeps Cct per l', the 12 loop rows and, with NNLO, CctNNLO per l'
+// which cosmology / half a CTA works on.  mix = 0: blocks [0, B) are the a = 1 halves, [B, 2B) the a = 0 halves (the block
+// scheduler hands out the heavier halves first and the light ones fill the tail).  mix = k: the halves alternate in groups -
+// k a = 1 CTAs, then the a = 0 CTAs of the same cosmologies - so that every SM holds both kinds at once: the a = 0 half is
+// latency bound (barriers, short DMMA chains) and leaves FP64-pipe time that the Horner sweeps of the a = 1 half can use.
+__device__ __forceinline__ void rs_block(const int B, const int mix, int& b, int& half) {
+  const int i = blockIdx.x;
+  if (mix <= 0) { half = i >= B; b = half ? i - B : i; return; }
+  const int per = 2 * mix, g = i / per, r = i - g * per;
+  const int base = g * mix, n = min(mix, B - base);  // the last group may be short
+  half = r >= n;
+  b = base + (half ? r - n : r);
+  if (r >= 2 * n) { b = -1; }  // padding blocks of a short last group
+}
+
 template <int NL, bool NNLO, int IA>
 struct Accum {
   double lin[NL], loop[IA ? 12 : 1], nnlo[(IA && NNLO) ? NL : 1];
@@ -195,7 +210,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // one CTA = one cosmology and one a in {0, 1}; 3 CTAs per SM (a single warp cannot issue DFMAs at the full pipe
 // rate, it takes 3-4 warps per scheduler)
 template <int NL, int NIR, bool NNLO, int IA>
-__device__ __forceinline__ void resum_body(const ResumArgs& a) {
+__device__ __forceinline__ void resum_body(const ResumArgs& a, const int b) {
   extern __shared__ __align__(16) double sm[];
   constexpr int NQH = NL * NL * NIR * RS_SLOTS;  // this a's half of the expanded Q table
   constexpr int qls = NL * NIR * RS_SLOTS;  // Q table of one l
@@ -203,7 +218,7 @@ __device__ __forceinline__ void resum_body(const ResumArgs& a) {
   double* Xs = Qs + NQH;                 // [NsP]
   double* Ys = Xs + a.NsP;               // [NsP]
   double* Cs = Ys + a.NsP;               // [NL][nrow][NsP]
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const size_t Bp = a.Bp;
   const int nrow = IA ? a.ncr - 1 : 1, row0 = IA ? 1 : 0;
 
@@ -301,7 +316,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // n columns: 0..11 the loop rows, 12 + l' the Cct row of l' (zero for the other l', so the Cct sums stay separate per l'),
 // 16 + l' CctNNLO.  The columns left over by the groups of 8 (129 = 16 x 8 + 1) take the scalar sweep, one warp each.
 template <int NL, int NIR, bool NNLO>
-__device__ __forceinline__ void resum_body_mma(const ResumArgs& a) {
+__device__ __forceinline__ void resum_body_mma(const ResumArgs& a, const int b) {
   extern __shared__ __align__(16) double sm[];
   constexpr int NQL = NL * NIR * RS_SLOTS, qls = NQL;  // Q table of one l
   constexpr int NT = NNLO ? 3 : 2;
@@ -311,7 +326,7 @@ __device__ __forceinline__ void resum_body_mma(const ResumArgs& a) {
   double* Ys = Xs + NsP;           // [NsP]
   double* Cs = Ys + NsP;           // [NL][nrow][CP]
   uint64_t* bar = reinterpret_cast<uint64_t*>(Cs + (size_t)NL * nrow * CP);
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const size_t Bp = a.Bp;
   for (int s = tid; s < NsP; s += RS_THREADS) {
     const bool ok = s < a.Ns;
@@ -450,7 +465,7 @@ __device__ __forceinline__ void resum_body_mma(const ResumArgs& a) {
 // NIR/8 n8-tiles of p, K = s in steps of 4.  Fragment layout of mma.m8n8k4.f64: a = A[lane>>2][lane&3],
 // b = B[lane&3][lane>>2], c = C[lane>>2][2(lane&3) + {0,1}].
 template <int NL, int NIR>
-__device__ __forceinline__ void resum_linear_body(const ResumArgs& a) {
+__device__ __forceinline__ void resum_linear_body(const ResumArgs& a, const int b) {
   extern __shared__ __align__(16) double sm[];
   constexpr int NT = NIR / 8;
   const int NsP = a.NsP, pitch = rl_pitch(NsP), KP = a.KPAD;
@@ -459,7 +474,7 @@ __device__ __forceinline__ void resum_linear_body(const ResumArgs& a) {
   double* k2p = base + 2 * NL * NsP;           // [KP][NIR]      k^{2(p+1)}
   double* part = k2p + KP * NIR;               // [nslots][NL][KP] per-slot partial sums (fixed summation order)
   double* Qs = part + a.nslots * NL * KP;      // [NL][NL][NIR][4]  Q_0(f)
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t Bp = a.Bp;
 
   {
@@ -565,17 +580,20 @@ __device__ __forceinline__ void resum_linear_body(const ResumArgs& a) {
   }
 }
 
-// grid (B, 2): blockIdx.y = 0 runs the heavier a = 1 half (issued first), blockIdx.y = 1 the a = 0 half that fills the tail
+// one CTA = one cosmology and one half (a = 1: counterterm + loop rows, a = 0: linear terms); order of the CTAs: rs_block
 template <int NL, int NIR, bool NNLO, int MINB>
 __global__ void __launch_bounds__(RS_THREADS, MINB * 128 / RS_THREADS) resum_kernel(ResumArgs a) {
+  int b, half;
+  rs_block(a.B, a.mix, b, half);
+  if (b < 0) return;
 #ifdef EFTB_TIMING_ONLY_HALF  // timing builds only (-DEFTB_TIMING_ONLY_HALF=0|1, wrong results): one half alone, same launch
-  if ((int)blockIdx.y != EFTB_TIMING_ONLY_HALF) return;
+  if (half != EFTB_TIMING_ONLY_HALF) return;
 #endif
-  if (blockIdx.y == 0) {
-    if (a.mma) resum_body_mma<NL, NIR, NNLO>(a);
-    else resum_body<NL, NIR, NNLO, 1>(a);
+  if (half == 0) {
+    if (a.mma) resum_body_mma<NL, NIR, NNLO>(a, b);
+    else resum_body<NL, NIR, NNLO, 1>(a, b);
   } else {
-    resum_linear_body<NL, NIR>(a);
+    resum_linear_body<NL, NIR>(a, b);
   }
 }
 
@@ -617,8 +635,12 @@ int run(ResumArgs a, cudaStream_t s, int phase) {
   static const int minb = getenv("EFTB_RESUM_MINB") ? atoi(getenv("EFTB_RESUM_MINB")) : 4;  // tuning knob: CTAs per SM
   EFTB_SET_SMEM(conf3, (resum_kernel<NL, NIR, NNLO, 3>), smem);
   EFTB_SET_SMEM(conf4, (resum_kernel<NL, NIR, NNLO, 4>), smem);
-  if (minb == 3) resum_kernel<NL, NIR, NNLO, 3><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
-  else resum_kernel<NL, NIR, NNLO, 4><<<dim3(a.B, 2), RS_THREADS, smem, s>>>(a);
+  // CTA order (rs_block); measured at 8192 points x 3 tracers: 0 -> 6.41 ms, 1 -> 6.29, 2 -> 6.28, 4 -> 6.27, 16 -> 6.27
+  static const int mix = getenv("EFTB_RESUM_MIX") ? atoi(getenv("EFTB_RESUM_MIX")) : 4;
+  a.mix = mix;
+  const int nblk = mix <= 0 ? 2 * a.B : ((a.B + mix - 1) / mix) * 2 * mix;
+  if (minb == 3) resum_kernel<NL, NIR, NNLO, 3><<<nblk, RS_THREADS, smem, s>>>(a);
+  else resum_kernel<NL, NIR, NNLO, 4><<<nblk, RS_THREADS, smem, s>>>(a);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;
 }
