@@ -536,6 +536,54 @@ def run_config3(args):
     e2e_logp = e2e_out[0].numpy().copy()
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
 
+    # ---- the same end-to-end loop with the linear power PRODUCED ON THE DEVICE (boltzmann.EisensteinHu):
+    # per point the host hands over the three sampled cosmological parameters and the nuisance parameters; P_lin, f, DA, H
+    # of the three tracers are computed by eftb_eh_power inside the step
+    prod_ms, prod_h2d, prod_diff = None, None, None
+    if not args.no_producer:
+        from eftpipe_b200 import boltzmann, synthetic
+
+        theta = synthetic.draw_cosmologies(B, 20261018 + 3 + 1000 * rank)
+        ex = {}
+        for name, z in TRACERS3:  # the sigma8 normalisation is redshift independent: the first tracer's serves all three
+            ex[name] = boltzmann.EisensteinHu(rdrag=synthetic.RDRAG, share_sigma8_with=ex.get(TRACERS3[0][0]))
+            ex[name].initialize(zeff=z)
+        parrays = {"theta." + n: theta[:, i].copy() for i, n in enumerate(("omegam", "h", "sigma8"))}
+        parrays.update({"nuis." + k: v for k, v in nuis.items()})
+
+        def producer_device(**dv):
+            c = {}
+            for name in ex:
+                ex[name].calculate(omegam=dv["theta.omegam"], h=dv["theta.h"], sigma8=dv["theta.sigma8"])
+                c[name] = ex[name].cosmo()
+            th.calculate(c)
+            res = like.calculate({k: dv["nuis." + k] for k in nuis})
+            return res["logp"], like.device.residuals(B)
+
+        ppipe = HostPipeline(producer_device, {n: tuple(np.asarray(a).shape) for n, a in parrays.items()}, nslots=2,
+                             use_graph=graph is not None)
+        for slot in range(2):
+            for n, a in parrays.items():
+                ppipe.host_in(slot)[n].copy_(torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)))
+        for i in range(max(2, args.warmup)):
+            ppipe.submit(i % 2)
+        ppipe.join()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for i in range(args.steps):
+            ppipe.submit(i % 2)
+        ppipe.join()
+        p1.record()
+        torch.cuda.synchronize()
+        prod_ms = p0.elapsed_time(p1)
+        plogp = ppipe.wait((args.steps - 1) % 2)[0].numpy()
+        skip = 0 if golden is None else golden.size  # the golden points of rank 0 carry the reference run's own tables
+        prod_diff = float(np.max(np.abs(plogp[skip:] / logp.cpu().numpy()[skip:] - 1.0))) if B > skip else None
+        prod_h2d = ppipe.h2d_bytes
+
     # ---- max over ranks
     t = torch.tensor([dev_ms, e2e_ms, coll_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -600,6 +648,11 @@ def run_config3(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
         "collective_ms": coll_ms / args.steps,
+        "e2e_device_producer": None if prod_ms is None else {
+            "value": B * args.steps / (prod_ms * 1e-3), "unit": UNIT + " (this rank)", "h2d_bytes_per_step": prod_h2d, "d2h_bytes_per_step": d2h,
+            "what": "as e2e, but P_lin / f / DA / H of the three tracers are produced on the device by boltzmann.EisensteinHu from the "
+                    "sampled (omegam, h, sigma8): 9 doubles per point cross PCIe instead of 615",
+            "max_rel_logp_diff_vs_table_inputs": prod_diff},
         "roofline": roof, "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
         "stage_ms_per_tracer": {n: {k: round(v, 4) for k, v in d.items()} for n, d in per_tracer.items()},
         "setup_s": {"plans_and_windows": round(t_setup, 1), "synthetic_inputs": round(t_inputs, 1)},
@@ -1029,6 +1082,7 @@ def main():
     ap.add_argument("--workload", default="config3", choices=["config1", "config2", "config3", "config5"],
                     help="config3 (default) = the north-star multi-tracer likelihood, per-GPU batch = config 4's shard")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-producer", action="store_true", help="skip the e2e leg with the on-device linear-power producer")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (use with `ncu --profile-from-start off`)")

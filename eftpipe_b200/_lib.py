@@ -88,7 +88,8 @@ SIGNATURES = {
     "eftb_operator_create": (C.c_int, [_I, _I, c_double_p, C.POINTER(_VP)]),
     "eftb_operator_destroy": (None, [_VP]),
     "eftb_operator_apply": (C.c_int, [_VP, _VP, _VP, _I, _VP]),
-    "eftb_eh_power": (C.c_int, [_I, _VP, C.c_double, C.c_double, C.c_double, C.c_double, _VP, _I, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "eftb_eh_power": (C.c_int, [_I, _VP, C.c_double, C.c_double, C.c_double, C.c_double, _VP, _I, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP,
+                                _VP, _I, _VP]),
     "eftb_like_create": (C.c_int, [C.POINTER(EftbLikeConfig), C.POINTER(EftbLikeConstants), C.POINTER(_VP)]),
     "eftb_like_destroy": (None, [_VP]),
     "eftb_like_workspace_bytes": (_SZ, [_VP, _I]),

@@ -69,6 +69,8 @@ __device__ __forceinline__ double Efun(double Om, double a) { return sqrt(Om / a
 struct EhArgs {
   const double *theta, *kh, *gl_u, *gl_w;  // theta [B][3]: Om, h, sigma8; GL nodes / weights on [0, 1]
   double *pkh, *f, *DA, *H;
+  double* sig2;   // [B] variance of the un-normalised spectrum in 8 Mpc/h spheres (redshift independent)
+  int have_sig2;  // 1: read sig2 (another tracer of the same cosmologies computed it), 0: compute and store it
   int B, nk, ngl, nsig;
   double z, omega_b, ns, Tcmb;
 };
@@ -95,16 +97,23 @@ __global__ void __launch_bounds__(EH_THREADS) eh_power_kernel(EhArgs a) {
   if (tid == 0) cs = eh_setup(Om, a.omega_b / (h * h), h, a.Tcmb);
   __syncthreads();
   const EhConst c = cs;
-  // sigma8 of the un-normalised spectrum: trapezoid over ln k on logspace(-4, 2, nsig) (synthetic._sigma8_unnorm)
-  const double dl = 6.0 * M_LN10 / (a.nsig - 1);
-  double part = 0.0;
-  for (int i = tid; i < a.nsig; i += EH_THREADS) {
-    const double k = exp(-4.0 * M_LN10 + dl * i), T = eh_transfer(c, k), x = 8.0 * k;
-    const double W = 3.0 * (sin(x) - x * cos(x)) / (x * x * x);
-    const double y = k * k * k * pow(k, a.ns) * T * T * W * W / (2.0 * M_PI * M_PI);
-    part += (i == 0 || i == a.nsig - 1) ? 0.5 * y : y;
+  // sigma8 of the un-normalised spectrum: trapezoid over ln k on logspace(-4, 2, nsig) (synthetic._sigma8_unnorm).  It does
+  // not depend on the redshift: the tracers of one evaluation share it (ten times the work of the 200 output nodes)
+  double sig2;
+  if (a.have_sig2) {
+    sig2 = a.sig2[b];
+  } else {
+    const double dl = 6.0 * M_LN10 / (a.nsig - 1);
+    double part = 0.0;
+    for (int i = tid; i < a.nsig; i += EH_THREADS) {
+      const double k = exp(-4.0 * M_LN10 + dl * i), T = eh_transfer(c, k), x = 8.0 * k;
+      const double W = 3.0 * (sin(x) - x * cos(x)) / (x * x * x);
+      const double y = k * k * k * pow(k, a.ns) * T * T * W * W / (2.0 * M_PI * M_PI);
+      part += (i == 0 || i == a.nsig - 1) ? 0.5 * y : y;
+    }
+    sig2 = block_sum(part, red) * dl;
+    if (tid == 0 && a.sig2) a.sig2[b] = sig2;
   }
-  const double sig2 = block_sum(part, red) * dl;
   // growth D(a) = 2.5 Om E(a) / a * int_0^a E(x)^-3 dx with x = a t^2 (synthetic.make_batch_fast), at a = 1 / (1 + z) and a = 1
   const double az = 1.0 / (1.0 + a.z);
   double g1 = 0.0, g0 = 0.0, da = 0.0;
@@ -136,12 +145,13 @@ __global__ void __launch_bounds__(EH_THREADS) eh_power_kernel(EhArgs a) {
 
 extern "C" int eftb_eh_power(int B, const double* theta, double z, double omega_b, double ns, double Tcmb, const double* kh, int nk,
                              const double* gl_u, const double* gl_w, int ngl, int nsig, double* pkh, double* f, double* DA, double* H,
-                             void* stream) {
+                             double* sigma2, int have_sigma2, void* stream) {
   if (B < 1 || !theta || !kh || !gl_u || !gl_w || !pkh || !f || !DA || !H || nk < 1 || ngl < 1 || nsig < 2) {
     eftb_set_error("eftb_eh_power: NULL/invalid argument");
     return EFTB_ERR_ARG;
   }
-  EhArgs a{theta, kh, gl_u, gl_w, pkh, f, DA, H, B, nk, ngl, nsig, z, omega_b, ns, Tcmb};
+  if (have_sigma2 && !sigma2) { eftb_set_error("eftb_eh_power: have_sigma2 without sigma2"); return EFTB_ERR_ARG; }
+  EhArgs a{theta, kh, gl_u, gl_w, pkh, f, DA, H, sigma2, have_sigma2, B, nk, ngl, nsig, z, omega_b, ns, Tcmb};
   eh_power_kernel<<<B, EH_THREADS, 0, (cudaStream_t)stream>>>(a);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;

@@ -194,10 +194,12 @@ int eftb_operator_apply(const eftb_operator*, const double* X, double* C, int N,
  * matching growth rate f, angular distance DA (in c / H0) and H / H0 - the same model as eftpipe_b200/synthetic.py.
  * theta: [B][3] = (Omega_m, h, sigma8) point-major; kh: [nk] wavenumbers in h / Mpc; gl_u / gl_w: Gauss-Legendre nodes and
  * weights on [0, 1] (ngl of them) for the growth and distance integrals; nsig: nodes of the sigma8 quadrature on
- * logspace(-4, 2).  Outputs: pkh [B][nk] (point-major, what eftb_eval_terms takes), f, DA, H [B]. */
+ * logspace(-4, 2).  Outputs: pkh [B][nk] (point-major, what eftb_eval_terms takes), f, DA, H [B].
+ * sigma2 [B] (optional): the variance of the un-normalised spectrum - redshift independent, ten times the work of the nk
+ * output nodes.  have_sigma2 = 0: computed and stored there; 1: read from there (the tracers of one evaluation share it). */
 int eftb_eh_power(int B, const double* theta, double z, double omega_b, double ns, double Tcmb, const double* kh, int nk,
                   const double* gl_u, const double* gl_w, int ngl, int nsig, double* pkh, double* f, double* DA, double* H,
-                  void* stream);
+                  double* sigma2, int have_sigma2, void* stream);
 
 /* ---- likelihood (parambasis.py:42-136,:249-316; likelihood.py:483-594; marginal.py:79-196) ------- */
 typedef struct {

@@ -116,3 +116,33 @@ def test_sampled_cosmology_through_cobaya(tmp_path):
     point["sigma8"] = point["sigma8"] * 1.01
     model.logposterior(point)
     assert [c.n_computed for c in kernels] == [n + 1 for n in n0]
+
+
+def test_shared_sigma8_between_tracers():
+    """the sigma8 normalisation integral is redshift independent: a second tracer's producer reuses the first one's when it
+    was just evaluated on the very same parameter tensors - and only then"""
+    import torch
+
+    from eftpipe_b200 import boltzmann, synthetic
+
+    theta = synthetic.draw_cosmologies(40, 3)
+    dev = [torch.as_tensor(theta[:, i].copy(), device="cuda") for i in range(3)]
+    a = boltzmann.EisensteinHu()
+    b = boltzmann.EisensteinHu(share_sigma8_with=a)
+    ref = boltzmann.EisensteinHu()
+    a.initialize(zeff=0.696)
+    b.initialize(zeff=0.849)
+    ref.initialize(zeff=0.849)
+    kw = dict(omegam=dev[0], h=dev[1], sigma8=dev[2])
+    a.calculate(**kw)
+    b.calculate(**kw)
+    ref.calculate(**kw)
+    assert b._sig2 is a._sig2                                   # reused
+    assert torch.equal(b.cosmo()["pkh"], ref.cosmo()["pkh"]) and torch.equal(b.cosmo()["f"], ref.cosmo()["f"])
+    b.calculate(**kw)                                           # the primary was not re-evaluated since: no stale reuse
+    assert b._sig2 is not a._sig2 and torch.equal(b.cosmo()["pkh"], ref.cosmo()["pkh"])
+    other = dict(kw, sigma8=dev[2] * 1.1)                       # different tensors: no reuse
+    a.calculate(**kw)
+    b.calculate(**other)
+    assert b._sig2 is not a._sig2
+    np.testing.assert_allclose(_np(b.cosmo()["pkh"]), 1.21 * _np(ref.cosmo()["pkh"]), rtol=1e-13)
