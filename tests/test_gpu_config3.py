@@ -283,3 +283,47 @@ def test_wide_marginalisation_and_two_operand_form(golden3, monkeypatch):
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "two-operand ok" in out.stdout, out.stderr[-2000:]
     assert np.isfinite(lp_one).all()
+
+
+def test_nnlo_likelihood_through_theory_and_likelihood():
+    """with_NNLO=True end to end (round 1 dropped the NNLO counterterm silently at the last step): EFTLSS tracer with
+    `with_NNLO`, marginalisation over cr4 / cr6 next to the usual parameters, against marginal.py restated on vectors built
+    from the REFERENCE's binned NNLO terms (tests/golden/nnlo_chain.npz) by the reference-pinned oracle reductions."""
+    import pybird_oracle as orc
+    from eftpipe_b200 import likelihood, theory
+
+    g = dict(np.load(os.path.join(GOLDEN, "nnlo_chain.npz")))
+    g2 = np.load(os.path.join(GOLDEN, "config2_chain.npz"))
+    apk = json.loads(str(g["ap"]))
+    kout = g["kout"]
+    nk = kout.size
+    tracers = {"LRG": dict(prefix="", z=float(g["z"]), nd=4.5e-5, km=0.7, kr=0.25, with_NNLO=True, with_IRresum=True, with_APeffect=True,
+                           APeffect=dict(rdrag_AP=147.66, h_AP=0.6777, **apk), with_window="helpers.MatrixWindow",
+                           window=dict(matrix=g2["Weff_LRG"]))}
+    rng = np.random.default_rng(8)
+    table = np.column_stack([kout] + [1e4 * rng.standard_normal(nk) for _ in range(3)])
+    cov = np.diag(rng.uniform(1e5, 1e6, 3 * nk))
+    names = ("b3", "cct", "cr1", "cr2", "cr4", "cr6", "ce0", "cequad")
+    like = likelihood.EFTLike(tracers=["LRG"], data=dict(table=table, ls=[0, 2, 4], kmin=0.0, kmax=1.0), cov=dict(matrix=cov),
+                              with_binning=True, jeffreys=False, marg={n: {"scale": 3.0} for n in names})
+    th = theory.EFTLSS(tracers).must_provide(like.get_requirements()).initialize()
+    like.initialize_with_provider(th)
+    assert sorted(like.gaussian_names) == sorted(names)
+    names = list(like.gaussian_names)  # the order of marginal.py:198-232 (the basis' parameter order)
+    th.calculate({"LRG": dict(pkh=g["plin"], f=g["f"], DA=g["DA"], H=g["H"])})
+    p = g["params"]  # b1, b2, b3, b4, cct, cr1, cr2, ce0, cemono, cequad, cr4, cr6
+    params = {"b1": p[:, 0], "b2": p[:, 1], "b4": p[:, 3], "cemono": p[:, 8]}
+    res = like.calculate(params, want_bestfit=True)
+    co = orc.Common(**json.loads(str(g["common"])))
+    sig = np.eye(len(names)) / 9.0
+    for i in range(p.shape[0]):
+        terms = {n: g["bin_" + n][i] for n in ("P11l", "Pctl", "Ploopl", "Pstl", "PctNNLOl", "Picc")}
+        png = orc.reduce_Plk(co, g["f"][i], terms, [p[i, 0], p[i, 1], 0.0, p[i, 3], 0.0, 0.0, 0.0], es=[0.0, p[i, 8], 0.0],
+                             cnnlo=(0.0, 0.0)).reshape(-1)
+        tab = orc.gaussian_table_west(co, g["f"][i], terms, p[i, 0])
+        pg = np.array([tab[n].reshape(-1) for n in names])
+        assert np.abs(pg[names.index("cr4")]).max() > 0 and np.abs(pg[names.index("cr6")]).max() > 0  # the NNLO rows are really there
+        ref, full, best = orc.marginalized_logp(png, pg, like.data_vector, like.invcov, sigma_inv=sig, return_bestfit=True)
+        assert _np(res["logp"])[i] == pytest.approx(ref, rel=1e-8)
+        got_best = np.array([_np(res["bestfit"]["marg_" + n])[i] for n in names])
+        np.testing.assert_allclose(got_best, best, rtol=1e-5, atol=1e-8)

@@ -316,3 +316,22 @@ def test_callable_priors_per_point_match_the_reference_evaluation():
     off = env["b1"] > 2.0
     assert off.any() and (~off).any()
     assert not s2[off].any() and np.allclose(s2[~off], [1 / 9.0, 0.25])
+
+
+def test_tracer_prefix_defaults_follow_the_reference():
+    """theory.py:285-291: an absent `prefix` means `<tracer>_`, also for the parents of a cross tracer (ADVICE round 1:
+    the first version read `LRG_b1` etc. as absent and evaluated with b1 = 0, without an error)"""
+    from eftpipe_b200 import theory
+
+    tr = {"LRG": dict(z=0.7, km=0.7, kr=0.25, nd=4.5e-5), "ELG": dict(z=0.85, km=0.7, kr=0.25, nd=2e-4, prefix=""),
+          "X": dict(z=0.77, cross=["LRG", "ELG"])}
+    th = theory.EFTLSS(tr)
+    assert th.build_basis("LRG").prefix == "LRG_" and th.build_basis("ELG").prefix == ""
+    x = th.build_basis("X")
+    assert x.prefix == "X_" and x.cross_prefix == ["LRG_", "ELG_"]  # an EMPTY parent prefix falls back too (theory.py:290-291)
+    assert x.non_gaussian_params()[:3] == ["LRG_b1", "LRG_b2", "LRG_b4"]
+    assert theory.tracer_prefix("A", {"prefix": "p_"}) == "p_"
+    # with_icc / provider_kwargs are reference keys (theory.py:341-344, :384-388): accepted; icc on a cross is refused at build
+    theory.EFTLSS({"A": dict(z=0.7, km=0.7, nd=1e-4, with_icc=True, icc={}, provider_kwargs={})})
+    with pytest.raises(marginal.LoggedError):
+        theory.EFTLSS({"A": dict(z=0.7, km=0.7, nd=1e-4, bogus_key=1)})
