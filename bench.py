@@ -1049,6 +1049,32 @@ def run_terms_only(args):
     lat = sorted(lat[2:])
     stage_ms = stage_times(dp, torch, d_plin, d_f, None, None, B, max(3, min(args.steps, 5)))
     flops = stage_flops(dp)
+    # parity of this very run: the first points against the oracle restatement of the reference (tests pin it to the reference)
+    terms_check = None
+    if rank == 0 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import warnings
+
+        import pybird_oracle as orc
+
+        warnings.filterwarnings("ignore")
+        kw = dict(Nl=3) if args.workload == "config1" else dict(Nl=3, kmax=0.4)
+        oco = orc.Common(**kw)
+        onl, ors = orc.NonLinear(oco, NFFT=256 if args.workload == "config1" else 512), orc.Resum(oco)
+        got = step().cpu().numpy()
+        worst = 0.0
+        for i in range(min(B, 2)):
+            ob = orc.Bird(oco, b.kin, b.plin[i], b.f[i])
+            onl.PsCf(ob)
+            orc.set_PsCfl(ob)
+            ors.Ps(ob)
+            ref = np.concatenate([ob.P11l, ob.Pctl, ob.Ploopl, ob.Pstl], axis=1)  # (Nl, 24, Nk)
+            if args.workload != "config1":
+                ref = np.einsum("bk,ltk->ltb", binm, ref)
+            scale = np.abs(ref).max(axis=-1, keepdims=True)
+            scale[scale == 0] = 1.0
+            worst = max(worst, float(np.max(np.abs(got[i] - ref) / scale)))
+        terms_check = {"points": min(B, 2), "max_rowmax_rel_err_vs_oracle": worst}
     dfma_tf, dgemm_tf = fp64_peaks(lib, torch)
     peak = max(dfma_tf, dgemm_tf)
     top = max(stage_ms, key=lambda k: stage_ms[k])
@@ -1065,7 +1091,7 @@ def run_terms_only(args):
               "latency_ms": {"device_median": ms[len(ms) // 2], "device_min": ms[0], "host_visible_median": float(np.median(lat))},
               "roofline": {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                            "traffic": None, "per_stage_tflops": {k: flops[k] * B / (stage_ms[k] * 1e-3) / 1e12 for k in stage_ms if k in flops}},
-              "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}})
+              "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "terms_check": terms_check})
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -635,8 +635,10 @@ int run(ResumArgs a, cudaStream_t s, int phase) {
   static const int minb = getenv("EFTB_RESUM_MINB") ? atoi(getenv("EFTB_RESUM_MINB")) : 4;  // tuning knob: CTAs per SM
   EFTB_SET_SMEM(conf3, (resum_kernel<NL, NIR, NNLO, 3>), smem);
   EFTB_SET_SMEM(conf4, (resum_kernel<NL, NIR, NNLO, 4>), smem);
-  // CTA order (rs_block); measured at 8192 points x 3 tracers: 0 -> 6.41 ms, 1 -> 6.29, 2 -> 6.28, 4 -> 6.27, 16 -> 6.27
-  static const int mix = getenv("EFTB_RESUM_MIX") ? atoi(getenv("EFTB_RESUM_MIX")) : 4;
+  // CTA order (rs_block); measured at 8192 points x 3 tracers: 0 -> 6.41 ms, 1 -> 6.29, 2 -> 6.28, 4 -> 6.27, 16 -> 6.27; at
+  // 1024 / 2048 points the plain order is better (0.281 / 0.556 ms against 0.315 / 0.567: the a = 0 halves fill the tail)
+  static const int mix_env = getenv("EFTB_RESUM_MIX") ? atoi(getenv("EFTB_RESUM_MIX")) : -1;
+  const int mix = mix_env >= 0 ? mix_env : (a.B >= 4096 ? 4 : 0);
   a.mix = mix;
   const int nblk = mix <= 0 ? 2 * a.B : ((a.B + mix - 1) / mix) * 2 * mix;
   if (minb == 3) resum_kernel<NL, NIR, NNLO, 3><<<nblk, RS_THREADS, smem, s>>>(a);
