@@ -25,7 +25,8 @@
 //   IR0[l,l',k] = sum_{slot,p} Q_0[l,l',p,slot] k^{2(p+1)} G_slot[k,p],   G_slot[k,p] = sum_s R_v[k,s] W_slot[p,s],
 //   W_(l',X)[p,s] = X^{p+1} C11_l',  W_(l',Y,v)[p,s] = Y X^p C11_l'
 // - per slot a (Nkr x Ns)(Ns x NIR) product with a FIXED left operand: DMMA m8n8k4 with the B fragments built on the
-// fly as base_slot[s] * X(s)^p from two small shared-memory tables (resum_linear_body).
+// fly as base_slot[s] * X(s)^p from two small shared-memory tables (resum_linear_body); the fold over p with
+// Q_0 k^{2(p+1)} is a second, small DMMA product fed straight from the C fragments of the first.
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -463,17 +464,22 @@ __device__ __forceinline__ void resum_body_mma(const ResumArgs& a, const int b) 
 
 // a = 0 half on the tensor pipe: one CTA = one cosmology; a warp task = (slot, chunk of RL_MCH m8-tiles of k) with all
 // NIR/8 n8-tiles of p, K = s in steps of 4.  Fragment layout of mma.m8n8k4.f64: a = A[lane>>2][lane&3],
-// b = B[lane&3][lane>>2], c = C[lane>>2][2(lane&3) + {0,1}].
+// b = B[lane&3][lane>>2], c = C[lane>>2][2(lane&3) + {0,1}].  The A fragments (the fixed operator, read through L1) are
+// double-buffered in registers two K-steps ahead of the DMMAs; the tasks left over by whole rounds of the warps are
+// split along K (partial sums in extra planes of `part`, added in a fixed order) so that every warp gets the same work.
+__host__ __device__ inline int rl_kpitch(int KP) { return KP + 2; }  // = 2 mod 8: conflict-free k2p columns
+__host__ __device__ inline int rl_planes(int nslots) { return nslots + RS_THREADS / 32 - 1; }
+
 template <int NL, int NIR>
 __device__ __forceinline__ void resum_linear_body(const ResumArgs& a, const int b) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int NT = NIR / 8;
-  const int NsP = a.NsP, pitch = rl_pitch(NsP), KP = a.KPAD;
+  constexpr int NT = NIR / 8, NW = RS_THREADS / 32;
+  const int NsP = a.NsP, pitch = rl_pitch(NsP), KP = a.KPAD, KPP = rl_kpitch(KP);
   double* Xpow = sm;                           // [NIR][pitch]   X(s)^p
   double* base = Xpow + NIR * pitch;           // [2][NL][NsP]   X C11_l' | Y C11_l'
-  double* k2p = base + 2 * NL * NsP;           // [KP][NIR]      k^{2(p+1)}
-  double* part = k2p + KP * NIR;               // [nslots][NL][KP] per-slot partial sums (fixed summation order)
-  double* Qs = part + a.nslots * NL * KP;      // [NL][NL][NIR][4]  Q_0(f)
+  double* k2p = base + 2 * NL * NsP;           // [NIR][KPP]     k^{2(p+1)}
+  double* part = k2p + NIR * KPP;              // [planes][NL][KP] partial sums per slot (+ K-split pieces), fixed summation order
+  double* Qs = part + rl_planes(a.nslots) * NL * KP;  // [NL][NL][NIR][4]  Q_0(f)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t Bp = a.Bp;
 
@@ -497,7 +503,7 @@ __device__ __forceinline__ void resum_linear_body(const ResumArgs& a, const int 
       const double k2 = k < a.Nkr ? a.kr2[k] : 0.0;
       double kp = k2;
 #pragma unroll
-      for (int p = 0; p < NIR; ++p) { k2p[k * NIR + p] = kp; kp *= k2; }
+      for (int p = 0; p < NIR; ++p) { k2p[p * KPP + k] = kp; kp *= k2; }
     }
     constexpr int NQH = NL * NL * NIR * RS_SLOTS;
     const double* qf = a.Qf + (size_t)b * (2 * NQH);  // a = 0 half of the expanded table
@@ -505,10 +511,21 @@ __device__ __forceinline__ void resum_linear_body(const ResumArgs& a, const int 
   }
   __syncthreads();
 
-  const int mchunks = KP / (8 * RL_MCH), ntask = a.nslots * mchunks, nks = NsP / 4;
+  const int mchunks = KP / (8 * RL_MCH), ntask = a.nslots * mchunks, nkb = NsP / 8;  // K blocks of 2 steps (8 points of s)
+  const int nfull = (ntask / NW) * NW, rem = ntask - nfull;
+  const int nsplit = (rem > 0 && NW % rem == 0) ? NW / rem : 1;  // pieces of a left-over task
   const int r = lane >> 2, c4 = lane & 3;
-  for (int task = warp; task < ntask; task += RS_THREADS / 32) {
+  const int nunit = nsplit > 1 ? nfull + NW : ntask;
+  for (int unit = warp; unit < nunit; unit += NW) {
+    int task = unit, kb0 = 0, kb1 = nkb, plane = -1;
+    if (unit >= nfull && nsplit > 1) {
+      const int u = unit - nfull, h = u % nsplit;
+      task = nfull + u / nsplit;
+      kb0 = h * nkb / nsplit; kb1 = (h + 1) * nkb / nsplit;
+      if (h > 0) plane = a.nslots + (task - nfull) * (nsplit - 1) + (h - 1);
+    }
     const int slot = task / mchunks, mh = task - slot * mchunks;
+    if (plane < 0) plane = slot;
     const int lp = a.slot_lp[slot], sc = a.slot_s[slot];
     const int v = sc == 0 ? lp : sc - 1;                       // Bessel order of this slot
     const double* bb = base + ((sc == 0 ? 0 : NL) + lp) * NsP + c4;
@@ -519,44 +536,65 @@ __device__ __forceinline__ void resum_linear_body(const ResumArgs& a, const int 
     for (int i = 0; i < RL_MCH; ++i)
 #pragma unroll
       for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-#pragma unroll 4
-    for (int ks = 0; ks < nks; ++ks) {
-      double af[RL_MCH], bf[NT];
+    auto load_a = [&](double (&af)[2][RL_MCH], const int kb) {
 #pragma unroll
-      for (int i = 0; i < RL_MCH; ++i) af[i] = __ldg(ap + (size_t)i * 8 * NsP + 4 * ks);
-      const double bs = bb[4 * ks];
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int j = 0; j < NT; ++j) bf[j] = bs * xp[j * 8 * pitch + 4 * ks];
+        for (int i = 0; i < RL_MCH; ++i) af[u][i] = __ldg(ap + (size_t)i * 8 * NsP + 8 * kb + 4 * u);
+    };
+    auto block = [&](const double (&af)[2][RL_MCH], const int kb) {
 #pragma unroll
-      for (int i = 0; i < RL_MCH; ++i)
+      for (int u = 0; u < 2; ++u) {
+        double bf[NT];
+        const double bs = bb[8 * kb + 4 * u];
 #pragma unroll
-        for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < NT; ++j) bf[j] = bs * xp[j * 8 * pitch + 8 * kb + 4 * u];
+#pragma unroll
+        for (int i = 0; i < RL_MCH; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[u][i], bf[j]);
+      }
+    };
+    double a0[2][RL_MCH], a1[2][RL_MCH];
+    int kb = kb0;
+    load_a(a0, kb);
+    for (; kb + 1 < kb1; kb += 2) {
+      load_a(a1, kb + 1);
+      block(a0, kb);
+      if (kb + 2 < kb1) load_a(a0, kb + 2);
+      block(a1, kb + 1);
     }
-    // fold Q_0[l,l',p,slot] k^{2(p+1)} over this lane's p columns, then over the 4 lanes of the row
+    if (kb < kb1) block(a0, kb);  // odd number of blocks: a0 holds the last one
+    // fold  sum_p Q_0[l,l',p,slot] k^{2(p+1)} G[k,p]  as a second DMMA product: the C fragment scaled by k^{2(p+1)} is the A
+    // fragment of K-step (j, e) for the column order p = 8j + 2(lane&3) + e (a contraction does not care about the order),
+    // B[p][n] = Q_0[l = n] for n < NL, zero beyond; C2[k][l] lands in lane (k, l/2)
+    double qb[NT][2];
+    {
+      const int n = lane >> 2;
+      const double* q = Qs + (size_t)(((n < NL ? n : 0) * NL + lp) * NIR) * RS_SLOTS + sc;
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) qb[j][e] = n < NL ? q[(j * 8 + 2 * c4 + e) * RS_SLOTS] : 0.0;
+    }
+    double acc2[RL_MCH][2];
+#pragma unroll
+    for (int i = 0; i < RL_MCH; ++i) acc2[i][0] = acc2[i][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int i = 0; i < RL_MCH; ++i) {
+          const int k = (mh * RL_MCH + i) * 8 + r;
+          const double w = k2p[(j * 8 + 2 * c4 + e) * KPP + k] * acc[i][j][e];
+          dmma884(acc2[i][0], acc2[i][1], w, qb[j][e]);
+        }
 #pragma unroll
     for (int i = 0; i < RL_MCH; ++i) {
       const int k = (mh * RL_MCH + i) * 8 + r;
-      double w[NT][2];
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const double2 kk = *reinterpret_cast<const double2*>(k2p + k * NIR + j * 8 + 2 * c4);
-        w[j][0] = kk.x * acc[i][j][0];
-        w[j][1] = kk.y * acc[i][j][1];
-      }
-#pragma unroll
-      for (int l = 0; l < NL; ++l) {
-        const double* q = Qs + (size_t)((l * NL + lp) * NIR) * RS_SLOTS + sc;
-        double sum = 0.0;
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          const int p = j * 8 + 2 * c4;
-          sum = fma(q[p * RS_SLOTS], w[j][0], sum);
-          sum = fma(q[(p + 1) * RS_SLOTS], w[j][1], sum);
-        }
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        if (c4 == 0) part[(size_t)(slot * NL + l) * KP + k] = sum;
-      }
+      if (2 * c4 < NL) part[(size_t)(plane * NL + 2 * c4) * KP + k] = acc2[i][0];
+      if (2 * c4 + 1 < NL) part[(size_t)(plane * NL + 2 * c4 + 1) * KP + k] = acc2[i][1];
     }
   }
   __syncthreads();
@@ -569,6 +607,15 @@ __device__ __forceinline__ void resum_linear_body(const ResumArgs& a, const int 
       const double val = part[(size_t)(slot * NL + l) * KP + ik];
 #pragma unroll
       for (int i = 0; i < NL; ++i) lin[i] += a.slot_lp[slot] == i ? val : 0.0;
+    }
+    if (nsplit > 1) {  // the later K pieces of the split tasks: each covers one chunk of k of one slot
+      for (int e = 0; e < rem * (nsplit - 1); ++e) {
+        const int t = nfull + e / (nsplit - 1), slot = t / mchunks, mh = t - slot * mchunks;
+        if (ik / (8 * RL_MCH) != mh) continue;
+        const double val = part[(size_t)((a.nslots + e) * NL + l) * KP + ik];
+#pragma unroll
+        for (int i = 0; i < NL; ++i) lin[i] += a.slot_lp[slot] == i ? val : 0.0;
+      }
     }
     double* out = a.T + ((size_t)(l * a.Nk + a.Nklow + ik) * a.nterm) * Bp + b;
     for (int i = 0; i < 3; ++i) {
@@ -627,8 +674,8 @@ int run(ResumArgs a, cudaStream_t s, int phase) {
   a.mma = !scalar_dots && a.NsP % RS_PASS == 0 && a.Ns % 2 == 0 &&
           ((reinterpret_cast<uintptr_t>(a.Cr) | reinterpret_cast<uintptr_t>(a.Qf)) & 15) == 0;
   size_t smem = sizeof(double) * ((size_t)NL * NL * NIR * RS_SLOTS + 2 * a.NsP + (size_t)NL * (a.ncr - 1) * (a.NsP + 4) + 2);  // + mbarrier
-  const size_t smem_lin = sizeof(double) * ((size_t)NIR * rl_pitch(a.NsP) + 2 * NL * a.NsP + (size_t)a.KPAD * NIR +
-                                            (size_t)a.nslots * NL * a.KPAD + (size_t)NL * NL * NIR * RS_SLOTS);
+  const size_t smem_lin = sizeof(double) * ((size_t)NIR * rl_pitch(a.NsP) + 2 * NL * a.NsP + (size_t)rl_kpitch(a.KPAD) * NIR +
+                                            (size_t)rl_planes(a.nslots) * NL * a.KPAD + (size_t)NL * NL * NIR * RS_SLOTS);
   if (smem_lin > smem) smem = smem_lin;
   if (smem > 200 * 1024) { eftb_set_error("resum: %zu bytes of shared memory needed", smem); return EFTB_ERR_ARG; }
   static DeviceSmem conf3, conf4;

@@ -42,6 +42,8 @@ def capture_graph(fn, warmup=2):
         out = fn()
     # kernels of this library recorded into the graph = kernels every replay launches (bench.py `gpu_launches`)
     graph.library_launches = int(lib.eftb_launch_count() - n0)
+    # the graph holds raw pointers into the plans / workspaces `fn` closes over: keep them alive as long as the graph
+    graph.keepalive = fn
     return graph, out
 
 
