@@ -53,7 +53,15 @@ struct ResumArgs {
 };
 
 constexpr int RL_MCH = 3;  // m8 tiles (k rows) per warp task of the linear-term GEMM
-constexpr int RS_PASS = 16; // s points per warp pass of the DMMA form (4 quads of the m8n8k4 K dimension); NsP is a multiple
+#ifndef EFTB_RS_MC
+#define EFTB_RS_MC 4
+#endif
+#ifndef EFTB_RS_MINB
+#define EFTB_RS_MINB 4
+#endif
+constexpr int RS_MINB = EFTB_RS_MINB;  // resident CTAs per SM the kernel is compiled for
+constexpr int RS_MC = EFTB_RS_MC;      // quads (of 4 s points, the m8n8k4 K dimension) per warp pass of the DMMA form
+constexpr int RS_PASS = 4 * RS_MC;     // s points per warp pass; NsP is a multiple of 16
 
 __host__ __device__ inline int rl_pitch(int NsP) { return NsP + ((4 - NsP % 16) + 16) % 16; }  // = 4 mod 16: conflict-free B fragments
 
@@ -94,7 +102,7 @@ __device__ __forceinline__ void horner_step(double& acc, double z, double q) {
 
 // Horner sweep of the NS polynomial slots of one (a, l, l') over the RS_C points of a chunk, then the weighted slot
 // sum  T[c] = R[l'][c] z[c] P[0][c] + Y k^2 [c] sum_v R[v][c] P[1+v][c]
-template <int NIR, int NS, int NL>
+template <int NIR, int NS, int NL, int RS_C>
 __device__ __forceinline__ void horner(const double* __restrict__ q, const double (&z)[RS_C], const double (&yk)[RS_C],
                                        const double (&Rv)[NL][RS_C], int lp, double (&T)[RS_C]) {
   double P[NS][RS_C];
@@ -379,27 +387,27 @@ __device__ __forceinline__ void resum_body_mma(const ResumArgs& a, const int b) 
 #pragma unroll
     for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
     for (int s0 = 0; s0 < NsP; s0 += RS_PASS) {
-      double Rv[NL][RS_C], z[RS_C], yk[RS_C];
+      double Rv[NL][RS_MC], z[RS_MC], yk[RS_MC];
       const double* rbase = a.Rt + (size_t)(s0 + c4) * a.Nkr + ik;
 #pragma unroll
       for (int v = 0; v < NL; ++v)
 #pragma unroll
-        for (int c = 0; c < RS_C; ++c) Rv[v][c] = __ldg(rbase + ((size_t)v * NsP + 4 * c) * a.Nkr);
+        for (int c = 0; c < RS_MC; ++c) Rv[v][c] = __ldg(rbase + ((size_t)v * NsP + 4 * c) * a.Nkr);
 #pragma unroll
-      for (int c = 0; c < RS_C; ++c) {
+      for (int c = 0; c < RS_MC; ++c) {
         z[c] = k2 * Xs[s0 + 4 * c + c4];
         yk[c] = k2 * Ys[s0 + 4 * c + c4];
       }
 #pragma unroll
       for (int lp = 0; lp < NL; ++lp) {
         const double* q = Ql + (size_t)(lp * NIR) * RS_SLOTS;
-        double T[RS_C];
+        double T[RS_MC];
         if (a.nslot[lp] > 3) horner<NIR, 4, NL>(q, z, yk, Rv, lp, T);
         else horner<NIR, 3, NL>(q, z, yk, Rv, lp, T);
         const double* cb = Cs + (size_t)lp * nrow * CP + s0;
         const bool v1 = r < 4 || r - 4 == lp, v2 = r == lp;
 #pragma unroll
-        for (int c = 0; c < RS_C; ++c) {
+        for (int c = 0; c < RS_MC; ++c) {
           const double b0 = cb[off0 + 4 * c];
           const double b1 = v1 ? cb[off1 + 4 * c] : 0.0;
           dmma884(acc[0][0], acc[0][1], T[c], b0);
@@ -441,15 +449,33 @@ __device__ __forceinline__ void resum_body_mma(const ResumArgs& a, const int b) 
       }
     }
   }
-  // left-over columns: the scalar sweep with the s-chunks spread over the lanes of one warp
-  const int nchunk = NsP / RS_C;
+  // left-over columns: one warp each, lane = one s point at a time (a light sweep: one Horner chain per slot, the 13 (14)
+  // rows read at consecutive s - conflict-free), then a shuffle reduction
   for (int t = warp; t < rem; t += RS_THREADS / 32) {
     const int task = 8 * nrg + t;
     const int l = task / a.Nkr, ik = task - l * a.Nkr;
     const double k2 = a.kr2[ik];
+    const double* Ql = Qs + (size_t)l * qls;
     Accum<NL, NNLO, 1> A;
     A.zero();
-    for (int ch = lane; ch < nchunk; ch += 32) sweep_chunk<NL, NIR, NNLO, 1>(a, Qs + (size_t)l * qls, Xs, Ys, Cs, CP, ik, k2, ch * RS_C, A);
+    for (int s = lane; s < NsP; s += 32) {
+      double Rv[NL][1], z[1], yk[1];
+#pragma unroll
+      for (int v = 0; v < NL; ++v) Rv[v][0] = __ldg(a.Rt + ((size_t)v * NsP + s) * a.Nkr + ik);
+      z[0] = k2 * Xs[s];
+      yk[0] = k2 * Ys[s];
+#pragma unroll
+      for (int lp = 0; lp < NL; ++lp) {
+        double T[1];
+        if (a.nslot[lp] > 3) horner<NIR, 4, NL>(Ql + (size_t)(lp * NIR) * RS_SLOTS, z, yk, Rv, lp, T);
+        else horner<NIR, 3, NL>(Ql + (size_t)(lp * NIR) * RS_SLOTS, z, yk, Rv, lp, T);
+        const double* crow = Cs + (size_t)lp * nrow * CP + s;
+        A.lin[lp] = fma(T[0], crow[0], A.lin[lp]);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) A.loop[i] = fma(T[0], crow[(size_t)(1 + i) * CP], A.loop[i]);
+        if (NNLO) A.nnlo[lp] = fma(T[0], crow[(size_t)13 * CP], A.nnlo[lp]);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < NL; ++i) A.lin[i] = warp_sum(A.lin[i]);
 #pragma unroll
@@ -628,7 +654,7 @@ __device__ __forceinline__ void resum_linear_body(const ResumArgs& a, const int 
 }
 
 // one CTA = one cosmology and one half (a = 1: counterterm + loop rows, a = 0: linear terms); order of the CTAs: rs_block
-template <int NL, int NIR, bool NNLO, int MINB>
+template <int NL, int NIR, bool NNLO, int MINB, bool MMA>
 __global__ void __launch_bounds__(RS_THREADS, MINB * 128 / RS_THREADS) resum_kernel(ResumArgs a) {
   int b, half;
   rs_block(a.B, a.mix, b, half);
@@ -637,7 +663,7 @@ __global__ void __launch_bounds__(RS_THREADS, MINB * 128 / RS_THREADS) resum_ker
   if (half != EFTB_TIMING_ONLY_HALF) return;
 #endif
   if (half == 0) {
-    if (a.mma) resum_body_mma<NL, NIR, NNLO>(a, b);
+    if (MMA) resum_body_mma<NL, NIR, NNLO>(a, b);
     else resum_body<NL, NIR, NNLO, 1>(a, b);
   } else {
     resum_linear_body<NL, NIR>(a, b);
@@ -678,18 +704,17 @@ int run(ResumArgs a, cudaStream_t s, int phase) {
                                             (size_t)rl_planes(a.nslots) * NL * a.KPAD + (size_t)NL * NL * NIR * RS_SLOTS);
   if (smem_lin > smem) smem = smem_lin;
   if (smem > 200 * 1024) { eftb_set_error("resum: %zu bytes of shared memory needed", smem); return EFTB_ERR_ARG; }
-  static DeviceSmem conf3, conf4;
-  static const int minb = getenv("EFTB_RESUM_MINB") ? atoi(getenv("EFTB_RESUM_MINB")) : 4;  // tuning knob: CTAs per SM
-  EFTB_SET_SMEM(conf3, (resum_kernel<NL, NIR, NNLO, 3>), smem);
-  EFTB_SET_SMEM(conf4, (resum_kernel<NL, NIR, NNLO, 4>), smem);
+  static DeviceSmem conf_mma, conf_scalar;
+  EFTB_SET_SMEM(conf_mma, (resum_kernel<NL, NIR, NNLO, RS_MINB, true>), smem);
+  EFTB_SET_SMEM(conf_scalar, (resum_kernel<NL, NIR, NNLO, RS_MINB, false>), smem);
   // CTA order (rs_block); measured at 8192 points x 3 tracers: 0 -> 6.41 ms, 1 -> 6.29, 2 -> 6.28, 4 -> 6.27, 16 -> 6.27; at
   // 1024 / 2048 points the plain order is better (0.281 / 0.556 ms against 0.315 / 0.567: the a = 0 halves fill the tail)
   static const int mix_env = getenv("EFTB_RESUM_MIX") ? atoi(getenv("EFTB_RESUM_MIX")) : -1;
   const int mix = mix_env >= 0 ? mix_env : (a.B >= 4096 ? 4 : 0);
   a.mix = mix;
   const int nblk = mix <= 0 ? 2 * a.B : ((a.B + mix - 1) / mix) * 2 * mix;
-  if (minb == 3) resum_kernel<NL, NIR, NNLO, 3><<<nblk, RS_THREADS, smem, s>>>(a);
-  else resum_kernel<NL, NIR, NNLO, 4><<<nblk, RS_THREADS, smem, s>>>(a);
+  if (a.mma) resum_kernel<NL, NIR, NNLO, RS_MINB, true><<<nblk, RS_THREADS, smem, s>>>(a);
+  else resum_kernel<NL, NIR, NNLO, RS_MINB, false><<<nblk, RS_THREADS, smem, s>>>(a);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;
 }
@@ -701,7 +726,7 @@ int run(ResumArgs a, cudaStream_t s, int phase) {
 // table qpack[d][a][l][l'][p][slot].
 int resum_pack(eftb_plan* p, const double* R, const double* q) {
   const eftb_config& c = p->cfg;
-  const int Nl = c.Nl, NIR = c.NIR, Na = c.Na, Nn = 2 * NIR * Na, NsP = eftb_round_up(c.Ns, RS_PASS);
+  const int Nl = c.Nl, NIR = c.NIR, Na = c.Na, Nn = 2 * NIR * Na, NsP = eftb_round_up(c.Ns, 16);
   if (Nl > 3 || Na != Nl || Na + 1 > RS_SLOTS || c.qdeg > 16) {
     eftb_set_error("resum: unsupported sizes Nl=%d Na=%d qdeg=%d", Nl, Na, c.qdeg);
     return EFTB_ERR_ARG;
