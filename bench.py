@@ -997,7 +997,7 @@ def run_terms_only(args):
         name = "config1: single LRG z=0.7 one-loop P0/P2/P4 + IR resummation, no AP/window, B=%d (latency)" % B
     else:
         g = P.GridConfig(Nl=3, kmax=0.4, NFFT=512)
-        binm, keff, _, _ = P.binning_matrix(g.k, np.arange(0.0025, 0.4, 0.005), accboost=1)
+        binm, keff, _, _ = P.binning_matrix(g.k, np.arange(0.0025, 0.4, 0.005), accboost=1, decimals=4)  # bin width 0.005 survives the rounding
         proj = P.compose_projection(g, binning=binm)
         proj["kout"] = keff
         host = P.build_tracer_plan(Nl=3, kmax=0.4, NFFT=512, projection=proj)
