@@ -249,3 +249,121 @@ class Window:
             bird.add_Picc(-self.icc.PSN)  # window.py:405
         if self.snapshot:
             bird.create_snapshot("window")
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Window *matrix* stage (window.py:418-577): a pre-tabulated mixing matrix between band powers instead of the
+# configuration-space multipoles.  It interpolates every term onto a fixed band grid and multiplies by the matrix - on
+# the fixed internal nodes again one fixed operator, here on (Nl * Nk) -> (n_ell_out * n_bin_out).
+class PInfo:
+    """multipoles / k range / number of bins of one side of a tabulated window matrix (window.py:418-423)"""
+
+    def __init__(self, ells, kmin, kmax, nbins):
+        self.ells, self.kmin, self.kmax, self.nbins = tuple(ells), float(kmin), float(kmax), int(nbins)
+
+    def centres(self):
+        edges = np.linspace(self.kmin, self.kmax, self.nbins + 1)
+        return 0.5 * (edges[1:] + edges[:-1])
+
+
+def to_window_matrix(matrix, inpoles: PInfo, outpoles: PInfo, ells_in, kmax_in, ells_out, kmin_out, kmax_out):
+    """Cut the (multipole, band) blocks `ells_out` x `ells_in`, bands below `kmax_in` on the input side and in
+    [kmin_out, kmax_out) on the output side, out of a flat (out, in) matrix and return them as
+    (len(ells_out), len(ells_in), nk_out, nk_in) (window.py:426-469; like the reference it keeps the order of the
+    multipoles of the file)."""
+    matrix = np.asarray(matrix, float)
+
+    def select(info, ells, lo, hi):
+        c = info.centres()
+        i0, i1 = np.searchsorted(c, lo) if lo is not None else 0, np.searchsorted(c, hi)
+        keep = np.zeros(info.nbins * len(info.ells), dtype=bool)
+        for j, ell in enumerate(info.ells):
+            if ell in ells:
+                keep[j * info.nbins + i0 : j * info.nbins + i1] = True
+        return keep
+
+    sub = matrix[np.ix_(select(outpoles, tuple(ells_out), kmin_out, kmax_out), select(inpoles, tuple(ells_in), None, kmax_in))]
+    nout, nin = sub.shape[0] // len(ells_out), sub.shape[1] // len(ells_in)
+    return sub.reshape(len(ells_out), nout, len(ells_in), nin).transpose(0, 2, 1, 3).copy()
+
+
+class PolesInfo(tuple):
+    """(nells, kstart, kend, nbin) (window.py:472-476)"""
+
+    def __new__(cls, nells, kstart, kend, nbin):
+        return super().__new__(cls, (nells, kstart, kend, nbin))
+
+    nells = property(lambda self: self[0])
+    kstart = property(lambda self: self[1])
+    kend = property(lambda self: self[2])
+    nbin = property(lambda self: self[3])
+
+
+class WindowMatrix:
+    """`eftpipe.window.WindowMatrix` (window.py:479-577): `matrix` (n_ell_out, n_ell_in, nbin_out, nbin_in); every term is
+    interpolated (cubic, extrapolating) from `co.k` onto `kavg` and contracted with it.  Same keywords, the same
+    validation errors, and the reference's hard-wired band grid (`kavg`, window.py:541-544)."""
+
+    def __init__(self, matrix, inpoles, outpoles, co=None, window_st=False, icc=None, name="pybird.WindowMatrix", snapshot=False):
+        from .pybird import common
+
+        self.matrix = np.asarray(matrix, float)
+        self.inpoles, self.outpoles = PolesInfo(*inpoles), PolesInfo(*outpoles)
+        self.co = co if co is not None else common
+        self.window_st, self.icc, self.name, self.snapshot = window_st, icc, name, snapshot
+        if self.icc:
+            raise NotImplementedError("ICC not implemented for WindowMatrix")
+        if self.matrix.shape != (self.outpoles.nells, self.inpoles.nells, self.outpoles.nbin, self.inpoles.nbin):
+            raise ValueError("matrix shape does not match meta information")
+        if self.inpoles.nells != self.co.Nl:
+            raise ValueError("input poles do not match self.co.Nl")
+        self._op = None
+
+    @classmethod
+    def load(cls, path, ells, kmin, kmax, co=None, window_st=False, icc=None, name="pybird.WindowMatrix", snapshot=False):
+        """window.py:507-538: a text matrix in the layout the reference hard-codes (in: l = 0, 2, 4 on 400 bands of
+        [0, 0.4]; out: l = 0..4 on 40 bands of [0, 0.4])"""
+        from .pybird import common
+
+        co = co if co is not None else common
+        m = to_window_matrix(np.loadtxt(path), PInfo((0, 2, 4), 0, 0.4, 400), PInfo((0, 1, 2, 3, 4), 0, 0.4, 40),
+                             ells_in=tuple(2 * i for i in range(co.Nl)), kmax_in=co.k.max(), ells_out=tuple(ells),
+                             kmin_out=kmin, kmax_out=kmax)
+        return cls(m, PolesInfo(co.Nl, 0, co.k.max(), m.shape[3]), PolesInfo(len(ells), kmin, kmax, m.shape[2]), co=co,
+                   window_st=window_st, icc=icc, name=name, snapshot=snapshot)
+
+    @property
+    def kavg(self):
+        return np.linspace(0, 0.4, 400)[:300]  # window.py:541-544 (the reference's own hard-wired grid)
+
+    def effective_matrix(self):
+        """(n_ell_out, nbin_out, Nl, Nk): interpolation onto `kavg` composed with the band matrix"""
+        from .plan import cubic_matrix
+
+        if self.matrix.shape[3] != self.kavg.size:
+            raise ValueError(f"matrix has {self.matrix.shape[3]} input bands, the band grid {self.kavg.size}")
+        return np.einsum("alkp,pn->akln", self.matrix, cubic_matrix(self.co.k, self.kavg), optimize=True)
+
+    def convolve(self, Plk):
+        """host arrays (l, ..., Nk) -> (a, ..., nbin_out) (window.py:550-558)"""
+        return np.einsum("akln,l...n->a...k", self.effective_matrix(), np.asarray(Plk, float), optimize=True)
+
+    def Window(self, bird):
+        """in place on a batched device Bird (one DMMA GEMM over the batch) or on a numpy BirdLike (window.py:560-577)"""
+        from .pybird import _TermsView, apply_node_operator
+
+        if isinstance(bird, _TermsView):
+            if self._op is None:
+                op = self.effective_matrix()
+                self._op = (np.ascontiguousarray(op.reshape(op.shape[0] * op.shape[1], -1)), op.shape[0])
+            apply_node_operator(bird, self._op[0], self._op[1], stochastic=self.window_st, cache_owner=self)
+            bird.Picc = np.zeros((self.matrix.shape[0], self.matrix.shape[2]))  # window.py:573-575: convolved, then zeroed
+        else:
+            bird.P11l, bird.Pctl, bird.Ploopl = self.convolve(bird.P11l), self.convolve(bird.Pctl), self.convolve(bird.Ploopl)
+            if bird.co.with_NNLO:
+                bird.PctNNLOl = self.convolve(bird.PctNNLOl)
+            if self.window_st:
+                bird.Pstl = self.convolve(bird.Pstl)
+            bird.Picc = np.zeros((self.matrix.shape[0], self.matrix.shape[2]))
+        if self.snapshot:
+            bird.create_snapshot("window")

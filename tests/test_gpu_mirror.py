@@ -619,3 +619,42 @@ def test_custom_basis_by_dotted_path(chain, golden2, dr16):
     for i in range(B):
         png, pg = refs[i]
         assert _np(logp)[i] == pytest.approx(orc.marginalized_logp(png, pg, minfo.data_vector, golden2["lrg_invcov"], jeffreys=True), rel=1e-8)
+
+
+def test_window_matrix_stage_on_the_device(golden2):
+    """window.py:479-577 on a batched device Bird: the band-power window matrix changes the node grid (50 nodes -> 23 bands);
+    the term arrays are set to the seeded inputs of tests/golden/make_golden_windowmatrix.py (point 0) and to twice them
+    (point 1) and compared with what the unmodified reference returned"""
+    import importlib.util
+
+    from eftpipe_b200 import pybird, window
+
+    spec = importlib.util.spec_from_file_location("mkwm", os.path.join(os.path.dirname(__file__), "golden", "make_golden_windowmatrix.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    gw = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "window_matrix.npz")))
+    co = pybird.Common(Nl=3, kmax=0.3, with_NNLO=True)
+    flat, terms = mk.inputs(co.Nl, co.Nk)
+    ells, kmin, kmax = [int(x) for x in gw["ells"]], float(gw["kmin"]), float(gw["kmax"])
+    cut = window.to_window_matrix(flat, window.PInfo((0, 2, 4), 0, 0.4, 400), window.PInfo((0, 1, 2, 3, 4), 0, 0.4, 40),
+                                  ells_in=(0, 2, 4), kmax_in=co.k.max(), ells_out=tuple(ells), kmin_out=kmin, kmax_out=kmax)
+    wm = window.WindowMatrix(cut, window.PolesInfo(co.Nl, 0, co.k.max(), cut.shape[3]), window.PolesInfo(len(ells), kmin, kmax, cut.shape[2]),
+                             co=co, window_st=True)
+    g = golden2
+    bird = pybird.Bird(g["kin"], g["plin"][:2], g["f"][:2], co=co)
+    pybird.NonLinear(load=False, save=False, co=co).PsCf(bird)
+    bird.setPsCfl()
+    for n in ("P11l", "Pctl", "Ploopl", "Pstl", "PctNNLOl"):
+        setattr(bird, n, np.stack([terms[n], 2.0 * terms[n]]))
+    wm.Window(bird)
+    for n in ("P11l", "Pctl", "Ploopl", "Pstl", "PctNNLOl"):
+        got, want = _np(getattr(bird, n)), gw["st1." + n]
+        assert got.shape == (2,) + want.shape, n
+        assert rowmax_rel(got[0], want) <= 1e-11 and rowmax_rel(got[1], 2.0 * want) <= 1e-11, n
+    assert _np(bird.Picc).shape[-2:] == gw["st1.Picc"].shape and not _np(bird.Picc).any()
+    # window_st=False cannot keep the stochastic rows on a different grid than the rest of one term array
+    bird2 = pybird.Bird(g["kin"], g["plin"][:2], g["f"][:2], co=co)
+    pybird.NonLinear(load=False, save=False, co=co).PsCf(bird2)
+    bird2.setPsCfl()
+    with pytest.raises(ValueError, match="stochastic"):
+        window.WindowMatrix(cut, wm.inpoles, wm.outpoles, co=co, window_st=False).Window(bird2)

@@ -335,3 +335,50 @@ def test_tracer_prefix_defaults_follow_the_reference():
     theory.EFTLSS({"A": dict(z=0.7, km=0.7, nd=1e-4, with_icc=True, icc={}, provider_kwargs={})})
     with pytest.raises(marginal.LoggedError):
         theory.EFTLSS({"A": dict(z=0.7, km=0.7, nd=1e-4, bogus_key=1)})
+
+
+def _window_matrix_case():
+    """seeded inputs of tests/golden/make_golden_windowmatrix.py + the reference's outputs"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("mkwm", os.path.join(os.path.dirname(__file__), "golden", "make_golden_windowmatrix.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "window_matrix.npz")))
+    assert int(g["seed"]) == mk.SEED
+    return mk, g
+
+
+def test_window_matrix_stage_against_reference_golden():
+    """window.py:418-577: the band-power window matrix (cut out of a flat file matrix, cubic interpolation onto the band grid,
+    contraction) on a numpy bird-like, against what the unmodified reference returned for the same seeded inputs"""
+    import types
+
+    from eftpipe_b200 import pybird, window
+
+    mk, g = _window_matrix_case()
+    co = pybird.Common(Nl=3, kmax=0.3, with_NNLO=True)
+    flat, terms = mk.inputs(co.Nl, co.Nk)
+    ells, kmin, kmax = [int(x) for x in g["ells"]], float(g["kmin"]), float(g["kmax"])
+    cut = window.to_window_matrix(flat, window.PInfo((0, 2, 4), 0, 0.4, 400), window.PInfo((0, 1, 2, 3, 4), 0, 0.4, 40),
+                                  ells_in=(0, 2, 4), kmax_in=co.k.max(), ells_out=tuple(ells), kmin_out=kmin, kmax_out=kmax)
+    assert cut.shape == tuple(g["cut_shape"])
+    assert np.array_equal(cut[:, :, ::4, ::25], g["cut_sub"])
+    np.testing.assert_allclose(cut.sum(axis=3), g["cut_rowsum"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(cut.sum(axis=2), g["cut_colsum"], rtol=0, atol=1e-12)
+    for st in (False, True):
+        wm = window.WindowMatrix(cut, window.PolesInfo(co.Nl, 0, co.k.max(), cut.shape[3]), window.PolesInfo(len(ells), kmin, kmax, cut.shape[2]),
+                                 co=co, window_st=st)
+        bird = types.SimpleNamespace(co=co, create_snapshot=lambda name: None, **{k: v.copy() for k, v in terms.items()})
+        wm.Window(bird)
+        for n in ("P11l", "Pctl", "Ploopl", "Pstl", "PctNNLOl", "Picc"):
+            want = g[f"st{int(st)}.{n}"]
+            assert np.shape(getattr(bird, n)) == want.shape, (st, n)
+            np.testing.assert_allclose(getattr(bird, n), want, rtol=1e-11, atol=1e-11 * np.abs(want).max(), err_msg=f"{st} {n}")
+    # the reference's validation errors (window.py:490-506)
+    with pytest.raises(ValueError, match="matrix shape"):
+        window.WindowMatrix(cut[:, :, :-1], window.PolesInfo(3, 0, 0.3, 300), window.PolesInfo(3, kmin, kmax, cut.shape[2]), co=co)
+    with pytest.raises(ValueError, match="input poles"):
+        window.WindowMatrix(cut[:, :2], window.PolesInfo(2, 0, 0.3, 300), window.PolesInfo(3, kmin, kmax, cut.shape[2]), co=co)
+    with pytest.raises(NotImplementedError):
+        window.WindowMatrix(cut, window.PolesInfo(3, 0, 0.3, 300), window.PolesInfo(3, kmin, kmax, cut.shape[2]), co=co, icc=object())
