@@ -32,7 +32,7 @@
 
 namespace {
 
-constexpr int AD_WARPS = 4;
+constexpr int AD_WARPS = 4;                  // warps per CTA (8 when the coefficient table leaves room for one CTA per SM only)
 constexpr int AD_MT = 10;                    // m-tiles: 80 rows >= 2 * 38
 constexpr int AD_NT = 4;                     // n-tiles per warp: 32 cosmologies
 constexpr int AD_KSTEP_BYTES = AD_MT * 8 * 16;  // 10 m-tiles x (2 pairs x 4 channels) complex = 1280 B
@@ -171,13 +171,14 @@ __device__ __noinline__ uint32_t antidiag_task(const double* __restrict__ cs, un
   return iter0 + (uint32_t)(d1 - d0);
 }
 
-__global__ void __launch_bounds__(AD_WARPS * 32) antidiag_kernel(AdArgs a) {
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) antidiag_kernel(AdArgs a) {
   extern __shared__ __align__(128) unsigned char smraw[];
   const int Nh = a.Nmax >> 1;
   const int nrow = 2 * (Nh + 1);
   double* cs = reinterpret_cast<double*>(smraw);                                   // [Nh+1][2][32]
   unsigned char* ring0 = smraw + (size_t)nrow * 32 * sizeof(double);               // [warps][NST][S * 1280]
-  uint64_t* bars0 = reinterpret_cast<uint64_t*>(ring0 + (size_t)AD_WARPS * AD_NST * AD_S * AD_KSTEP_BYTES);
+  uint64_t* bars0 = reinterpret_cast<uint64_t*>(ring0 + (size_t)WARPS * AD_NST * AD_S * AD_KSTEP_BYTES);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* ring = ring0 + (size_t)warp * AD_NST * AD_S * AD_KSTEP_BYTES;
   uint64_t* bars = bars0 + warp * AD_NST;
@@ -196,14 +197,14 @@ __global__ void __launch_bounds__(AD_WARPS * 32) antidiag_kernel(AdArgs a) {
       group = task / a.nb;
       if (task != task0) __syncthreads();  // every warp is done with the previous group's coefficients
       // FFTLog coefficients of this group's 32 cosmologies: rows (n, re), (n, im)
-      for (int i = tid; i < nrow * 32; i += AD_WARPS * 32) {
+      for (int i = tid; i < nrow * 32; i += WARPS * 32) {
         const int row = i >> 5, n = i & 31, idx = row >> 1;
         const double* src = (row & 1) ? a.cim : a.cre;
         cs[i] = src[(size_t)idx * a.Bp + b0 + n];
       }
       __syncthreads();
     }
-    const int bin = (task % a.nb) * AD_WARPS + warp;
+    const int bin = (task % a.nb) * WARPS + warp;
     const int d0 = a.bin_off[bin], d1 = a.bin_off[bin + 1];
     if (d0 < d1) iter0 = antidiag_task(cs, ring, bars, a.tab, a.descs, d0, d1, a.D, a.Nmax, a.Bp, b0, iter0);
   }
@@ -306,18 +307,27 @@ int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cuda
   AntidiagPack* P = p->ad;
   if (!P) { eftb_set_error("antidiag: plan has no pair table"); return EFTB_ERR_ARG; }
   const int ngroups = Bp / 32;
-  const size_t smem = (size_t)2 * (c.Nmax / 2 + 1) * 32 * sizeof(double) + (size_t)AD_WARPS * AD_NST * AD_S * AD_KSTEP_BYTES +
-                      AD_WARPS * AD_NST * sizeof(uint64_t);
+  const size_t cs_bytes = (size_t)2 * (c.Nmax / 2 + 1) * 32 * sizeof(double);
+  auto smem_for = [&](int warps) { return cs_bytes + (size_t)warps * AD_NST * AD_S * AD_KSTEP_BYTES + warps * AD_NST * sizeof(uint64_t); };
+  // two CTAs of 4 warps per SM when they fit (NFFT = 256); a longer coefficient table (NFFT = 512: 132 kB) leaves room for
+  // one CTA only, which then runs 8 warps on the same table - the kernel needs two warps per scheduler to keep the DMMA
+  // pipe fed (measured at NFFT = 512: 4 warps 16.1 ms, 0.58 of peak)
+  static const int force_w = getenv("EFTB_AD_WARPS") ? atoi(getenv("EFTB_AD_WARPS")) : 0;  // tuning knob (A/B runs)
+  int W = AD_WARPS;
+  if (2 * (smem_for(4) + 1024) > 227 * 1024 && smem_for(8) + 1024 <= 227 * 1024) W = 8;
+  if (force_w == 4 || (force_w == 8 && smem_for(8) + 1024 <= 227 * 1024)) W = force_w;
+  const size_t smem = smem_for(W);
   if (smem > 227 * 1024) { eftb_set_error("antidiag: Nmax=%d needs %zu bytes of shared memory", c.Nmax, smem); return EFTB_ERR_ARG; }
-  static DeviceSmem configured;
-  EFTB_SET_SMEM(configured, antidiag_kernel, smem);
+  static DeviceSmem configured4, configured8;
+  EFTB_SET_SMEM(configured4, antidiag_kernel<4>, smem_for(4));
+  if (W == 8) EFTB_SET_SMEM(configured8, antidiag_kernel<8>, smem_for(8));
   const int sms = eftb_sm_count();
   if (!sms) return EFTB_ERR_CUDA;
-  // resident CTAs: limited by shared memory (and to 2 per SM by registers)
-  const int per_sm = std::max(1, std::min(2, (int)((227 * 1024) / (smem + 1024))));
+  // resident CTAs: limited by shared memory (and to 2 x 4 warps per SM by registers)
+  const int per_sm = W == 8 ? 1 : std::max(1, std::min(2, (int)((227 * 1024) / (smem + 1024))));
   const int slots = sms * per_sm;
   // bins per group: the tasks should fill whole rounds of the resident CTAs; ties go to fewer, larger tasks
-  const int maxnb = std::min(16, (c.Nmax + 1 + AD_WARPS - 1) / AD_WARPS);
+  const int maxnb = std::min(16, (c.Nmax + 1 + W - 1) / W);
   int nb = 1;
   double best = -1.0;
   for (int cand = 1; cand <= maxnb; ++cand) {
@@ -330,7 +340,7 @@ int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cuda
   if (force_nb > 0) nb = std::min(force_nb, maxnb);
   const int ntasks = ngroups * nb;
   AdSchedule sc;
-  int rc = get_schedule(P, c.Nmax, nb * AD_WARPS, &sc);
+  int rc = get_schedule(P, c.Nmax, nb * W, &sc);
   if (rc) return rc;
   AdArgs a;
   const bool second = cf_set && c.row_cre_cf >= 0;  // pybird.py:1151-1160: coef_cf differs from coef_pk
@@ -338,7 +348,8 @@ int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cuda
   a.cim = F + (size_t)(second ? c.row_cim_cf : c.row_cim) * Bp;
   a.tab = P->tab; a.descs = sc.descs; a.bin_off = sc.bin_off; a.D = D; a.Nmax = c.Nmax; a.Bp = Bp;
   a.nb = nb; a.ntasks = ntasks;
-  antidiag_kernel<<<std::min(ntasks, slots), AD_WARPS * 32, smem, s>>>(a);
+  if (W == 8) antidiag_kernel<8><<<std::min(ntasks, slots), 8 * 32, smem, s>>>(a);
+  else antidiag_kernel<4><<<std::min(ntasks, slots), 4 * 32, smem, s>>>(a);
   EFTB_LAUNCH_CHECK();
   return EFTB_OK;
 }
