@@ -326,15 +326,19 @@ int launch_antidiag(const eftb_plan* p, int Bp, const double* F, double* D, cuda
   // resident CTAs: limited by shared memory (and to 2 x 4 warps per SM by registers)
   const int per_sm = W == 8 ? 1 : std::max(1, std::min(2, (int)((227 * 1024) / (smem + 1024))));
   const int slots = sms * per_sm;
-  // bins per group: the tasks should fill whole rounds of the resident CTAs; ties go to fewer, larger tasks
-  const int maxnb = std::min(16, (c.Nmax + 1 + W - 1) / W);
+  // bins per group: estimated makespan = rounds of the resident CTAs x time of one task, where a task lasts as long as its
+  // longest warp list - the average list, but never less than the longest single anti-diagonal (lists are whole
+  // anti-diagonals) - plus ~2 k-steps of task overhead; ties go to fewer, larger tasks.  One group (the
+  // B = 1 latency case) spreads over up to 64 CTAs: 0.088 -> 0.047 ms.
+  const int maxnb = std::min(64, (c.Nmax + 1 + W - 1) / W);
+  const double total_steps = (double)P->kstart[c.Nmax + 1], longest = (double)(P->kstart[c.Nmax + 1] - P->kstart[c.Nmax]);
   int nb = 1;
-  double best = -1.0;
+  double best = 1e300;
   for (int cand = 1; cand <= maxnb; ++cand) {
     const long nt = (long)ngroups * cand;
     const long rounds = (nt + slots - 1) / slots;
-    const double eff = (double)nt / (double)(rounds * slots);
-    if (eff > best + 1e-3) { best = eff; nb = cand; }
+    const double cost = (double)rounds * (std::max(total_steps / (cand * W), longest) + 2.0);
+    if (cost < best * (1.0 - 1e-3)) { best = cost; nb = cand; }
   }
   static const int force_nb = getenv("EFTB_AD_NB") ? atoi(getenv("EFTB_AD_NB")) : 0;  // tuning knob (A/B runs)
   if (force_nb > 0) nb = std::min(force_nb, maxnb);
