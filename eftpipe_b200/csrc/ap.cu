@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
     }
   }
   const double* grow0 = Gs + (size_t)(r < NL ? r : 0) * KP + c4;
-  for (int ik = warp; ik < a.Nk; ik += APPLY_THREADS / 32) {
+  // one k node alone: rows l of the m8 tile (NL of 8 used) - the fallback for nodes that cannot be paired
+  auto single = [&](const int ik) {
     const int2 mw = metas[ik];
     const double* grow = grow0 + (size_t)ik * NL * KP;
     const double* cbase = coefs + mw.x;
@@ -371,6 +372,51 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
         const size_t o = nodebase + ooff[t][h];
         if ((store >> (2 * t + h)) & 1u) a.Tout[o] = norm * acc[t][h];
         else if ((copy >> (2 * t + h)) & 1u) a.Tout[o] = a.Tin[o];
+      }
+  };
+  // Two neighbouring k nodes share one m8 tile (rows 0..NL-1: node A, rows 4..4+NL-1: node B) whenever both windows fit
+  // the compact width from the smaller of the two first B-spline indices: the coefficient (B) fragments are then common
+  // and node X reads its operator row shifted by jlo(X) - jmin columns.  Half the DMMAs and half the B-fragment loads.
+  const int pl = r & 3, pn = r >> 2;             // multipole and node-in-pair of this lane's A / C row
+  unsigned pstore = 0, pcopy = 0;
+#pragma unroll
+  for (int t = 0; t < NT_MAX; ++t)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 8 * t + 2 * c4 + h;
+      const bool valid = i < a.nterm && pl < NL;
+      const bool st = !a.ap_st && i >= 21 && i < 24;
+      if (valid && !st) pstore |= 1u << (2 * t + h);
+      if (valid && st) pcopy |= 1u << (2 * t + h);
+    }
+  const int npair = (a.Nk + 1) / 2;
+  for (int ip = warp; ip < npair; ip += APPLY_THREADS / 32) {
+    const int ikA = 2 * ip, ikB = ikA + 1;
+    if (ikB >= a.Nk) { single(ikA); continue; }
+    const int2 mA = metas[ikA], mB = metas[ikB];
+    const int jmin = min(mA.x, mB.x), shA = mA.x - jmin, shB = mB.x - jmin;
+    if (mA.y + shA > APPLY_WS || mB.y + shB > APPLY_WS) { single(ikA); single(ikB); continue; }
+    const int ikX = pn ? ikB : ikA, sh = pn ? shB : shA;
+    const double* grow = Gs + ((size_t)ikX * NL + (pl < NL ? pl : 0)) * KP;
+    const double* cbase = coefs + jmin;
+    double acc[NT_MAX][2];
+#pragma unroll
+    for (int t = 0; t < NT_MAX; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < NKS; ++s) {
+      const int kap = 4 * s + c4, lp = kap / APPLY_WS, c = kap - lp * APPLY_WS - sh;  // this node's own window column
+      const double af = (pl < NL && kap < KK && c >= 0) ? grow[lp * APPLY_WS + c] : 0.0;
+#pragma unroll
+      for (int t = 0; t < NT_MAX; ++t) dmma884(acc[t][0], acc[t][1], af, cbase[ioff[t] + boff[s]]);
+    }
+    const size_t nodebase = ((size_t)(pl * a.Nk + ikX) * a.nterm) * Bp + b;
+#pragma unroll
+    for (int t = 0; t < NT_MAX; ++t)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const size_t o = nodebase + ooff[t][h];
+        if ((pstore >> (2 * t + h)) & 1u) a.Tout[o] = norm * acc[t][h];
+        else if ((pcopy >> (2 * t + h)) & 1u) a.Tout[o] = a.Tin[o];
       }
   }
 }
