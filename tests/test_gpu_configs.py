@@ -194,3 +194,29 @@ def test_resum_scalar_fallback_agrees_with_dmma_form(tmp_path):
         a, b = outs["dmma"][name], outs["scalar"][name]
         assert np.isfinite(a).all() and a.shape == b.shape
         assert rowmax_rel(a, b) <= 1e-11, name  # same algebra, different summation order
+
+
+@pytest.mark.parametrize("kmax,NFFT", [(0.4, 256), (0.35, 512)])
+def test_ap_on_the_larger_k_grids(kmax, NFFT):
+    """AP resampling on the Nk = 84 / 74 node grids (kmax = 0.4 / 0.35) with both loop-matrix sizes: larger operator and
+    coefficient blocks per cosmology in ap_apply_kernel, the 8-warp anti-diagonal CTA (NFFT = 512), 77 / 67 resummed nodes"""
+    import torch
+
+    import pybird_oracle as orc
+    from eftpipe_b200 import engine, plan, synthetic
+
+    Om_AP, z_AP = 0.307115, 0.696
+    DA0, H0 = synthetic.angular_distance(Om_AP, z_AP), synthetic.hubble(Om_AP, z_AP)
+    batch = synthetic.make_batch(5, 0.7, seed=23, unique=5)
+    DA = DA0 * np.array([1.0, 1.06, 0.95, 1.02, 0.9])
+    H = H0 * np.array([1.0, 0.97, 1.04, 1.1, 1.0])
+    dp = engine.DevicePlan(plan.build_tracer_plan(Nl=3, kmax=kmax, NFFT=NFFT, ap=dict(DA=DA0, H=H0, APst=True)))
+    got, _ = dp.eval_terms(batch.plin, batch.f, DA, H)
+    torch.cuda.synchronize()
+    got = _np(got)
+    co = orc.Common(Nl=3, kmax=kmax)
+    assert got.shape[-1] == co.Nk and np.isfinite(got).all()
+    nl, rs = orc.NonLinear(co, NFFT=NFFT), orc.Resum(co)
+    ap = orc.APeffect(co, DA=DA0, H=H0, APst=True)
+    for i in (0, 1, 4):
+        assert rowmax_rel(got[i], _oracle_terms(orc, co, nl, rs, batch, i, ap=ap, DA=DA, H=H)) <= TOL, (kmax, NFFT, i)
