@@ -196,3 +196,49 @@ def _window(model, tracer):
     fx = np.load(refdriver.FIXTURE)
     w = W.Window(window_configspace_array=fx["win_LRG"], co=pb.Common(Nl=3), accboost=4, windowk=0.1)
     return w.Wal, w.p, pb.Common(Nl=3).k, 0.1
+
+
+@pytest.mark.gpu
+def test_every_product_of_one_tracer_against_reference(tmp_path):
+    """The reference's own regression test of the theory component (tests/regression/test_eftlss.py::test_ELG_NGC_reg): one
+    evaluation serves interpolators (plain / chained), the four (chained, binned) grid products, their Gaussian tables and
+    the derived parameters.  Same requirements, same points, compared with what the unmodified reference returned
+    (tests/golden/products_elg.npz, made by make_golden_products.py) - single points (floats, Cobaya proper)."""
+    import importlib.util
+
+    from cobaya.model import get_model
+    from cobaya.theory import Theory
+
+    spec = importlib.util.spec_from_file_location("mkprod", os.path.join(GOLDEN, "make_golden_products.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    g = dict(np.load(os.path.join(GOLDEN, "products_elg.npz")))
+    table = {k[4:]: v for k, v in g.items() if k.startswith("tab.")}
+    pts = {k[3:]: v for k, v in g.items() if k.startswith("pt.")}
+    paths = refdriver.write_dr16(os.path.join(str(tmp_path), "dr16"))
+
+    class Consumer(Theory):
+        def get_requirements(self):
+            return mk.requirements()
+
+    info = mk.build_info("eftpipe_b200", paths, table)
+    info["theory"]["consumer"] = {"class": Consumer}
+    model = get_model(info)
+    eft = model.theory["eftpipe_b200.eftlss"]
+    to_np = lambda v: v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+    for i in range(mk.B):
+        _, derived = model.loglikes({k: v[i] for k, v in pts.items()})
+        got = mk.collect(eft)
+        for key, val in got.items():
+            want = g[key] if key.endswith((".ls", ".k")) else g[key][i]
+            val = to_np(val)
+            assert val.shape == want.shape, (key, val.shape, want.shape)
+            if key.endswith(".ls"):
+                assert list(val) == list(want), key
+            elif key.endswith(".k"):
+                np.testing.assert_allclose(val, want, rtol=1e-13, err_msg=key)
+            else:
+                assert rowmax_rel(val, want) <= 1e-8, (i, key, rowmax_rel(val, want))
+        for d in ("alperp", "alpara"):
+            assert float(derived[f"{mk.TRACER}_{d}"]) == pytest.approx(float(g["derived." + d][i]), rel=1e-12), d
+        assert float(derived[mk.TRACER + "_fsigma8_z"]) == float(g["derived.fsigma8_z"][i])  # the table extractor's -1
