@@ -23,6 +23,7 @@ struct ApArgs {
   const double *coef, *Tin, *DA, *H, *k, *knot_lo, *basis, *mu, *wl;
   double *Tout, *G;  // G: dense overflow operator [nb][Nk][NQ][wcap] (columns >= APPLY_WS of wide windows only)
   double* Gc;       // compact operator [nb][Nk][NL][KP]: row (k, l) = [l'][c < APPLY_WS] zero padded - what ap_apply streams
+  double* Tpm;      // point-major results of ap_apply [nb][NL * Nk * nterm]: contiguous per cosmology, transposed afterwards
   int2* meta;       // per (b, k): first B-spline index of the window, window length
   int b0, nb;       // this launch handles cosmologies [b0, b0 + nb)
   int Bp, Nk, nterm, nmu, nint, ap_st, wcap;
@@ -335,6 +336,23 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
     }
   }
   const double* grow0 = Gs + (size_t)(r < NL ? r : 0) * KP + c4;
+  // results go to a point-major block [NL * Nk][nterm] of this cosmology: the terms 2 c4, 2 c4 + 1 of a tile are adjacent, so
+  // a lane stores 16 bytes and the four lanes of a row fill whole sectors (the batch-minor array took 3600 scattered 8-byte
+  // stores per cosmology: L1/TEX 91 % busy); ap_transpose_kernel brings them to [row][Bp] and passes the un-resampled rows through
+  double* tpm = a.Tpm + (size_t)bl * NL * a.Nk * a.nterm;
+  const bool vec2 = (a.nterm & 1) == 0;
+  auto put_terms = [&](double* node, const double (&acc)[NT_MAX][2], const unsigned flags) {
+#pragma unroll
+    for (int t = 0; t < NT_MAX; ++t) {
+      const unsigned f2 = (flags >> (2 * t)) & 3u;
+      double* o = node + 8 * t + 2 * c4;
+      if (f2 == 3u && vec2) *reinterpret_cast<double2*>(o) = make_double2(norm * acc[t][0], norm * acc[t][1]);
+      else {
+        if (f2 & 1u) o[0] = norm * acc[t][0];
+        if (f2 & 2u) o[1] = norm * acc[t][1];
+      }
+    }
+  };
   // one k node alone: rows l of the m8 tile (NL of 8 used) - the fallback for nodes that cannot be paired
   auto single = [&](const int ik) {
     const int2 mw = metas[ik];
@@ -350,7 +368,7 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
       for (int t = 0; t < NT_MAX; ++t) dmma884(acc[t][0], acc[t][1], af, cbase[ioff[t] + boff[s]]);
     }
     // C[row = r (multipole)][col = 2 c4 + h (term in tile)]
-    const size_t nodebase = ((size_t)(r * a.Nk + ik) * a.nterm) * Bp + b;
+    double* node = tpm + (size_t)(r * a.Nk + ik) * a.nterm;
     if (mw.y > APPLY_WS && r < NL) {  // strong AP distortion: the columns beyond the compact window from the dense overflow
       const double* Gk = Gb + ((size_t)ik * NQ + r * NL) * a.wcap;
 #pragma unroll
@@ -365,14 +383,7 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
               acc[t][h] = fma(__ldg(Gk + lp * a.wcap + c), __ldg(cg + (size_t)lp * lstride + c), acc[t][h]);
         }
     }
-#pragma unroll
-    for (int t = 0; t < NT_MAX; ++t)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const size_t o = nodebase + ooff[t][h];
-        if ((store >> (2 * t + h)) & 1u) a.Tout[o] = norm * acc[t][h];
-        else if ((copy >> (2 * t + h)) & 1u) a.Tout[o] = a.Tin[o];
-      }
+    put_terms(node, acc, store);
   };
   // Two neighbouring k nodes share one m8 tile (rows 0..NL-1: node A, rows 4..4+NL-1: node B) whenever both windows fit
   // the compact width from the smaller of the two first B-spline indices: the coefficient (B) fragments are then common
@@ -409,15 +420,29 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
 #pragma unroll
       for (int t = 0; t < NT_MAX; ++t) dmma884(acc[t][0], acc[t][1], af, cbase[ioff[t] + boff[s]]);
     }
-    const size_t nodebase = ((size_t)(pl * a.Nk + ikX) * a.nterm) * Bp + b;
-#pragma unroll
-    for (int t = 0; t < NT_MAX; ++t)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const size_t o = nodebase + ooff[t][h];
-        if ((pstore >> (2 * t + h)) & 1u) a.Tout[o] = norm * acc[t][h];
-        else if ((pcopy >> (2 * t + h)) & 1u) a.Tout[o] = a.Tin[o];
-      }
+    put_terms(tpm + (size_t)(pl * a.Nk + ikX) * a.nterm, acc, pstore);
+  }
+}
+
+// Tpm[nb][R] (row = (l, k, term)) -> Tout[R][Bp], columns b0 .. b0 + nb; rows of terms that are not resampled (Pstl without
+// APst, pybird.py:1618-1619) are copied from Tin instead; in the last chunk the padded lanes b >= B replicate point B - 1
+__global__ void __launch_bounds__(256) ap_transpose_kernel(ApArgs a, int R, int B) {
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;  // column block relative to b0, row block
+  const bool last = a.b0 + a.nb >= B;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = min(c0 + j, a.nb - 1), r = r0 + threadIdx.x;
+    tile[j][threadIdx.x] = r < R ? a.Tpm[(size_t)c * R + r] : 0.0;
+  }
+  __syncthreads();
+  const int ncol = last ? a.Bp - a.b0 : a.nb;  // the last chunk also fills the padding
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r >= R || c >= ncol) continue;
+    const int term = r % a.nterm;
+    const size_t o = (size_t)r * a.Bp + a.b0 + c;
+    const bool pass = !a.ap_st && term >= 21 && term < 24;
+    a.Tout[o] = pass ? a.Tin[(size_t)r * a.Bp + min(a.b0 + c, B - 1)] : tile[threadIdx.x][j];
   }
 }
 
@@ -458,6 +483,10 @@ int run(ApArgs a, int B, cudaStream_t s, int phase) {
       if (a.nterm <= 24) ap_apply_kernel<NL, 3><<<a.nb, APPLY_THREADS, smem_a, s>>>(a);
       else ap_apply_kernel<NL, 4><<<a.nb, APPLY_THREADS, smem_a, s>>>(a);
       EFTB_LAUNCH_CHECK();
+      const int R = NL * a.Nk * a.nterm;
+      const int ncol = b0 + a.nb >= B ? a.Bp - b0 : a.nb;
+      ap_transpose_kernel<<<dim3((ncol + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, s>>>(a, R, B);
+      EFTB_LAUNCH_CHECK();
     }
   }
   return EFTB_OK;
@@ -469,7 +498,9 @@ size_t ap_scratch_doubles(const eftb_plan* p, int B) {
   const eftb_config& c = p->cfg;
   const size_t chunk = ap_chunk(c, B);
   // dense overflow G | meta (int2 = 8 bytes each) | pad to 16 bytes | compact operator Gc
-  const size_t n = chunk * c.Nk * c.Nl * c.Nl * c.Nk + chunk * c.Nk + 1 + chunk * c.Nk * c.Nl * apply_kp(c.Nl);
+  // dense overflow G | meta (int2 = 8 bytes each) | pad | compact operator Gc | pad | point-major results Tpm
+  const size_t n = chunk * c.Nk * c.Nl * c.Nl * c.Nk + chunk * c.Nk + 1 + chunk * c.Nk * c.Nl * apply_kp(c.Nl) + 1 +
+                   chunk * c.Nl * c.Nk * c.nterm;
   return (n + 1) & ~(size_t)1;  // whole 16-byte units: the buffers that follow in the workspace are TMA sources too
 }
 
@@ -498,6 +529,8 @@ int launch_ap(const eftb_plan* p, int B, int Bp, const double* coef, const doubl
   {
     const size_t off = (size_t)a.nb * c.Nk * c.Nl * c.Nl * c.Nk + (size_t)a.nb * c.Nk;
     a.Gc = scratch + off + (off & 1);  // 16-byte aligned (the scratch base is): TMA bulk copies read it
+    const size_t off2 = (size_t)(a.Gc - scratch) + (size_t)a.nb * c.Nk * c.Nl * apply_kp(c.Nl);
+    a.Tpm = scratch + off2 + (off2 & 1);  // 16-byte aligned: double2 stores
   }
   if ((phase & EFTB_PHASE_SECOND) && ((reinterpret_cast<uintptr_t>(coef) | reinterpret_cast<uintptr_t>(a.Gc)) & 15)) {
     eftb_set_error("ap: the scratch / coefficient buffers must be 16-byte aligned (TMA sources)");
