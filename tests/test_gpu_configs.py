@@ -133,6 +133,33 @@ def test_large_batch_is_consistent_with_small_batches():
         np.testing.assert_array_equal(_np(small), big[sl])
 
 
+def test_batch_beyond_one_ap_chunk():
+    """12288 points are more than one launch of the AP kernels holds (the dense overflow operator is capped at 2 GB =
+    11930 cosmologies of 50 nodes): two chunks, the second one with the batch padding; points of both chunks and across
+    the chunk boundary equal the same points evaluated in batches of 32"""
+    import torch
+
+    from eftpipe_b200 import engine, plan, synthetic
+
+    Om_AP, z_AP = 0.307115, 0.696
+    DA0, H0 = synthetic.angular_distance(Om_AP, z_AP), synthetic.hubble(Om_AP, z_AP)
+    B = 12288 - 7  # ragged: the last chunk ends inside a group of 32
+    batch = synthetic.make_batch(B, 0.7, seed=6, unique=64)
+    for APst in (True, False):
+        dp = engine.DevicePlan(plan.build_tracer_plan(Nl=3, ap=dict(DA=DA0, H=H0, APst=APst)))
+        big, _ = dp.eval_terms(batch.plin, batch.f, batch.DA, batch.H)
+        torch.cuda.synchronize()
+        big = _np(big).copy()
+        assert np.isfinite(big).all()
+        for lo in (0, 11914, B - 32):
+            sl = slice(lo, lo + 32)
+            small, _ = dp.eval_terms(batch.plin[sl], batch.f[sl], batch.DA[sl], batch.H[sl])
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(_np(small), big[sl])
+        del dp, big
+        torch.cuda.empty_cache()
+
+
 def test_odd_node_count_with_nnlo():
     """kmax = 0.305 gives 65 k nodes; with NNLO (27 term rows) the per-cosmology coefficient block has an odd number of
     doubles - the TMA-staged AP kernels pad the stride.  Fused pipeline against the oracle."""
