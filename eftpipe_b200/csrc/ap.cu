@@ -276,7 +276,6 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
   int2* metas = reinterpret_cast<int2*>(coefs + coef_stride(NL, a.nterm, a.Nk) + APPLY_SLACK);  // [Nk]
   uint64_t* bar = reinterpret_cast<uint64_t*>(metas + a.Nk);
   const int bl = blockIdx.x, b = a.b0 + bl, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const size_t Bp = a.Bp;
   const double* Gb = a.G + (size_t)bl * a.Nk * NQ * a.wcap;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(bar)));
@@ -320,19 +319,16 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
     boff[s] = kap < KK ? lp * lstride + (kap - lp * APPLY_WS) : 0;
   }
   int ioff[NT_MAX];          // B operand: term 8 t + r (clamped)
-  size_t ooff[NT_MAX][2];    // C columns: term i = 8 t + 2 c4 + h  ->  i * Bp
-  unsigned store = 0, copy = 0;  // per (t, h): result stored / Pstl row passed through unchanged (no APst, pybird.py:1618-1619)
+  unsigned store = 0;  // per (t, h): result stored; the Pstl rows pass through unchanged without APst (pybird.py:1618-1619): ap_transpose_kernel
 #pragma unroll
   for (int t = 0; t < NT_MAX; ++t) {
     ioff[t] = min(8 * t + r, a.nterm - 1) * a.Nk;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int i = 8 * t + 2 * c4 + h;
-      ooff[t][h] = (size_t)i * Bp;
       const bool valid = i < a.nterm && r < NL;
       const bool st = !a.ap_st && i >= 21 && i < 24;
       if (valid && !st) store |= 1u << (2 * t + h);
-      if (valid && st) copy |= 1u << (2 * t + h);
     }
   }
   const double* grow0 = Gs + (size_t)(r < NL ? r : 0) * KP + c4;
@@ -389,7 +385,7 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
   // the compact width from the smaller of the two first B-spline indices: the coefficient (B) fragments are then common
   // and node X reads its operator row shifted by jlo(X) - jmin columns.  Half the DMMAs and half the B-fragment loads.
   const int pl = r & 3, pn = r >> 2;             // multipole and node-in-pair of this lane's A / C row
-  unsigned pstore = 0, pcopy = 0;
+  unsigned pstore = 0;
 #pragma unroll
   for (int t = 0; t < NT_MAX; ++t)
 #pragma unroll
@@ -398,7 +394,6 @@ __global__ void __launch_bounds__(APPLY_THREADS, 3) ap_apply_kernel(ApArgs a) {
       const bool valid = i < a.nterm && pl < NL;
       const bool st = !a.ap_st && i >= 21 && i < 24;
       if (valid && !st) pstore |= 1u << (2 * t + h);
-      if (valid && st) pcopy |= 1u << (2 * t + h);
     }
   const int npair = (a.Nk + 1) / 2;
   for (int ip = warp; ip < npair; ip += APPLY_THREADS / 32) {
