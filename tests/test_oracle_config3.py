@@ -173,3 +173,49 @@ def test_config3_one_point_full_chain(golden3):
         png.append(red.reshape(-1))
     # LRG / X: all three multipoles on 18 bins; ELG: chained l = 0, 2 on 17 bins
     assert rowmax_rel(np.concatenate(png), g["LEX_NGC.PNG"][i]) <= 1e-9
+
+
+def test_every_product_of_one_tracer_full_chain():
+    """the oracle's own chain (window build, binning, chained transform, reduction, Gaussian tables, interpolator) against the
+    products the unmodified reference's theory component served in one evaluation (tests/golden/products_elg.npz, modelled on
+    the reference's tests/regression/test_eftlss.py)"""
+    g = dict(np.load(os.path.join(GOLDEN, "products_elg.npz")))
+    fx = np.load(os.path.join(os.path.dirname(GOLDEN), "..", "eftpipe_b200", "data", "dr16_ngc.npz"))
+    i, T = 2, "ELG_NGC"
+    pt = {k[len("pt." + T) + 1:]: v[i] for k, v in g.items() if k.startswith("pt." + T)}
+    co = orc.Common(Nl=3, kmA=0.7, krA=0.25, ndA=2.3e-4)
+    nl, rs = orc.NonLinear(co), orc.Resum(co)
+    ap = orc.APeffect(co, Om_AP=0.307115, z_AP=0.849, APst=True)
+    Wal, p = orc.compute_Wal(fx["win_ELG"], co, Na=3, Nl=3, accboost=4)
+    Waldk = orc.mask_and_measure(Wal, p, co.k, windowk=0.1)
+    b = orc.Bird(co, np.logspace(-5, 0, 200), g["tab.pkh"][i], g["tab.f"][i], g["tab.DA"][i], g["tab.H"][i], 0.849)
+    nl.PsCf(b)
+    orc.set_PsCfl(b)
+    rs.Ps(b)
+    ap.AP(b)
+    orc.apply_window(b, Waldk, p, window_st=True)
+    plain = orc.bird_terms(b)
+    binned = orc.Binning(g["kout"], co).transform(plain)
+    b2 = pt["c2"] / np.sqrt(2.0)
+    bs = [pt["b1"], b2, pt["b3"], b2, pt["cct"], pt["cr1"], pt["cr2"]]
+    es = [pt["ce0"], 0.0, pt["cequad"]]
+    for ch in (False, True):
+        for bn in (False, True):
+            tag = f"c{int(ch)}b{int(bn)}"
+            terms = binned if bn else plain
+            cc = orc.Common(Nl=3, kmA=0.7, krA=0.25, ndA=2.3e-4)
+            if ch:
+                terms = orc.chained_transform(terms, co.Nl)
+                cc.No = 2
+            red = orc.reduce_Plk(cc, b.f, terms, bs, es=es)
+            assert rowmax_rel(red, g[f"grid_{tag}.P"][i]) <= 1e-9, tag
+            tab = orc.gaussian_table_west(cc, b.f, terms, pt["b1"])
+            for n in ("b3", "cct", "cr1", "cr2", "ce0", "cemono", "cequad"):
+                assert rowmax_rel(tab[n], g[f"gauss_{tag}.{T}_{n}"][i]) <= 1e-9, (tag, n)
+    # the interpolators are built from the un-binned products (theory.py:862-871)
+    red = orc.reduce_Plk(co, b.f, plain, bs, es=es)
+    assert rowmax_rel(orc.plk_interpolator(co.k, red)(g["kout"]), g["plk"][i]) <= 1e-9
+    cc = orc.Common(Nl=3, kmA=0.7, krA=0.25, ndA=2.3e-4)
+    cc.No = 2
+    redc = orc.reduce_Plk(cc, b.f, orc.chained_transform(plain, co.Nl), bs, es=es)
+    assert rowmax_rel(orc.plk_interpolator(co.k, redc)(g["kout"]), g["plk_chained"][i]) <= 1e-9
